@@ -1,0 +1,665 @@
+// api.cu -- the C-ABI of libbonejthickness.so (include/bonej_thickness.h) and the pipeline driver.
+//
+// One call of bjt_thickness_u8 is one LocalThicknessWrapper.processImage(ImagePlus) plus the
+// StackStatistics that ThicknessWrapper.addMapResults reads (ThicknessWrapper.java:158-196):
+//   upload -> EDT x,y,z -> ridge -> paint -> 2*sqrt/cleanup/mask/NaN/calibrate/stats -> download.
+// All device memory belongs to the context and is cached between calls; nothing here keeps a
+// caller pointer after returning.  There is no CPU path: every failure is reported, never routed.
+#include "common.cuh"
+#include "../../include/bonej_thickness.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+
+using namespace bjt;
+
+struct bjt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    char err[512] = {0};
+    std::mutex mu;
+    struct Buf { void *p = nullptr; size_t cap = 0; };
+    std::map<std::string, Buf> bufs;
+    uint32_t *h_scal = nullptr;        // pinned readback area (64 words)
+    StatsPartial *h_stats = nullptr;   // pinned
+    cudaEvent_t ev[16];
+    int paint_path = -1;
+    int64_t launches = 0;
+};
+
+static char g_err[512] = "no error";
+
+static int fail(bjt_ctx *c, int code, const char *fmt, ...) {
+    char *dst = c ? c->err : g_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(c, BJT_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define CKL()                                                                                            \
+    do {                                                                                                 \
+        cudaError_t e_ = cudaGetLastError();                                                             \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(c, BJT_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+static int ws_get(bjt_ctx *c, const char *name, size_t bytes, void **out) {
+    bjt_ctx::Buf &b = c->bufs[name];
+    if (b.cap < bytes) {
+        if (b.p) { CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+        if (bytes == 0) bytes = 256;
+        CK(cudaMalloc(&b.p, bytes));
+        b.cap = bytes;
+    }
+    *out = b.p;
+    return BJT_OK;
+}
+#define WS(name, bytes, ptr)                                             \
+    do {                                                                 \
+        int rc_ = ws_get(c, name, (bytes), (void **)&(ptr));             \
+        if (rc_) return rc_;                                             \
+    } while (0)
+
+static int check_dims(bjt_ctx *c, int w, int h, int d) {
+    if (!c) return fail(nullptr, BJT_E_ARG, "null context");
+    if (w <= 0 || h <= 0 || d <= 0) return fail(c, BJT_E_ARG, "non-positive volume size %d x %d x %d", w, h, d);
+    if (w > MAX_EXTENT || h > MAX_EXTENT || d > MAX_EXTENT)
+        return fail(c, BJT_E_ARG, "volume extent above %d is not supported", MAX_EXTENT);
+    return BJT_OK;
+}
+
+extern "C" {
+
+int bjt_create(bjt_ctx **out, int device) {
+    if (!out) return fail(nullptr, BJT_E_ARG, "null output pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, BJT_E_CUDA, "no CUDA device: %s (libbonejthickness has no CPU fallback)",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= ndev) return fail(nullptr, BJT_E_ARG, "device %d out of range (%d devices)", device, ndev);
+    bjt_ctx *c = new bjt_ctx();
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost(&c->h_scal, 64 * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMallocHost(&c->h_stats, sizeof(StatsPartial)) != cudaSuccess) {
+        fail(nullptr, BJT_E_CUDA, "context setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return BJT_E_CUDA;
+    }
+    c->own_stream = true;
+    for (auto &ev : c->ev) cudaEventCreate(&ev);
+    *out = c;
+    return BJT_OK;
+}
+
+int bjt_release_workspace(bjt_ctx *c) {
+    if (!c) return BJT_E_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &kv : c->bufs) if (kv.second.p) cudaFree(kv.second.p);
+    c->bufs.clear();
+    return BJT_OK;
+}
+
+void bjt_destroy(bjt_ctx *c) {
+    if (!c) return;
+    bjt_release_workspace(c);
+    for (auto &ev : c->ev) cudaEventDestroy(ev);
+    if (c->h_scal) cudaFreeHost(c->h_scal);
+    if (c->h_stats) cudaFreeHost(c->h_stats);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *bjt_last_error(const bjt_ctx *c) { return c ? c->err : g_err; }
+
+int bjt_set_stream(bjt_ctx *c, void *stream) {
+    if (!c) return BJT_E_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    c->stream = (cudaStream_t)stream;
+    c->own_stream = false;
+    return BJT_OK;
+}
+
+int bjt_set_paint_path(bjt_ctx *c, int path) {
+    if (!c || path < -1 || path > 2) return BJT_E_ARG;
+    c->paint_path = path;
+    return BJT_OK;
+}
+
+int bjt_device_info(bjt_ctx *c, char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor) {
+    if (!c) return BJT_E_ARG;
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, c->device));
+    if (name && name_len > 0) { strncpy(name, p.name, (size_t)name_len - 1); name[name_len - 1] = 0; }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return BJT_OK;
+}
+
+void *bjt_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void bjt_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// stages on device buffers (no locking, no sync unless a value is needed on the host)
+
+static void stats_out(const StatsPartial &r, bjt_stats *st) {
+    if (!st) return;
+    st->count = r.count; st->sum = r.sum; st->sum2 = r.sum2; st->min = r.mn; st->max = r.mx;
+    const double n = (double)r.count;
+    st->mean = r.sum / n;                 // 0/0 = NaN when the map is empty, as in the Java code
+    double sd = 0.0;
+    if (r.count > 0) {
+        sd = (n * r.sum2 - r.sum * r.sum) / n;
+        sd = sd > 0.0 ? sqrt(sd / (n - 1.0)) : 0.0;
+    }
+    st->sd = sd;
+}
+
+static int dev_edt(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, int inverse, int thresh, int n_sentinel,
+                   uint16_t *gx, uint32_t *gy, uint32_t *sq, uint32_t *maxval_host, cudaEvent_t *evs) {
+    const uint32_t n0 = no_result(n_sentinel);
+    uint8_t *present; uint32_t *scal;
+    WS("present", (size_t)n0 + 1, present);
+    WS("scalars", 256, scal);
+    CK(cudaMemsetAsync(present, 0, (size_t)n0 + 1, c->stream));
+    CK(cudaMemsetAsync(scal, 0, 256, c->stream));
+    if (evs) CK(cudaEventRecord(evs[0], c->stream));
+    c->launches += launch_edt_x(d_in, w, h, d, inverse, thresh, gx, c->stream); CKL();
+    if (evs) CK(cudaEventRecord(evs[1], c->stream));
+    c->launches += launch_edt_y(gx, w, h, d, n0, gy, c->stream); CKL();
+    if (evs) CK(cudaEventRecord(evs[2], c->stream));
+    c->launches += launch_edt_z(gy, w, h, d, n0, sq, present, scal, c->stream); CKL();
+    if (evs) CK(cudaEventRecord(evs[3], c->stream));
+    if (maxval_host) {
+        CK(cudaMemcpyAsync(c->h_scal, scal, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        *maxval_host = c->h_scal[0];
+    }
+    return BJT_OK;
+}
+
+// present table (zeroed or filled by the z pass) -> thresholds -> ridge.  maxval: largest sq value.
+static int dev_ridge(bjt_ctx *c, const uint32_t *sq, int w, int h, int d, uint32_t maxval, const uint8_t *present,
+                     uint32_t *ridge, int64_t *n_ridge) {
+    uint32_t *values, *t1, *t2, *t3, *scal;
+    const size_t tb = ((size_t)maxval + 1) * sizeof(uint32_t);
+    WS("values", tb, values); WS("t1", tb, t1); WS("t2", tb, t2); WS("t3", tb, t3);
+    WS("scalars", 256, scal);
+    CK(cudaMemsetAsync(scal + 2, 0, 16, c->stream));   // [2] = nvalues, [4..5] = ridge count (u64)
+    c->launches += launch_collect_values(present, maxval, values, scal + 2, c->stream); CKL();
+    CK(cudaMemcpyAsync(c->h_scal + 2, scal + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const uint32_t nvalues = c->h_scal[2];
+    c->launches += launch_ridge_template(values, nvalues, t1, t2, t3, c->stream); CKL();
+    c->launches += launch_ridge(sq, w, h, d, t1, t2, t3, ridge, (unsigned long long *)(scal + 4), c->stream); CKL();
+    if (n_ridge) {
+        CK(cudaMemcpyAsync(c->h_scal + 4, scal + 4, 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        *n_ridge = (int64_t)(*(unsigned long long *)(c->h_scal + 4));
+    }
+    return BJT_OK;
+}
+
+// ridge of an arbitrary squared map on the device: largest value, presence table, thresholds, test
+static int dev_ridge_full(bjt_ctx *c, const uint32_t *sq, int w, int h, int d, uint32_t *ridge, int64_t *n_ridge) {
+    const size_t N = (size_t)w * h * d;
+    uint32_t *scal; uint8_t *present;
+    WS("scalars", 256, scal);
+    CK(cudaMemsetAsync(scal, 0, 4, c->stream));
+    c->launches += launch_mark_present(sq, N, nullptr, scal, c->stream); CKL();
+    CK(cudaMemcpyAsync(c->h_scal, scal, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const uint32_t maxval = c->h_scal[0];
+    WS("present", (size_t)maxval + 1, present);
+    CK(cudaMemsetAsync(present, 0, (size_t)maxval + 1, c->stream));
+    c->launches += launch_mark_present(sq, N, present, scal, c->stream); CKL();
+    return dev_ridge(c, sq, w, h, d, maxval, present, ridge, n_ridge);
+}
+
+static int dev_paint(bjt_ctx *c, const uint32_t *ridge, int w, int h, int d, int path, int64_t n_ridge_known,
+                     uint32_t *rsq, int *path_used) {
+    const size_t N = (size_t)w * h * d;
+    if (path < 0) path = c->paint_path;
+    if (path < 0) path = 0;
+    // separable painter: 16-bit items, then 32-bit items, then the scatter fallback
+    for (; path <= 1; ++path) {
+        uint32_t *scal; void *wsp;
+        const size_t wb = paint_sep_workspace_bytes(w, h, d, path);
+        if (wb == 0) continue;                       // this variant cannot represent the volume
+        WS("scalars", 256, scal);
+        WS("paint_sep", wb, wsp);
+        CK(cudaMemsetAsync(scal + 8, 0, 4, c->stream));
+        c->launches += launch_paint_sep(ridge, w, h, d, path, wsp, rsq, scal + 8, c->stream); CKL();
+        CK(cudaMemcpyAsync(c->h_scal + 8, scal + 8, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->h_scal[8] == 0) { if (path_used) *path_used = path; return BJT_OK; }
+        if (c->paint_path >= 0 && c->paint_path == path)
+            return fail(c, BJT_E_INTERNAL, "separable painter (path %d) overflowed its lists (flag %u)", path, c->h_scal[8]);
+    }
+    // scatter
+    {
+        uint32_t *scal; uint4 *points;
+        WS("scalars", 256, scal);
+        unsigned long long npts = 0;
+        if (n_ridge_known >= 0) {
+            npts = (unsigned long long)n_ridge_known;
+        } else {   // count first (null sink)
+            CK(cudaMemsetAsync(scal + 10, 0, 8, c->stream));
+            c->launches += launch_compact_ridge(ridge, w, h, d, nullptr, (unsigned long long *)(scal + 10), c->stream); CKL();
+            CK(cudaMemcpyAsync(c->h_scal + 10, scal + 10, 8, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            npts = *(unsigned long long *)(c->h_scal + 10);
+        }
+        WS("points", (size_t)(npts > 0 ? npts : 1) * sizeof(uint4), points);
+        CK(cudaMemsetAsync(scal + 10, 0, 8, c->stream));
+        CK(cudaMemsetAsync(rsq, 0, N * sizeof(uint32_t), c->stream));
+        c->launches += launch_compact_ridge(ridge, w, h, d, points, (unsigned long long *)(scal + 10), c->stream); CKL();
+        c->launches += launch_paint_scatter(points, npts, w, h, d, rsq, c->stream); CKL();
+        if (path_used) *path_used = 2;
+    }
+    return BJT_OK;
+}
+
+static int dev_finish(bjt_ctx *c, const uint32_t *rsq, const uint8_t *d_original, int w, int h, int d, int inverse,
+                      int calibrate, double pixel_width, float *d_out, bjt_stats *stats) {
+    const size_t N = (size_t)w * h * d;
+    uint8_t *flags; StatsPartial *partials, *result;
+    const int np = finish_partials(w, h, d);
+    WS("flags", N, flags);
+    WS("partials", (size_t)np * sizeof(StatsPartial), partials);
+    WS("stats_result", sizeof(StatsPartial), result);
+    c->launches += launch_finish(rsq, d_original, w, h, d, inverse, calibrate, (float)pixel_width, flags, d_out,
+                                 partials, np, result, c->stream); CKL();
+    if (stats) {
+        CK(cudaMemcpyAsync(c->h_stats, result, sizeof(StatsPartial), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        stats_out(*c->h_stats, stats);
+    }
+    return BJT_OK;
+}
+
+// the whole chain on device buffers
+static int dev_pipeline(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, int inverse, int mask, int thresh,
+                        double pixel_width, float *d_out, bjt_stats *stats, bjt_timing *tm) {
+    const size_t N = (size_t)w * h * d;
+    const int n = w > h ? (w > d ? w : d) : (h > d ? h : d);
+    const uint32_t n0 = no_result(n);
+    uint16_t *gx; uint32_t *bufA, *bufB; uint32_t *scal;
+    WS("gx", N * sizeof(uint16_t), gx);
+    WS("bufA", N * sizeof(uint32_t), bufA);
+    WS("bufB", N * sizeof(uint32_t), bufB);
+    WS("scalars", 256, scal);
+    const int64_t launches0 = c->launches;
+
+    // input check of LocalThicknessWrapper.processImage: only 0 and 255
+    CK(cudaMemsetAsync(scal + 12, 0, 4, c->stream));
+    c->launches += launch_check_binary(d_in, N, scal + 12, c->stream); CKL();
+    CK(cudaMemcpyAsync(c->h_scal + 12, scal + 12, 4, cudaMemcpyDeviceToHost, c->stream));
+
+    uint32_t maxval = 0;
+    int rc = dev_edt(c, d_in, w, h, d, inverse, thresh, n, gx, bufA, bufB, &maxval, c->ev);
+    if (rc) return rc;
+    if (c->h_scal[12]) return fail(c, BJT_E_NOT_BINARY, "input is not a binary 0/255 image");
+    uint8_t *present; WS("present", (size_t)n0 + 1, present);
+
+    int64_t n_ridge = 0;
+    int path_used = 3;
+    uint32_t *rsq = bufB;
+    if (maxval == 0) {
+        // no foreground for this run: sq (bufB) is all zero and doubles as the painted map
+        CK(cudaEventRecord(c->ev[4], c->stream));
+        CK(cudaEventRecord(c->ev[5], c->stream));
+    } else if (maxval >= n0) {
+        // no background anywhere: every voxel carries the sentinel radius and is covered by every ball
+        c->launches += launch_fill_u32(bufB, N, n0, c->stream); CKL();
+        n_ridge = (int64_t)N;
+        CK(cudaEventRecord(c->ev[4], c->stream));
+        CK(cudaEventRecord(c->ev[5], c->stream));
+    } else {
+        rc = dev_ridge(c, bufB, w, h, d, maxval, present, bufA, &n_ridge);
+        if (rc) return rc;
+        CK(cudaEventRecord(c->ev[4], c->stream));
+        rc = dev_paint(c, bufA, w, h, d, -1, n_ridge, bufB, &path_used);
+        if (rc) return rc;
+        CK(cudaEventRecord(c->ev[5], c->stream));
+    }
+    rc = dev_finish(c, rsq, mask ? d_in : nullptr, w, h, d, inverse, 1, pixel_width, d_out, stats);
+    if (rc) return rc;
+    CK(cudaEventRecord(c->ev[6], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (tm) {
+        cudaEventElapsedTime(&tm->ms_edt_x, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&tm->ms_edt_y, c->ev[1], c->ev[2]);
+        cudaEventElapsedTime(&tm->ms_edt_z, c->ev[2], c->ev[3]);
+        cudaEventElapsedTime(&tm->ms_ridge, c->ev[3], c->ev[4]);
+        cudaEventElapsedTime(&tm->ms_paint, c->ev[4], c->ev[5]);
+        cudaEventElapsedTime(&tm->ms_finish, c->ev[5], c->ev[6]);
+        tm->ms_cleanup = tm->ms_finish;
+        cudaEventElapsedTime(&tm->ms_total, c->ev[0], c->ev[6]);
+        tm->n_ridge = n_ridge;
+        tm->rsq_max = maxval;
+        tm->paint_path = path_used;
+        tm->n_launches = c->launches - launches0;
+    }
+    return BJT_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+#define ENTER(c)                                            \
+    if (!(c)) return fail(nullptr, BJT_E_ARG, "null context"); \
+    std::lock_guard<std::mutex> lk_((c)->mu);               \
+    DeviceGuard dg_((c)->device)
+
+extern "C" {
+
+int bjt_dev_thickness_u8(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, int inverse, int mask, int threshold,
+                         double pixel_width, float *d_out_map, bjt_stats *stats, bjt_timing *timing) {
+    ENTER(c);
+    int rc = check_dims(c, w, h, d);
+    if (rc) return rc;
+    if (!d_in) return fail(c, BJT_E_ARG, "null input");
+    if (timing) memset(timing, 0, sizeof *timing);
+    return dev_pipeline(c, d_in, w, h, d, inverse, mask, threshold, pixel_width, d_out_map, stats, timing);
+}
+
+static int host_run(bjt_ctx *c, const uint8_t *in, const uint8_t *const *in_slices, int w, int h, int d, int both,
+                    int inverse, int mask, int threshold, double pixel_width, float *out0, float *const *out_slices,
+                    float *out1, bjt_stats *st0, bjt_stats *st1, bjt_timing *tm0, bjt_timing *tm1) {
+    int rc = check_dims(c, w, h, d);
+    if (rc) return rc;
+    if (!in && !in_slices) return fail(c, BJT_E_ARG, "null input");
+    const size_t N = (size_t)w * h * d, wh = (size_t)w * h;
+    uint8_t *d_in; float *d_out;
+    WS("in", N, d_in);
+    WS("out", N * sizeof(float), d_out);
+    if (tm0) memset(tm0, 0, sizeof *tm0);
+    if (tm1) memset(tm1, 0, sizeof *tm1);
+    CK(cudaEventRecord(c->ev[8], c->stream));
+    if (in) CK(cudaMemcpyAsync(d_in, in, N, cudaMemcpyHostToDevice, c->stream));
+    else for (int z = 0; z < d; ++z) {
+        if (!in_slices[z]) return fail(c, BJT_E_ARG, "null input slice %d", z);
+        CK(cudaMemcpyAsync(d_in + z * wh, in_slices[z], wh, cudaMemcpyHostToDevice, c->stream));
+    }
+    CK(cudaEventRecord(c->ev[9], c->stream));
+    for (int run = 0; run < (both ? 2 : 1); ++run) {
+        const int inv = both ? run : inverse;
+        float *out = run == 0 ? out0 : out1;
+        bjt_timing *tm = run == 0 ? tm0 : tm1;
+        const bool want_map = out || (run == 0 && out_slices);
+        rc = dev_pipeline(c, d_in, w, h, d, inv, mask, threshold, pixel_width, want_map ? d_out : nullptr,
+                          run == 0 ? st0 : st1, tm);
+        if (rc) return rc;
+        CK(cudaEventRecord(c->ev[10], c->stream));
+        if (out) CK(cudaMemcpyAsync(out, d_out, N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        else if (run == 0 && out_slices) for (int z = 0; z < d; ++z) {
+            if (!out_slices[z]) return fail(c, BJT_E_ARG, "null output slice %d", z);
+            CK(cudaMemcpyAsync(out_slices[z], d_out + z * wh, wh * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        }
+        CK(cudaEventRecord(c->ev[11], c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (tm) {
+            if (run == 0) cudaEventElapsedTime(&tm->ms_h2d, c->ev[8], c->ev[9]);
+            cudaEventElapsedTime(&tm->ms_d2h, c->ev[10], c->ev[11]);
+            tm->ms_total += tm->ms_h2d + tm->ms_d2h;
+        }
+    }
+    return BJT_OK;
+}
+
+int bjt_thickness_u8(bjt_ctx *c, const uint8_t *in, int w, int h, int d, int inverse, int mask, int threshold,
+                     double pixel_width, float *out_map, bjt_stats *stats, bjt_timing *timing) {
+    ENTER(c);
+    return host_run(c, in, nullptr, w, h, d, 0, inverse, mask, threshold, pixel_width, out_map, nullptr, nullptr, stats,
+                    nullptr, timing, nullptr);
+}
+
+int bjt_thickness_u8_slices(bjt_ctx *c, const uint8_t *const *in_slices, int w, int h, int d, int inverse, int mask,
+                            int threshold, double pixel_width, float *const *out_slices, bjt_stats *stats,
+                            bjt_timing *timing) {
+    ENTER(c);
+    if (!in_slices) return fail(c, BJT_E_ARG, "null input");
+    return host_run(c, nullptr, in_slices, w, h, d, 0, inverse, mask, threshold, pixel_width, nullptr, out_slices,
+                    nullptr, stats, nullptr, timing, nullptr);
+}
+
+int bjt_thickness_both_u8(bjt_ctx *c, const uint8_t *in, int w, int h, int d, int mask, int threshold,
+                          double pixel_width, float *out_th, float *out_sp, bjt_stats *stats_th, bjt_stats *stats_sp,
+                          bjt_timing *timing_th, bjt_timing *timing_sp) {
+    ENTER(c);
+    return host_run(c, in, nullptr, w, h, d, 1, 0, mask, threshold, pixel_width, out_th, nullptr, out_sp, stats_th,
+                    stats_sp, timing_th, timing_sp);
+}
+
+// ---- stage-level, host buffers ---------------------------------------------------------------------
+
+int bjt_edt_sq_u8(bjt_ctx *c, const uint8_t *in, int w, int h, int d, int inverse, int threshold, uint32_t *out_sq) {
+    ENTER(c);
+    int rc = check_dims(c, w, h, d);
+    if (rc) return rc;
+    if (!in || !out_sq) return fail(c, BJT_E_ARG, "null buffer");
+    const size_t N = (size_t)w * h * d;
+    const int n = w > h ? (w > d ? w : d) : (h > d ? h : d);
+    uint8_t *d_in; uint16_t *gx; uint32_t *bufA, *bufB;
+    WS("in", N, d_in); WS("gx", N * 2, gx); WS("bufA", N * 4, bufA); WS("bufB", N * 4, bufB);
+    CK(cudaMemcpyAsync(d_in, in, N, cudaMemcpyHostToDevice, c->stream));
+    uint32_t maxval;
+    rc = dev_edt(c, d_in, w, h, d, inverse, threshold, n, gx, bufA, bufB, &maxval, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_sq, bufB, N * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return BJT_OK;
+}
+
+int bjt_ridge_u32(bjt_ctx *c, const uint32_t *sq, int w, int h, int d, uint32_t *out_ridge) {
+    ENTER(c);
+    int rc = check_dims(c, w, h, d);
+    if (rc) return rc;
+    if (!sq || !out_ridge) return fail(c, BJT_E_ARG, "null buffer");
+    const size_t N = (size_t)w * h * d;
+    uint32_t *bufA, *bufB;
+    WS("bufA", N * 4, bufA); WS("bufB", N * 4, bufB);
+    CK(cudaMemcpyAsync(bufB, sq, N * 4, cudaMemcpyHostToDevice, c->stream));
+    rc = dev_ridge_full(c, bufB, w, h, d, bufA, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_ridge, bufA, N * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return BJT_OK;
+}
+
+int bjt_ridge_template(bjt_ctx *c, const int32_t *rsq_values, int n, int32_t *t1, int32_t *t2, int32_t *t3) {
+    ENTER(c);
+    if (n < 0 || (n > 0 && (!rsq_values || !t1 || !t2 || !t3))) return fail(c, BJT_E_ARG, "bad template arguments");
+    if (n == 0) return BJT_OK;
+    uint32_t *v, *a, *b, *e;
+    const size_t bytes = (size_t)n * 4;
+    WS("values", bytes, v); WS("t1", bytes, a); WS("t2", bytes, b); WS("t3", bytes, e);
+    CK(cudaMemcpyAsync(v, rsq_values, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->launches += launch_ridge_template_compact(v, (uint32_t)n, a, b, e, c->stream); CKL();
+    CK(cudaMemcpyAsync(t1, a, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(t2, b, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(t3, e, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return BJT_OK;
+}
+
+int bjt_paint_rsq(bjt_ctx *c, const uint32_t *ridge, int w, int h, int d, int path, uint32_t *out_rsq) {
+    ENTER(c);
+    int rc = check_dims(c, w, h, d);
+    if (rc) return rc;
+    if (!ridge || !out_rsq) return fail(c, BJT_E_ARG, "null buffer");
+    const size_t N = (size_t)w * h * d;
+    uint32_t *bufA, *bufB;
+    WS("bufA", N * 4, bufA); WS("bufB", N * 4, bufB);
+    CK(cudaMemcpyAsync(bufA, ridge, N * 4, cudaMemcpyHostToDevice, c->stream));
+    const int saved = c->paint_path;
+    if (path >= 0) c->paint_path = path;
+    rc = dev_paint(c, bufA, w, h, d, path, -1, bufB, nullptr);
+    c->paint_path = saved;
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_rsq, bufB, N * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return BJT_OK;
+}
+
+int bjt_cleanup_f32(bjt_ctx *c, const uint32_t *rsq, const uint8_t *original, int w, int h, int d, int inverse,
+                    int calibrate, double pixel_width, float *out_map, bjt_stats *stats) {
+    ENTER(c);
+    int rc = check_dims(c, w, h, d);
+    if (rc) return rc;
+    if (!rsq) return fail(c, BJT_E_ARG, "null buffer");
+    const size_t N = (size_t)w * h * d;
+    uint32_t *bufB; uint8_t *d_in = nullptr; float *d_out;
+    WS("bufB", N * 4, bufB); WS("out", N * 4, d_out);
+    CK(cudaMemcpyAsync(bufB, rsq, N * 4, cudaMemcpyHostToDevice, c->stream));
+    if (original) { WS("in", N, d_in); CK(cudaMemcpyAsync(d_in, original, N, cudaMemcpyHostToDevice, c->stream)); }
+    rc = dev_finish(c, bufB, d_in, w, h, d, inverse, calibrate, pixel_width, d_out, stats);
+    if (rc) return rc;
+    if (out_map) CK(cudaMemcpyAsync(out_map, d_out, N * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return BJT_OK;
+}
+
+int bjt_stats_f32(bjt_ctx *c, const float *map, size_t n, bjt_stats *stats) {
+    ENTER(c);
+    if (!map || !stats || n == 0) return fail(c, BJT_E_ARG, "bad stats arguments");
+    float *d_out; StatsPartial *partials, *result;
+    const int np = 148 * 8;
+    WS("out", n * 4, d_out); WS("partials", (size_t)np * sizeof(StatsPartial), partials);
+    WS("stats_result", sizeof(StatsPartial), result);
+    CK(cudaMemcpyAsync(d_out, map, n * 4, cudaMemcpyHostToDevice, c->stream));
+    c->launches += launch_stats(d_out, n, partials, np, result, c->stream); CKL();
+    CK(cudaMemcpyAsync(c->h_stats, result, sizeof(StatsPartial), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    stats_out(*c->h_stats, stats);
+    return BJT_OK;
+}
+
+// ---- stage-level, device buffers -------------------------------------------------------------------
+
+int bjt_dev_edt_x(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, int inverse, int threshold, uint16_t *d_gx) {
+    ENTER(c);
+    int rc = check_dims(c, w, h, d);
+    if (rc) return rc;
+    c->launches += launch_edt_x(d_in, w, h, d, inverse, threshold, d_gx, c->stream); CKL();
+    return BJT_OK;
+}
+
+int bjt_dev_edt_y(bjt_ctx *c, const uint16_t *d_gx, int w, int h, int d, int n_sentinel, uint32_t *d_gy) {
+    ENTER(c);
+    int rc = check_dims(c, w, h, d);
+    if (rc) return rc;
+    c->launches += launch_edt_y(d_gx, w, h, d, no_result(n_sentinel), d_gy, c->stream); CKL();
+    return BJT_OK;
+}
+
+int bjt_dev_edt_z(bjt_ctx *c, const uint32_t *d_gy, int w, int h, int d, int n_sentinel, uint32_t *d_sq) {
+    ENTER(c);
+    int rc = check_dims(c, w, h, d);
+    if (rc) return rc;
+    const uint32_t n0 = no_result(n_sentinel);
+    uint8_t *present; uint32_t *scal;
+    WS("present", (size_t)n0 + 1, present); WS("scalars", 256, scal);
+    CK(cudaMemsetAsync(present, 0, (size_t)n0 + 1, c->stream));
+    CK(cudaMemsetAsync(scal, 0, 4, c->stream));
+    c->launches += launch_edt_z(d_gy, w, h, d, n0, d_sq, present, scal, c->stream); CKL();
+    return BJT_OK;
+}
+
+int bjt_dev_ridge(bjt_ctx *c, const uint32_t *d_sq, int w, int h, int d, uint32_t *d_ridge) {
+    ENTER(c);
+    int rc = check_dims(c, w, h, d);
+    if (rc) return rc;
+    return dev_ridge_full(c, d_sq, w, h, d, d_ridge, nullptr);
+}
+
+int bjt_dev_paint(bjt_ctx *c, const uint32_t *d_ridge, int w, int h, int d, int path, uint32_t *d_rsq) {
+    ENTER(c);
+    int rc = check_dims(c, w, h, d);
+    if (rc) return rc;
+    const int saved = c->paint_path;
+    if (path >= 0) c->paint_path = path;
+    rc = dev_paint(c, d_ridge, w, h, d, path, -1, d_rsq, nullptr);
+    c->paint_path = saved;
+    return rc;
+}
+
+int bjt_dev_finish(bjt_ctx *c, const uint32_t *d_rsq, const uint8_t *d_original, int w, int h, int d, int inverse,
+                   int calibrate, double pixel_width, float *d_out, bjt_stats *stats) {
+    ENTER(c);
+    int rc = check_dims(c, w, h, d);
+    if (rc) return rc;
+    return dev_finish(c, d_rsq, d_original, w, h, d, inverse, calibrate, pixel_width, d_out, stats);
+}
+
+// ---- phantom ---------------------------------------------------------------------------------------
+
+int bjt_dev_phantom_u8(bjt_ctx *c, const int32_t *shapes_host, int nshapes, int w, int h, int d, int z0, int dz,
+                       uint8_t *d_out) {
+    ENTER(c);
+    int rc = check_dims(c, w, h, d);
+    if (rc) return rc;
+    if (nshapes < 0 || (nshapes > 0 && !shapes_host) || !d_out || z0 < 0 || dz <= 0 || z0 + dz > d)
+        return fail(c, BJT_E_ARG, "bad phantom arguments");
+    int32_t *d_shapes;
+    WS("shapes", (size_t)(nshapes > 0 ? nshapes : 1) * 16 * sizeof(int32_t), d_shapes);
+    if (nshapes) CK(cudaMemcpyAsync(d_shapes, shapes_host, (size_t)nshapes * 16 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    c->launches += launch_phantom(d_shapes, nshapes, w, h, d, z0, dz, d_out, c->stream); CKL();
+    CK(cudaStreamSynchronize(c->stream));
+    return BJT_OK;
+}
+
+int bjt_phantom_u8(bjt_ctx *c, const int32_t *shapes, int nshapes, int w, int h, int d, uint8_t *out) {
+    if (!c) return fail(nullptr, BJT_E_ARG, "null context");
+    if (!out) return fail(c, BJT_E_ARG, "null output");
+    uint8_t *d_in;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        DeviceGuard dg(c->device);
+        int rc = check_dims(c, w, h, d);
+        if (rc) return rc;
+        WS("in", (size_t)w * h * d, d_in);
+    }
+    int rc = bjt_dev_phantom_u8(c, shapes, nshapes, w, h, d, 0, d, d_in);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    DeviceGuard dg(c->device);
+    CK(cudaMemcpyAsync(out, d_in, (size_t)w * h * d, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return BJT_OK;
+}
+
+}  // extern "C"

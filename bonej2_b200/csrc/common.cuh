@@ -1,0 +1,79 @@
+// common.cuh -- shared declarations of libbonejthickness (sm_100a).  Internal; the public
+// surface is include/bonej_thickness.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace bjt {
+
+// EDT x-pass writes the in-row distance (not squared) as u16; rows without background carry GX_INF.
+constexpr uint16_t GX_INF = 0xFFFFu;
+// largest supported extent: 8 x 1024 voxels per row segment set of the x-pass kernel
+constexpr int MAX_EXTENT = 8192;
+
+struct StatsPartial {
+    double sum, sum2;
+    double mn, mx;
+    long long count;
+};
+
+// sentinel of EDT_S1D: noResult = 3 (n+1)^2, n = max(w,h,d)      
+__host__ __device__ inline uint32_t no_result(int n) { return 3u * (uint32_t)(n + 1) * (uint32_t)(n + 1); }
+
+__device__ __forceinline__ uint32_t isqrt_floor(uint32_t v) {
+    // exact floor(sqrt(v)) for v < 2^31
+    uint32_t r = (uint32_t)sqrtf((float)v);
+    while (r * r > v) --r;
+    while ((r + 1u) * (r + 1u) <= v) ++r;
+    return r;
+}
+__device__ __forceinline__ uint32_t isqrt_ceil(uint32_t v) {
+    uint32_t r = isqrt_floor(v);
+    return r * r < v ? r + 1u : r;
+}
+
+// ---- launchers (each returns the number of kernels it launched; errors via cudaGetLastError) ----
+int launch_edt_x(const uint8_t *in, int w, int h, int d, int inverse, int thresh, uint16_t *gx, cudaStream_t s);
+int launch_edt_y(const uint16_t *gx, int w, int h, int d, uint32_t n0, uint32_t *gy, cudaStream_t s);
+// present: n0+1 bytes, must be zeroed by the caller; maxval: one u32, zeroed by the caller
+int launch_edt_z(const uint32_t *gy, int w, int h, int d, uint32_t n0, uint32_t *sq, uint8_t *present,
+                 uint32_t *maxval, cudaStream_t s);
+
+// distinct-value list from the presence table; values[] sized >= number of present values
+int launch_collect_values(const uint8_t *present, uint32_t vmax, uint32_t *values, uint32_t *count, cudaStream_t s);
+// t1/t2/t3 indexed by r^2 value (direct index)
+int launch_ridge_template(const uint32_t *values, uint32_t nvalues, uint32_t *t1, uint32_t *t2, uint32_t *t3,
+                          cudaStream_t s);
+// same, compact output (parity test of createTemplate)
+int launch_ridge_template_compact(const uint32_t *values, uint32_t nvalues, uint32_t *t1, uint32_t *t2,
+                                  uint32_t *t3, cudaStream_t s);
+int launch_mark_present(const uint32_t *sq, size_t n, uint8_t *present, uint32_t *maxval, cudaStream_t s);
+int launch_ridge(const uint32_t *sq, int w, int h, int d, const uint32_t *t1, const uint32_t *t2,
+                 const uint32_t *t3, uint32_t *ridge, unsigned long long *count, cudaStream_t s);
+
+// brute-force scatter paint (path 2): points = compacted ridge (x | y<<16, z, r^2, pad)
+int launch_compact_ridge(const uint32_t *ridge, int w, int h, int d, uint4 *points, unsigned long long *count,
+                         cudaStream_t s);
+int launch_paint_scatter(const uint4 *points, unsigned long long npoints, int w, int h, int d, uint32_t *rsq,
+                         cudaStream_t s);
+int launch_fill_u32(uint32_t *p, size_t n, uint32_t v, cudaStream_t s);
+
+// separable paint (paths 0/1), see paint_sep.cu
+size_t paint_sep_workspace_bytes(int w, int h, int d, int wide);
+int launch_paint_sep(const uint32_t *ridge, int w, int h, int d, int wide, void *workspace, uint32_t *rsq,
+                     uint32_t *overflow_flag, cudaStream_t s);
+
+// 2*sqrt + cleanup + mask + NaN/calibrate + stats
+int launch_finish(const uint32_t *rsq, const uint8_t *original, int w, int h, int d, int inverse, int calibrate,
+                  float pixel_width, uint8_t *flags, float *out, StatsPartial *partials, int npartials,
+                  StatsPartial *result, cudaStream_t s);
+int finish_partials(int w, int h, int d);
+int launch_stats(const float *map, size_t n, StatsPartial *partials, int npartials, StatsPartial *result,
+                 cudaStream_t s);
+int launch_check_binary(const uint8_t *in, size_t n, uint32_t *bad, cudaStream_t s);
+
+int launch_phantom(const int32_t *shapes, int nshapes, int w, int h, int d, int z0, int dz, uint8_t *out,
+                   cudaStream_t s);
+
+}  // namespace bjt

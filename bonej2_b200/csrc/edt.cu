@@ -1,0 +1,243 @@
+// edt.cu -- exact squared Euclidean distance transform (Saito-Toriwaki decomposition), sm_100a.
+//
+// Replaces sc.fiji.localThickness.EDT_S1D (Step1/Step2/Step3 threads), reached
+// from ThicknessWrapper.createMap() (ThicknessWrapper.java:190-196).  Result per voxel:
+//   sq(p) = min( min_{q background, q inside the image} |p-q|^2 , 3(n+1)^2 ),  background -> 0.
+//
+//   x pass  one warp per row.  The row's background flags live in registers as bit masks
+//           (lane l owns 32 consecutive voxels of every 1024-voxel segment), nearest flags left
+//           and right come from clz/ffs plus a warp prefix-max / suffix-min over the lanes, and
+//           the in-row distance (not squared) goes out as u16: 1 B read + 2 B written per voxel.
+//   y, z    one thread per line, adjacent threads on adjacent x, so every access of a warp is
+//           one contiguous row segment.  Each thread walks its line once; the minimiser of
+//           f(y') + (y-y')^2 is monotone in y, so the scan for y starts at the previous
+//           minimiser and stops as soon as (y'-y)^2 reaches the running minimum.  Candidate
+//           reads hit L1; HBM sees one read and one write per voxel.
+#include "common.cuh"
+
+namespace bjt {
+
+// ---------------------------------------------------------------------------------------------
+// x pass
+
+__device__ __forceinline__ uint32_t bytes_lt_mask4(uint32_t word, uint32_t t4) {
+    // 4 bytes -> 4 bits (bit k = byte k < threshold)
+    uint32_t cmp = __vcmpltu4(word, t4);
+    return ((cmp & 0x01010101u) * 0x01020408u) >> 24;
+}
+
+__device__ __forceinline__ uint32_t mask16_of(uint4 v, uint32_t t4) {
+    return bytes_lt_mask4(v.x, t4) | (bytes_lt_mask4(v.y, t4) << 4) | (bytes_lt_mask4(v.z, t4) << 8) |
+           (bytes_lt_mask4(v.w, t4) << 12);
+}
+
+template <int NSEG, bool ALIGNED>
+__global__ void __launch_bounds__(256) edt_x_kernel(const uint8_t *__restrict__ in, int w, long long rows,
+                                                     int thresh, int inverse, uint16_t *__restrict__ gx) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;   // whole warp leaves together
+    const uint8_t *r = in + row * (long long)w;
+    uint16_t *o = gx + row * (long long)w;
+    const int BIG = 1 << 30;
+
+    uint32_t m[NSEG];
+    const uint32_t t4 = (uint32_t)(thresh < 0 ? 0 : (thresh > 255 ? 255 : thresh)) * 0x01010101u;
+#pragma unroll
+    for (int s = 0; s < NSEG; ++s) {
+        const int x0 = (s * 32 + lane) * 32;
+        uint32_t bits = 0;
+        if (x0 < w) {
+            if (ALIGNED && x0 + 32 <= w && thresh >= 0 && thresh <= 255) {
+                const uint4 *p = reinterpret_cast<const uint4 *>(r + x0);
+                uint4 a = __ldg(p), b = __ldg(p + 1);
+                bits = mask16_of(a, t4) | (mask16_of(b, t4) << 16);
+            } else {
+                const int nb = min(32, w - x0);
+                for (int b = 0; b < nb; ++b) bits |= ((int)r[x0 + b] < thresh ? 1u : 0u) << b;
+            }
+            if (inverse) {
+                const int nb = min(32, w - x0);
+                const uint32_t valid = nb >= 32 ? 0xFFFFFFFFu : ((1u << nb) - 1u);
+                bits = (~bits) & valid;
+            }
+        }
+        m[s] = bits;
+    }
+
+    // exclusive prefix-max of "last background index" and suffix-min of "first background index"
+    int cl[NSEG], cr[NSEG];
+    int segL = -1;
+#pragma unroll
+    for (int s = 0; s < NSEG; ++s) {
+        const int x0 = (s * 32 + lane) * 32;
+        int v = m[s] ? x0 + 31 - __clz(m[s]) : -1;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            int u = __shfl_up_sync(0xFFFFFFFFu, v, k);
+            if (lane >= k) v = max(v, u);
+        }
+        int ex = __shfl_up_sync(0xFFFFFFFFu, v, 1);
+        if (lane == 0) ex = -1;
+        cl[s] = max(segL, ex);
+        segL = max(segL, __shfl_sync(0xFFFFFFFFu, v, 31));
+    }
+    int segR = BIG;
+#pragma unroll
+    for (int s = NSEG - 1; s >= 0; --s) {
+        const int x0 = (s * 32 + lane) * 32;
+        int v = m[s] ? x0 + __ffs(m[s]) - 1 : BIG;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            int u = __shfl_down_sync(0xFFFFFFFFu, v, k);
+            if (lane + k < 32) v = min(v, u);
+        }
+        int ex = __shfl_down_sync(0xFFFFFFFFu, v, 1);
+        if (lane == 31) ex = BIG;
+        cr[s] = min(segR, ex);
+        segR = min(segR, __shfl_sync(0xFFFFFFFFu, v, 0));
+    }
+
+#pragma unroll
+    for (int s = 0; s < NSEG; ++s) {
+        const int x0 = (s * 32 + lane) * 32;
+        if (x0 >= w) continue;
+        const uint32_t bits = m[s];
+        int dist[32];
+        int cur = cl[s];
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+            if ((bits >> b) & 1u) cur = x0 + b;
+            dist[b] = cur >= 0 ? x0 + b - cur : BIG;
+        }
+        cur = cr[s];
+#pragma unroll
+        for (int b = 31; b >= 0; --b) {
+            if ((bits >> b) & 1u) cur = x0 + b;
+            const int dr = cur < BIG ? cur - (x0 + b) : BIG;
+            const int dd = min(dist[b], dr);
+            dist[b] = dd >= BIG ? (int)GX_INF : dd;
+        }
+        if (ALIGNED && x0 + 32 <= w) {
+            uint4 *q = reinterpret_cast<uint4 *>(o + x0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint4 v;
+                v.x = (uint32_t)dist[8 * k + 0] | ((uint32_t)dist[8 * k + 1] << 16);
+                v.y = (uint32_t)dist[8 * k + 2] | ((uint32_t)dist[8 * k + 3] << 16);
+                v.z = (uint32_t)dist[8 * k + 4] | ((uint32_t)dist[8 * k + 5] << 16);
+                v.w = (uint32_t)dist[8 * k + 6] | ((uint32_t)dist[8 * k + 7] << 16);
+                q[k] = v;
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < 32; ++b)
+                if (x0 + b < w) o[x0 + b] = (uint16_t)dist[b];
+        }
+    }
+}
+
+template <int NSEG>
+static void edt_x_dispatch(const uint8_t *in, int w, long long rows, int thresh, int inverse, uint16_t *gx,
+                           bool aligned, cudaStream_t s) {
+    const int warps = 8;
+    const unsigned grid = (unsigned)((rows + warps - 1) / warps);
+    if (aligned)
+        edt_x_kernel<NSEG, true><<<grid, warps * 32, 0, s>>>(in, w, rows, thresh, inverse, gx);
+    else
+        edt_x_kernel<NSEG, false><<<grid, warps * 32, 0, s>>>(in, w, rows, thresh, inverse, gx);
+}
+
+int launch_edt_x(const uint8_t *in, int w, int h, int d, int inverse, int thresh, uint16_t *gx, cudaStream_t s) {
+    const long long rows = (long long)h * d;
+    const bool aligned = (w % 16 == 0) && ((uintptr_t)in % 16 == 0) && ((uintptr_t)gx % 16 == 0);
+    const int nseg = (w + 1023) / 1024;
+    if (nseg <= 1) edt_x_dispatch<1>(in, w, rows, thresh, inverse, gx, aligned, s);
+    else if (nseg <= 2) edt_x_dispatch<2>(in, w, rows, thresh, inverse, gx, aligned, s);
+    else if (nseg <= 4) edt_x_dispatch<4>(in, w, rows, thresh, inverse, gx, aligned, s);
+    else edt_x_dispatch<8>(in, w, rows, thresh, inverse, gx, aligned, s);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// y / z passes
+
+__device__ __forceinline__ uint32_t f_of(uint16_t v, uint32_t n0) { return v == GX_INF ? n0 : (uint32_t)v * (uint32_t)v; }
+__device__ __forceinline__ uint32_t f_of(uint32_t v, uint32_t) { return v; }
+
+// line index t -> first element (t / w) * outer + t % w ; successive line positions are `stride` apart.
+template <typename TIn, bool MARK>
+__global__ void __launch_bounds__(256) edt_line_kernel(const TIn *__restrict__ in, uint32_t *__restrict__ out, int w,
+                                                        long long nlines, long long outer, long long stride, int L,
+                                                        uint32_t n0, uint8_t *__restrict__ present,
+                                                        uint32_t *__restrict__ maxval) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = t < nlines;
+    uint32_t tmax = 0;
+    if (valid) {
+        const long long base = (t / w) * outer + (t % w);
+        const TIn *col = in + base;
+        uint32_t *oc = out + base;
+        const uint32_t NONE = 0x7FFFFFFFu;
+        int a = 0;                                  // leftmost minimiser of the previous position
+        uint32_t fa = f_of(__ldg(col), n0);
+        uint32_t prev = 0xFFFFFFFFu;
+        for (int y = 0; y < L; ++y) {
+            const uint32_t fy = (y == a) ? fa : f_of(__ldg(col + (long long)y * stride), n0);
+            uint32_t res;
+            if (fy == 0u) {                         // background of this run: distance 0, new minimiser
+                res = 0u; a = y; fa = 0u;
+            } else {
+                const int da = y - a;
+                uint32_t m = fa >= n0 ? NONE : fa + (uint32_t)(da * da);
+                int best = a;
+                uint32_t fbest = fa;
+                for (int yp = a + 1; yp < L; ++yp) {
+                    const int dy = yp - y;
+                    if (dy > 0 && (uint32_t)(dy * dy) >= m) break;
+                    const uint32_t fv = f_of(__ldg(col + (long long)yp * stride), n0);
+                    if (fv < n0) {
+                        const uint32_t v = fv + (uint32_t)(dy * dy);
+                        if (v < m) { m = v; best = yp; fbest = fv; }
+                    }
+                }
+                if (m == NONE) {                    // no finite candidate on the rest of the line
+                    for (int yy = y; yy < L; ++yy) oc[(long long)yy * stride] = n0;
+                    if (MARK) present[n0] = 1;
+                    tmax = n0;
+                    break;
+                }
+                res = m < n0 ? m : n0;
+                a = best; fa = fbest;
+            }
+            oc[(long long)y * stride] = res;
+            if (MARK) {
+                if (res != prev) { present[res] = 1; prev = res; }
+                tmax = max(tmax, res);
+            }
+        }
+    }
+    if (MARK) {
+        tmax = __reduce_max_sync(0xFFFFFFFFu, tmax);
+        if ((threadIdx.x & 31) == 0 && tmax) atomicMax(maxval, tmax);
+    }
+}
+
+int launch_edt_y(const uint16_t *gx, int w, int h, int d, uint32_t n0, uint32_t *gy, cudaStream_t s) {
+    const long long nlines = (long long)w * d;
+    const unsigned grid = (unsigned)((nlines + 255) / 256);
+    edt_line_kernel<uint16_t, false><<<grid, 256, 0, s>>>(gx, gy, w, nlines, (long long)w * h, (long long)w, h, n0,
+                                                          nullptr, nullptr);
+    return 1;
+}
+
+int launch_edt_z(const uint32_t *gy, int w, int h, int d, uint32_t n0, uint32_t *sq, uint8_t *present,
+                 uint32_t *maxval, cudaStream_t s) {
+    const long long nlines = (long long)w * h;
+    const unsigned grid = (unsigned)((nlines + 255) / 256);
+    edt_line_kernel<uint32_t, true><<<grid, 256, 0, s>>>(gy, sq, w, nlines, (long long)w, (long long)w * h, d, n0,
+                                                         present, maxval);
+    return 1;
+}
+
+}  // namespace bjt

@@ -1,0 +1,160 @@
+// ridge.cu -- distance-ridge extraction on the squared EDT, sm_100a.
+//
+// Replaces sc.fiji.localThickness.Distance_Ridge (run / createTemplate / scanCube).
+// A foreground voxel p is dropped when an in-image 26-neighbour q (c = number of non-zero offset
+// components) has sq(q) >= T_c[sq(p)], where T_c[r^2] is the smallest squared radius of a grid
+// ball centred one step away (c components) that contains the grid ball of radius^2 r^2 at p.
+// Works on the integer squared map directly (the Java code recovers the same integers from its
+// float sqrt map via (int)(v*v+0.5f)).
+#include "common.cuh"
+
+namespace bjt {
+
+// ---- distinct r^2 values ----------------------------------------------------------------------
+__global__ void collect_values_kernel(const uint8_t *__restrict__ present, uint32_t vmax, uint32_t *__restrict__ values,
+                                      uint32_t *__restrict__ count) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = v <= vmax && v > 0 && present[v];
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, on);
+    if (!ballot) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(ballot));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (on) values[base + __popc(ballot & ((1u << lane) - 1u))] = v;
+}
+
+int launch_collect_values(const uint8_t *present, uint32_t vmax, uint32_t *values, uint32_t *count, cudaStream_t s) {
+    const unsigned grid = (unsigned)(((size_t)vmax + 1 + 255) / 256);
+    collect_values_kernel<<<grid, 256, 0, s>>>(present, vmax, values, count);
+    return 1;
+}
+
+__global__ void mark_present_kernel(const uint32_t *__restrict__ sq, size_t n, uint8_t *__restrict__ present,
+                                    uint32_t *__restrict__ maxval) {
+    uint32_t tmax = 0, prev = 0xFFFFFFFFu;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t v = sq[i];
+        if (present && v != prev) { present[v] = 1; prev = v; }
+        tmax = max(tmax, v);
+    }
+    tmax = __reduce_max_sync(0xFFFFFFFFu, tmax);
+    if ((threadIdx.x & 31) == 0 && tmax) atomicMax(maxval, tmax);
+}
+
+int launch_mark_present(const uint32_t *sq, size_t n, uint8_t *present, uint32_t *maxval, cudaStream_t s) {
+    const unsigned grid = (unsigned)min((size_t)148 * 16, (n + 255) / 256);
+    mark_present_kernel<<<grid ? grid : 1, 256, 0, s>>>(sq, n, present, maxval);
+    return 1;
+}
+
+// ---- template (scanCube): one block per distinct value ------------------------------------------
+// T_c[r^2] = max over k,j >= 0 with k^2+j^2 <= r^2 of (k+dz)^2 + (j+dy)^2 + (floor(sqrt(r^2-k^2-j^2))+dx)^2
+template <bool COMPACT>
+__global__ void __launch_bounds__(128) ridge_template_kernel(const uint32_t *__restrict__ values, uint32_t nvalues,
+                                                             uint32_t *__restrict__ t1, uint32_t *__restrict__ t2,
+                                                             uint32_t *__restrict__ t3) {
+    const uint32_t vi = blockIdx.x;
+    if (vi >= nvalues) return;
+    const uint32_t rsq = values[vi];
+    const uint32_t r = isqrt_floor(rsq);      // k, j beyond floor(sqrt) never satisfy k^2+j^2 <= r^2
+    const uint32_t side = r + 1;
+    uint32_t m1 = 0, m2 = 0, m3 = 0;
+    for (uint32_t idx = threadIdx.x; idx < side * side; idx += blockDim.x) {
+        const uint32_t k = idx / side, j = idx % side;
+        const uint32_t kj = k * k + j * j;
+        if (kj <= rsq) {
+            const uint32_t i1 = isqrt_floor(rsq - kj) + 1u;          // dx = 1 in all three templates
+            const uint32_t i1sq = i1 * i1;
+            m1 = max(m1, k * k + j * j + i1sq);                       // (1,0,0)
+            m2 = max(m2, k * k + (j + 1u) * (j + 1u) + i1sq);         // (1,1,0)
+            m3 = max(m3, (k + 1u) * (k + 1u) + (j + 1u) * (j + 1u) + i1sq);   // (1,1,1)
+        }
+    }
+    __shared__ uint32_t sm[3];
+    if (threadIdx.x < 3) sm[threadIdx.x] = 0;
+    __syncthreads();
+    m1 = __reduce_max_sync(0xFFFFFFFFu, m1);
+    m2 = __reduce_max_sync(0xFFFFFFFFu, m2);
+    m3 = __reduce_max_sync(0xFFFFFFFFu, m3);
+    if ((threadIdx.x & 31) == 0) { atomicMax(&sm[0], m1); atomicMax(&sm[1], m2); atomicMax(&sm[2], m3); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t o = COMPACT ? vi : rsq;
+        t1[o] = sm[0]; t2[o] = sm[1]; t3[o] = sm[2];
+    }
+}
+
+int launch_ridge_template(const uint32_t *values, uint32_t nvalues, uint32_t *t1, uint32_t *t2, uint32_t *t3,
+                          cudaStream_t s) {
+    if (!nvalues) return 0;
+    ridge_template_kernel<false><<<nvalues, 128, 0, s>>>(values, nvalues, t1, t2, t3);
+    return 1;
+}
+int launch_ridge_template_compact(const uint32_t *values, uint32_t nvalues, uint32_t *t1, uint32_t *t2,
+                                  uint32_t *t3, cudaStream_t s) {
+    if (!nvalues) return 0;
+    ridge_template_kernel<true><<<nvalues, 128, 0, s>>>(values, nvalues, t1, t2, t3);
+    return 1;
+}
+
+// ---- ridge test ------------------------------------------------------------------------------------
+// Block = 32 x 8 x 4 voxels; the (34 x 10 x 6) halo tile of sq is staged in shared memory so every
+// neighbour read is an LDS.  Out-of-image halo cells hold 0 (0 never reaches a threshold, T_c > r^2 >= 1).
+constexpr int RTX = 32, RTY = 8, RTZ = 4;
+
+__global__ void __launch_bounds__(RTX *RTY *RTZ) ridge_kernel(const uint32_t *__restrict__ sq, int w, int h, int d,
+                                                              const uint32_t *__restrict__ t1,
+                                                              const uint32_t *__restrict__ t2,
+                                                              const uint32_t *__restrict__ t3,
+                                                              uint32_t *__restrict__ ridge,
+                                                              unsigned long long *__restrict__ count) {
+    __shared__ uint32_t tile[RTZ + 2][RTY + 2][RTX + 2];
+    const int bx = blockIdx.x * RTX, by = blockIdx.y * RTY, bz = blockIdx.z * RTZ;
+    const int tid = threadIdx.x + RTX * (threadIdx.y + RTY * threadIdx.z);
+    const size_t wh = (size_t)w * h;
+    for (int i = tid; i < (RTZ + 2) * (RTY + 2) * (RTX + 2); i += RTX * RTY * RTZ) {
+        const int lx = i % (RTX + 2), ly = (i / (RTX + 2)) % (RTY + 2), lz = i / ((RTX + 2) * (RTY + 2));
+        const int gx = bx + lx - 1, gy = by + ly - 1, gz = bz + lz - 1;
+        uint32_t v = 0;
+        if (gx >= 0 && gx < w && gy >= 0 && gy < h && gz >= 0 && gz < d) v = __ldg(sq + gz * wh + (size_t)gy * w + gx);
+        tile[lz][ly][lx] = v;
+    }
+    __syncthreads();
+    const int x = bx + threadIdx.x, y = by + threadIdx.y, z = bz + threadIdx.z;
+    bool is_ridge = false;
+    uint32_t v = 0;
+    if (x < w && y < h && z < d) {
+        const int lx = threadIdx.x + 1, ly = threadIdx.y + 1, lz = threadIdx.z + 1;
+        v = tile[lz][ly][lx];
+        if (v > 0) {
+            const uint32_t th[3] = {__ldg(t1 + v), __ldg(t2 + v), __ldg(t3 + v)};
+            bool keep = true;
+#pragma unroll
+            for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int c = (dx != 0) + (dy != 0) + (dz != 0);
+                        if (c == 0) continue;
+                        if (tile[lz + dz][ly + dy][lx + dx] >= th[c - 1]) keep = false;
+                    }
+            is_ridge = keep;
+        }
+        ridge[z * wh + (size_t)y * w + x] = is_ridge ? v : 0u;
+    }
+    // block count of ridge points
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, is_ridge);
+    if ((tid & 31) == 0 && ballot) atomicAdd(count, (unsigned long long)__popc(ballot));
+}
+
+int launch_ridge(const uint32_t *sq, int w, int h, int d, const uint32_t *t1, const uint32_t *t2, const uint32_t *t3,
+                 uint32_t *ridge, unsigned long long *count, cudaStream_t s) {
+    dim3 grid((w + RTX - 1) / RTX, (h + RTY - 1) / RTY, (d + RTZ - 1) / RTZ);
+    dim3 block(RTX, RTY, RTZ);
+    ridge_kernel<<<grid, block, 0, s>>>(sq, w, h, d, t1, t2, t3, ridge, count);
+    return 1;
+}
+
+}  // namespace bjt

@@ -1,0 +1,130 @@
+/*
+ * bonej_thickness.h -- C-ABI of libbonejthickness.so, the B200 (sm_100a) implementation of the
+ * hot path behind BoneJ's `Plugins > BoneJ > Thickness` command.
+ *
+ * The boundary.  The reference has no FFI: ThicknessWrapper.createMap()
+ * (Modern/wrapperPlugins/src/main/java/org/bonej/wrapperPlugins/ThicknessWrapper.java:190-196)
+ * calls sc.fiji.localThickness.LocalThicknessWrapper.processImage(ImagePlus) and
+ * ThicknessWrapper.addMapResults() (:158-180) reads ij.process.StackStatistics mean/stdDev/max.
+ * The entry points below are what a JNI shim for that seam binds (see INTEGRATION.md and
+ * java/): plain pointers and sizes, no CUDA / torch types.  Volumes are [z][y][x], x fastest --
+ * the same byte order as the per-slice Java arrays (ImageStack.getPixels(z+1)) laid end to end
+ * and as DatasetUtil raw files (Modern/utilities/.../DatasetUtil.java:293-311).
+ *
+ * All functions return BJT_OK (0) or a negative BJT_E_* code; bjt_last_error() gives the text.
+ * There is no CPU fallback: without a usable CUDA device every compute entry point fails.
+ */
+#ifndef BONEJ_THICKNESS_H
+#define BONEJ_THICKNESS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BJT_OK            0
+#define BJT_E_CUDA       -1   /* CUDA runtime error (no device, launch failure, out of memory)   */
+#define BJT_E_ARG        -2   /* bad argument (null pointer, non-positive size, volume too large) */
+#define BJT_E_NOT_BINARY -3   /* input is not a 0/255 image: processImage() would return null     */
+#define BJT_E_INTERNAL   -4   /* capacity fallback exhausted (should not happen)                  */
+
+typedef struct bjt_ctx bjt_ctx;
+
+/* ij.process.StackStatistics as consumed at ThicknessWrapper.java:158-180: statistics over the
+ * non-NaN voxels of the calibrated map.  sd uses n-1 and is 0 when the numerator is <= 0.
+ * count == 0 is what the wrapper turns into NaN / NaN / NaN. */
+typedef struct bjt_stats {
+    int64_t count;
+    double  mean, sd, min, max;
+    double  sum, sum2;
+} bjt_stats;
+
+/* Per-stage device times (CUDA events on the context's stream), filled when a non-NULL pointer
+ * is passed.  ms_total covers upload .. download for the host entry points. */
+typedef struct bjt_timing {
+    float   ms_h2d, ms_edt_x, ms_edt_y, ms_edt_z, ms_ridge, ms_paint, ms_cleanup, ms_finish, ms_d2h, ms_total;
+    int64_t n_ridge;        /* distance-ridge points painted                                */
+    int64_t n_launches;     /* kernels of this library launched by the call                 */
+    uint32_t rsq_max;       /* largest squared EDT value                                    */
+    int32_t paint_path;     /* 0 = separable (16-bit items), 1 = separable (32-bit items),
+                               2 = brute-force scatter, 3 = constant fast path (no background) */
+} bjt_timing;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int  bjt_create(bjt_ctx **out, int device);            /* device < 0: current CUDA device        */
+void bjt_destroy(bjt_ctx *ctx);
+const char *bjt_last_error(const bjt_ctx *ctx);        /* ctx may be NULL (creation failures)    */
+int  bjt_set_stream(bjt_ctx *ctx, void *cuda_stream);  /* cudaStream_t; NULL = default stream    */
+int  bjt_release_workspace(bjt_ctx *ctx);              /* free cached device buffers             */
+int  bjt_device_info(bjt_ctx *ctx, char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor);
+/* paint_path override for tests: -1 automatic (default), 0/1/2 force that path */
+int  bjt_set_paint_path(bjt_ctx *ctx, int path);
+/* page-locked host memory (what a JNI direct ByteBuffer / the bench wraps so copies are DMA) */
+void *bjt_host_alloc(size_t bytes);
+void  bjt_host_free(void *p);
+
+/* ---- the seam: LocalThicknessWrapper.processImage + StackStatistics, HOST buffers ------------ *
+ * in       u8 [d][h][w], must contain only 0 and 255 (else BJT_E_NOT_BINARY)
+ * inverse  0 = Tb.Th (foreground), 1 = Tb.Sp (background)   (ThicknessWrapper.java:217-222)
+ * mask     maskArtefacts -> MaskThicknessMapWithOriginal      (ThicknessWrapper.java:186)
+ * threshold 128 in the reference; pixel_width = calibration.pixelWidth (calibratePixels = true)
+ * out_map  f32 [d][h][w], NaN background, calibrated units; may be NULL (showMaps = false)     */
+int bjt_thickness_u8(bjt_ctx *ctx, const uint8_t *in, int w, int h, int d, int inverse, int mask,
+                     int threshold, double pixel_width, float *out_map, bjt_stats *stats,
+                     bjt_timing *timing);
+
+/* Same, for Java's one-array-per-slice stacks: d pointers to w*h bytes / floats each. */
+int bjt_thickness_u8_slices(bjt_ctx *ctx, const uint8_t *const *in_slices, int w, int h, int d,
+                            int inverse, int mask, int threshold, double pixel_width,
+                            float *const *out_slices, bjt_stats *stats, bjt_timing *timing);
+
+/* mapChoice = "Both": one upload, the foreground run then the inverted run
+ * (ThicknessWrapper.java:127-134).  Outputs may be NULL individually. */
+int bjt_thickness_both_u8(bjt_ctx *ctx, const uint8_t *in, int w, int h, int d, int mask,
+                          int threshold, double pixel_width, float *out_th, float *out_sp,
+                          bjt_stats *stats_th, bjt_stats *stats_sp, bjt_timing *timing_th,
+                          bjt_timing *timing_sp);
+
+/* ---- device-resident variant (inputs / outputs already in HBM; bench `value`, sharded runs) -- */
+int bjt_dev_thickness_u8(bjt_ctx *ctx, const uint8_t *d_in, int w, int h, int d, int inverse,
+                         int mask, int threshold, double pixel_width, float *d_out_map,
+                         bjt_stats *stats, bjt_timing *timing);
+
+/* ---- stage-level entry points, HOST buffers (parity tests against the oracle) ---------------- */
+/* EDT_S1D before its sqrt pass: uint32 squared distance, background -> 0, sentinel 3(n+1)^2   */
+int bjt_edt_sq_u8(bjt_ctx *ctx, const uint8_t *in, int w, int h, int d, int inverse, int threshold,
+                  uint32_t *out_sq);
+/* Distance_Ridge on the squared map: r^2 at ridge points, 0 elsewhere */
+int bjt_ridge_u32(bjt_ctx *ctx, const uint32_t *sq, int w, int h, int d, uint32_t *out_ridge);
+/* Distance_Ridge.createTemplate / scanCube for a list of r^2 values */
+int bjt_ridge_template(bjt_ctx *ctx, const int32_t *rsq_values, int n, int32_t *t1, int32_t *t2, int32_t *t3);
+/* Local_Thickness_Parallel before its sqrt: painted max r^2 per voxel; path as bjt_timing.paint_path (-1 auto) */
+int bjt_paint_rsq(bjt_ctx *ctx, const uint32_t *ridge, int w, int h, int d, int path, uint32_t *out_rsq);
+/* 2*sqrt + Clean_Up_Local_Thickness (+ mask if original != NULL) + 0->NaN, x pixel_width (if calibrate) */
+int bjt_cleanup_f32(bjt_ctx *ctx, const uint32_t *rsq, const uint8_t *original, int w, int h, int d,
+                    int inverse, int calibrate, double pixel_width, float *out_map, bjt_stats *stats);
+int bjt_stats_f32(bjt_ctx *ctx, const float *map, size_t n, bjt_stats *stats);
+
+/* ---- stage-level entry points, DEVICE buffers (z-slab sharded orchestration, profiling) ------- *
+ * n_sentinel is max(w,h,d) of the WHOLE volume (a slab passes the global value).               */
+int bjt_dev_edt_x(bjt_ctx *ctx, const uint8_t *d_in, int w, int h, int d, int inverse, int threshold,
+                  uint16_t *d_gx);
+int bjt_dev_edt_y(bjt_ctx *ctx, const uint16_t *d_gx, int w, int h, int d, int n_sentinel, uint32_t *d_gy);
+int bjt_dev_edt_z(bjt_ctx *ctx, const uint32_t *d_gy, int w, int h, int d, int n_sentinel, uint32_t *d_sq);
+int bjt_dev_ridge(bjt_ctx *ctx, const uint32_t *d_sq, int w, int h, int d, uint32_t *d_ridge);
+int bjt_dev_paint(bjt_ctx *ctx, const uint32_t *d_ridge, int w, int h, int d, int path, uint32_t *d_rsq);
+int bjt_dev_finish(bjt_ctx *ctx, const uint32_t *d_rsq, const uint8_t *d_original, int w, int h, int d,
+                   int inverse, int calibrate, double pixel_width, float *d_out, bjt_stats *stats);
+
+/* ---- synthetic trabecular phantom (workload of BASELINE.json) ------------------- */
+/* shapes: n records of 16 int32 (bonej2_b200/phantom.py); out: u8 [d][h][w] in {0,255}          */
+int bjt_phantom_u8(bjt_ctx *ctx, const int32_t *shapes, int nshapes, int w, int h, int d, uint8_t *out);
+int bjt_dev_phantom_u8(bjt_ctx *ctx, const int32_t *shapes_host, int nshapes, int w, int h, int d,
+                       int z0, int dz, uint8_t *d_out);   /* rasterise slices [z0, z0+dz) of the volume */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BONEJ_THICKNESS_H */
