@@ -246,24 +246,42 @@ static int dev_ridge_full(bjt_ctx *c, const uint32_t *sq, int w, int h, int d, u
 }
 
 static int dev_paint(bjt_ctx *c, const uint32_t *ridge, int w, int h, int d, int path, int64_t n_ridge_known,
-                     uint32_t *rsq, int *path_used) {
+                     int64_t max_r, uint32_t *rsq, int *path_used) {
     const size_t N = (size_t)w * h * d;
     if (path < 0) path = c->paint_path;
-    if (path < 0) path = 0;
-    // separable painter: 16-bit items, then 32-bit items, then the scatter fallback
-    for (; path <= 1; ++path) {
-        uint32_t *scal; void *wsp;
-        const size_t wb = paint_sep_workspace_bytes(w, h, d, path);
-        if (wb == 0) continue;                       // this variant cannot represent the volume
+    const bool forced = path >= 0;
+    if (path <= 1) {
+        uint32_t *scal;
         WS("scalars", 256, scal);
-        WS("paint_sep", wb, wsp);
-        CK(cudaMemsetAsync(scal + 8, 0, 4, c->stream));
-        c->launches += launch_paint_sep(ridge, w, h, d, path, wsp, rsq, scal + 8, c->stream); CKL();
-        CK(cudaMemcpyAsync(c->h_scal + 8, scal + 8, 4, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        if (c->h_scal[8] == 0) { if (path_used) *path_used = path; return BJT_OK; }
-        if (c->paint_path >= 0 && c->paint_path == path)
-            return fail(c, BJT_E_INTERNAL, "separable painter (path %d) overflowed its lists (flag %u)", path, c->h_scal[8]);
+        if (max_r < 0) {   // largest tag decides whether items fit 16+16 bits
+            CK(cudaMemsetAsync(scal + 14, 0, 4, c->stream));
+            c->launches += launch_mark_present(ridge, N, nullptr, scal + 14, c->stream); CKL();
+            CK(cudaMemcpyAsync(c->h_scal + 14, scal + 14, 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            max_r = c->h_scal[14];
+        }
+        int wide = max_r >= 65536 ? 1 : 0;
+        if (forced && path == 0 && wide) return fail(c, BJT_E_ARG, "paint path 0 needs r^2 < 65536 (largest is %lld)", (long long)max_r);
+        if (forced && path == 1) wide = 1;
+        // small capacities first, then the large variant; list overflow is detected, never silent
+        for (int big = 0; big <= 1; ++big) {
+            const int variant = wide | (big << 1);
+            const size_t wb = paint_sep_workspace_bytes(w, h, d, variant);
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            size_t have = 0;
+            { auto it = c->bufs.find("paint_sep"); if (it != c->bufs.end()) have = it->second.cap; }
+            if (wb > have && wb - have + ((size_t)1 << 30) > free_b) continue;    // does not fit: next option
+            void *wsp;
+            WS("paint_sep", wb, wsp);
+            CK(cudaMemsetAsync(scal + 8, 0, 4, c->stream));
+            c->launches += launch_paint_sep(ridge, w, h, d, variant, wsp, rsq, scal + 8, c->stream); CKL();
+            CK(cudaMemcpyAsync(c->h_scal + 8, scal + 8, 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            if (c->h_scal[8] == 0) { if (path_used) *path_used = wide; return BJT_OK; }
+        }
+        if (forced)
+            return fail(c, BJT_E_INTERNAL, "separable painter (path %d) overflowed its lists (flags %u)", path, c->h_scal[8]);
     }
     // scatter
     {
@@ -348,7 +366,7 @@ static int dev_pipeline(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, in
         rc = dev_ridge(c, bufB, w, h, d, maxval, present, bufA, &n_ridge);
         if (rc) return rc;
         CK(cudaEventRecord(c->ev[4], c->stream));
-        rc = dev_paint(c, bufA, w, h, d, -1, n_ridge, bufB, &path_used);
+        rc = dev_paint(c, bufA, w, h, d, -1, n_ridge, (int64_t)maxval, bufB, &path_used);
         if (rc) return rc;
         CK(cudaEventRecord(c->ev[5], c->stream));
     }
@@ -527,7 +545,7 @@ int bjt_paint_rsq(bjt_ctx *c, const uint32_t *ridge, int w, int h, int d, int pa
     CK(cudaMemcpyAsync(bufA, ridge, N * 4, cudaMemcpyHostToDevice, c->stream));
     const int saved = c->paint_path;
     if (path >= 0) c->paint_path = path;
-    rc = dev_paint(c, bufA, w, h, d, path, -1, bufB, nullptr);
+    rc = dev_paint(c, bufA, w, h, d, path, -1, -1, bufB, nullptr);
     c->paint_path = saved;
     if (rc) return rc;
     CK(cudaMemcpyAsync(out_rsq, bufB, N * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -612,7 +630,7 @@ int bjt_dev_paint(bjt_ctx *c, const uint32_t *d_ridge, int w, int h, int d, int 
     if (rc) return rc;
     const int saved = c->paint_path;
     if (path >= 0) c->paint_path = path;
-    rc = dev_paint(c, d_ridge, w, h, d, path, -1, d_rsq, nullptr);
+    rc = dev_paint(c, d_ridge, w, h, d, path, -1, -1, d_rsq, nullptr);
     c->paint_path = saved;
     return rc;
 }

@@ -1,6 +1,344 @@
-// paint_sep.cu -- separable largest-inscribed-sphere painter (placeholder until the real one lands)
+// paint_sep.cu -- separable largest-inscribed-sphere painter (paths 0 and 1), sm_100a.
+//
+// Replaces the scatter of sc.fiji.localThickness.Local_Thickness_Parallel with an
+// exact axis-by-axis propagation: out(p) = max{ R_q : |p-q|^2 <= R_q } over ridge points q.  The
+// per-line algorithm is in paint_sep_core.cuh (shared with the CPU model
+// oracle/sep_paint_model.cpp that tests it without a GPU).  Cost is O(N * front size) instead of
+// the sum of ball volumes.
+//
+// Layout.  One thread per line, 32 adjacent lines per warp, every lane at the same position of its
+// line, so a warp moves through the volume as a plane front.  Fronts are variable-length lists:
+// per voxel one u64 index entry (offset:40 | count:24) into an item pool; a warp allocates the
+// items of one step with a single atomicAdd (shuffle prefix sum), so items of neighbouring lines
+// are neighbours in the pool.  Forward and backward fronts are kept as two lists; the next stage
+// reads both.
+//   stage 1  lines along x (thread per row), whole volume            ridge -> L1F, L1B
+//   stage 2  lines along y, lanes along x, per x-slab of XC columns   L1  -> L2F, L2B (slab-local)
+//   stage 3  lines along z, lanes along x, same slab                  L2  -> painted r^2 (coalesced)
+// Items are (slack, R).  PACKED: u32 = R << 16 | slack when the largest r^2 is below 65536;
+// otherwise u64.
+//
+// Capacities.  The fast kernels keep a line's active set in the thread's local frame (CAP items).
+// Lines that need more (a few, in very large pores) are recorded and redone by a second kernel
+// whose active sets live in a strided global scratch (CAP_BIG items, NSLOTS lines at a time).
+// Anything beyond that, or a full pool, raises a flag and the caller falls back to the scatter.
 #include "common.cuh"
+#include "paint_sep_core.cuh"
+
 namespace bjt {
-size_t paint_sep_workspace_bytes(int, int, int, int) { return 0; }
-int launch_paint_sep(const uint32_t *, int, int, int, int, void *, uint32_t *, uint32_t *, cudaStream_t) { return 0; }
+
+namespace {
+
+constexpr int XC = 256;                 // x-slab width of stages 2 and 3
+constexpr unsigned long long OFF_MASK = (1ull << 40) - 1ull;
+constexpr int CAP_FAST = 320, FMAX_FAST = 128, CAP_STAIR_FAST = 64;
+constexpr int CAP_BIG = 4096, FMAX_BIG = 1024, NSLOTS = 1024;
+
+enum : uint32_t { F_POOL1 = 1u, F_POOL2 = 2u, F_ACTIVE = 4u, F_FRONT = 8u };
+
+template <bool PACKED> struct ItemIO;
+template <> struct ItemIO<true> {
+    typedef uint32_t T;
+    static __device__ __forceinline__ T pack(SepItem it) { return (it.R << 16) | it.rho; }
+    static __device__ __forceinline__ SepItem get(const T *p, int k) {
+        const T v = __ldg(p + k);
+        SepItem it; it.rho = v & 0xFFFFu; it.R = v >> 16; return it;
+    }
+};
+template <> struct ItemIO<false> {
+    typedef uint2 T;
+    static __device__ __forceinline__ T pack(SepItem it) { return make_uint2(it.rho, it.R); }
+    static __device__ __forceinline__ SepItem get(const T *p, int k) {
+        const T v = __ldg(p + k);
+        SepItem it; it.rho = v.x; it.R = v.y; return it;
+    }
+};
+struct PlainIO { static __device__ __forceinline__ SepItem get(const SepItem *p, int k) { return p[k]; } };
+
+// warp-aggregated append of nf items per lane; returns the lane's offset or ~0 on pool overflow
+__device__ __forceinline__ unsigned long long warp_alloc(int nf, unsigned long long *counter, unsigned long long cap,
+                                                         uint32_t *flags, uint32_t flagbit) {
+    const int lane = threadIdx.x & 31;
+    int incl = nf;
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) {
+        const int u = __shfl_up_sync(0xFFFFFFFFu, incl, k);
+        if (lane >= k) incl += u;
+    }
+    const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (total == 0) return 0ull;
+    unsigned long long base = 0ull;
+    if (lane == 0) base = atomicAdd(counter, (unsigned long long)total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base + (unsigned long long)total > cap) {
+        if (lane == 0) atomicOr(flags, flagbit);
+        return ~0ull;
+    }
+    return base + (unsigned long long)(incl - nf);
 }
+
+struct SepArgs {
+    // stage 1 input
+    const uint32_t *ridge;
+    // stage 2/3 input lists
+    const unsigned long long *inF, *inB;
+    const void *in_pool;
+    // geometry
+    int w, h, d;            // whole volume
+    int xc0, xw;            // x-slab (stages 2, 3)
+    int dir;
+    // stage 1/2 output lists
+    unsigned long long *out_idx;
+    void *out_pool;
+    unsigned long long out_cap;
+    unsigned long long *out_counter;
+    uint32_t poolflag;
+    // stage 3 output
+    uint32_t *out;
+    // bookkeeping
+    uint32_t *flags;
+    int *redo_list;          // lines whose fast capacities were too small
+    int *redo_count;
+    uint32_t *scratch;       // strided stores of the redo kernels
+};
+
+// one line of stage 1 (STAGE == 1: line = row (y,z), position = x) or stage 2 (line = (lx, z), position = y).
+// All 32 lanes of the warp must call this together (warp-aggregated allocation); `valid` masks lanes.
+template <bool PACKED, int STAGE, class Active>
+__device__ __forceinline__ bool dyn_line(const SepArgs &a, long long line, bool valid, Active &A, SepItem *fr, int fmax) {
+    typedef ItemIO<PACKED> IO;
+    const int L = STAGE == 1 ? a.w : a.h;
+    long long in_base = 0, in_stride = 0, out_base = 0, out_stride = 0;
+    if (STAGE == 1) {
+        in_base = line * a.w; in_stride = 1;
+        out_base = in_base; out_stride = 1;
+    } else {
+        const int lx = (int)(line % a.xw);
+        const long long z = line / a.xw;
+        in_base = z * a.h * (long long)a.w + a.xc0 + lx; in_stride = a.w;
+        out_base = z * a.h * (long long)a.xw + lx; out_stride = a.xw;
+    }
+    A.clear();
+    bool ok = true;
+    const typename IO::T *ipool = reinterpret_cast<const typename IO::T *>(a.in_pool);
+    typename IO::T *opool = reinterpret_cast<typename IO::T *>(a.out_pool);
+    for (int step = 0; step < L; ++step) {
+        const int t = a.dir > 0 ? step : L - 1 - step;
+        int nf = 0;
+        if (valid) {
+            const long long vi = in_base + (long long)t * in_stride;
+            if (STAGE == 1) {
+                const uint32_t r = __ldg(a.ridge + vi);
+                if (r | (uint32_t)A.n) {
+                    SepItem one; one.rho = r; one.R = r;
+                    nf = A.template step<SepItem, PlainIO>(t, a.dir, a.dir < 0, &one, r ? 1 : 0, (const SepItem *)nullptr, 0, fr, fmax, ok);
+                }
+            } else {
+                const unsigned long long eF = __ldg(a.inF + vi), eB = __ldg(a.inB + vi);
+                if (eF | eB | (unsigned long long)A.n)
+                    nf = A.template step<typename IO::T, IO>(t, a.dir, a.dir < 0, ipool + (eF & OFF_MASK), (int)(eF >> 40),
+                                                             ipool + (eB & OFF_MASK), (int)(eB >> 40), fr, fmax, ok);
+            }
+            if (nf > fmax) { ok = false; nf = fmax; }
+        }
+        const unsigned long long off = warp_alloc(nf, a.out_counter, a.out_cap, a.flags, a.poolflag);
+        if (valid) {
+            unsigned long long entry = 0ull;
+            if (nf > 0 && off != ~0ull) {
+                for (int k = 0; k < nf; ++k) opool[off + k] = IO::pack(fr[k]);
+                entry = off | ((unsigned long long)nf << 40);
+            }
+            a.out_idx[out_base + (long long)t * out_stride] = entry;
+        }
+    }
+    return ok;
+}
+
+// one line of stage 3: line = (lx, y), position = z
+template <bool PACKED, class Stair>
+__device__ __forceinline__ bool stair_line(const SepArgs &a, long long line, Stair &S) {
+    typedef ItemIO<PACKED> IO;
+    const int lx = (int)(line % a.xw);
+    const long long y = line / a.xw;
+    const long long in_base = y * a.xw + lx, in_stride = (long long)a.h * a.xw;
+    const long long out_base = y * a.w + a.xc0 + lx, out_stride = (long long)a.h * a.w;
+    const typename IO::T *ipool = reinterpret_cast<const typename IO::T *>(a.in_pool);
+    S.clear();
+    bool ok = true;
+    for (int step = 0; step < a.d; ++step) {
+        const int z = a.dir > 0 ? step : a.d - 1 - step;
+        const int u = a.dir > 0 ? z : -z;
+        const long long vi = in_base + (long long)z * in_stride;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const unsigned long long e = __ldg((which ? a.inB : a.inF) + vi);
+            const typename IO::T *p = ipool + (e & OFF_MASK);
+            const int cnt = (int)(e >> 40);
+            for (int k = 0; k < cnt; ++k) {
+                const SepItem it = IO::get(p, k);
+                ok &= S.arrive(u, it.rho, it.R);
+            }
+        }
+        const uint32_t r = S.query(u);
+        uint32_t *o = a.out + out_base + (long long)z * out_stride;
+        if (a.dir > 0) *o = r;
+        else if (r > *o) *o = r;
+    }
+    return ok;
+}
+
+__device__ __forceinline__ void record_redo(const SepArgs &a, long long line) {
+    const int slot = atomicAdd(a.redo_count, 1);
+    a.redo_list[slot] = (int)line;
+}
+
+template <bool PACKED, int STAGE>
+__global__ void __launch_bounds__(128) sep_dyn_kernel(SepArgs a) {
+    const long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nlines = STAGE == 1 ? (long long)a.h * a.d : (long long)a.xw * a.d;
+    const bool valid = line < nlines;
+    SepActive<SepLocalStore<CAP_FAST> > A;
+    SepItem fr[FMAX_FAST];
+    const bool ok = dyn_line<PACKED, STAGE>(a, line, valid, A, fr, FMAX_FAST);
+    if (valid && !ok) record_redo(a, line);
+}
+
+// redo: NSLOTS threads, each takes failed lines slot, slot + NSLOTS, ...
+template <bool PACKED, int STAGE>
+__global__ void __launch_bounds__(32) sep_dyn_redo_kernel(SepArgs a) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int count = *a.redo_count;
+    if (count == 0) return;
+    SepActive<SepStridedStore> A;
+    A.st.base = a.scratch + slot; A.st.capacity = CAP_BIG; A.st.stride = NSLOTS;
+    SepItem *fr = reinterpret_cast<SepItem *>(a.scratch + (size_t)NSLOTS * SepStridedStore::words_per_slot(CAP_BIG)) +
+                  (size_t)slot * FMAX_BIG;
+    for (int base = 0; base < count; base += NSLOTS) {      // warp-uniform trip count
+        const int idx = base + slot;
+        const bool valid = idx < count;
+        const long long line = valid ? a.redo_list[idx] : 0;
+        const bool ok = dyn_line<PACKED, STAGE>(a, line, valid, A, fr, FMAX_BIG);
+        if (valid && !ok) atomicOr(a.flags, (uint32_t)F_ACTIVE);
+    }
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(128) sep_stair_kernel(SepArgs a) {
+    const long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= (long long)a.xw * a.h) return;
+    SepStair<SepLocalStore<CAP_STAIR_FAST, 1, 2> > S;
+    if (!stair_line<PACKED>(a, line, S)) record_redo(a, line);
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(32) sep_stair_redo_kernel(SepArgs a) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int count = *a.redo_count;
+    SepStair<SepStridedStore> S;
+    S.st.base = a.scratch + slot; S.st.capacity = CAP_BIG; S.st.stride = NSLOTS;
+    for (int idx = slot; idx < count; idx += NSLOTS)
+        if (!stair_line<PACKED>(a, a.redo_list[idx], S)) atomicOr(a.flags, (uint32_t)F_ACTIVE);
+}
+
+struct Plan {
+    size_t n, nslab, maxlines;
+    size_t off_idx1f, off_idx1b, off_idx2f, off_idx2b, off_pool1, off_pool2, off_counters, off_redo, off_scratch, total;
+    unsigned long long cap1, cap2;
+};
+
+Plan make_plan(int w, int h, int d, int wide, int scale) {
+    Plan p;
+    p.n = (size_t)w * h * d;
+    const int xw = w < XC ? w : XC;
+    p.nslab = (size_t)xw * h * d;
+    const size_t l1 = (size_t)h * d, l2 = (size_t)xw * d, l3 = (size_t)xw * h;
+    p.maxlines = l1 > l2 ? (l1 > l3 ? l1 : l3) : (l2 > l3 ? l2 : l3);
+    const size_t isz = wide ? 8 : 4;
+    p.cap1 = (unsigned long long)p.n * (unsigned)(4 * scale) + 65536;      // items
+    p.cap2 = (unsigned long long)p.nslab * (unsigned)(12 * scale) + 65536;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    p.off_counters = take(256);
+    p.off_idx1f = take(p.n * 8); p.off_idx1b = take(p.n * 8);
+    p.off_idx2f = take(p.nslab * 8); p.off_idx2b = take(p.nslab * 8);
+    p.off_pool1 = take(p.cap1 * isz); p.off_pool2 = take(p.cap2 * isz);
+    p.off_redo = take(p.maxlines * sizeof(int));
+    p.off_scratch = take((size_t)NSLOTS * (SepStridedStore::words_per_slot(CAP_BIG) * 4 + (size_t)FMAX_BIG * sizeof(SepItem)));
+    p.total = o;
+    return p;
+}
+
+template <bool PACKED>
+int run_sep(const uint32_t *ridge, int w, int h, int d, const Plan &p, char *ws, uint32_t *rsq, uint32_t *flags,
+            cudaStream_t s) {
+    int launches = 0;
+    unsigned long long *counters = reinterpret_cast<unsigned long long *>(ws + p.off_counters);
+    int *redo_count = reinterpret_cast<int *>(counters + 4);
+    SepArgs base{};
+    base.w = w; base.h = h; base.d = d; base.flags = flags;
+    base.redo_list = reinterpret_cast<int *>(ws + p.off_redo); base.redo_count = redo_count;
+    base.scratch = reinterpret_cast<uint32_t *>(ws + p.off_scratch);
+    unsigned long long *idx1f = reinterpret_cast<unsigned long long *>(ws + p.off_idx1f);
+    unsigned long long *idx1b = reinterpret_cast<unsigned long long *>(ws + p.off_idx1b);
+    unsigned long long *idx2f = reinterpret_cast<unsigned long long *>(ws + p.off_idx2f);
+    unsigned long long *idx2b = reinterpret_cast<unsigned long long *>(ws + p.off_idx2b);
+    void *pool1 = ws + p.off_pool1, *pool2 = ws + p.off_pool2;
+    cudaMemsetAsync(counters, 0, 256, s);
+    const int T = 128;
+    // stage 1: both directions share pool 1
+    for (int dir = +1; dir >= -1; dir -= 2) {
+        SepArgs a = base;
+        a.ridge = ridge; a.xc0 = 0; a.xw = w; a.dir = dir;
+        a.out_idx = dir > 0 ? idx1f : idx1b; a.out_pool = pool1; a.out_cap = p.cap1; a.out_counter = counters;
+        a.poolflag = F_POOL1;
+        const long long nlines = (long long)h * d;
+        cudaMemsetAsync(redo_count, 0, 4, s);
+        sep_dyn_kernel<PACKED, 1><<<(unsigned)((nlines + T - 1) / T), T, 0, s>>>(a);
+        sep_dyn_redo_kernel<PACKED, 1><<<NSLOTS / 32, 32, 0, s>>>(a);
+        launches += 2;
+    }
+    for (int xc0 = 0; xc0 < w; xc0 += XC) {
+        const int xw = (w - xc0) < XC ? (w - xc0) : XC;
+        cudaMemsetAsync(counters + 1, 0, 8, s);
+        for (int dir = +1; dir >= -1; dir -= 2) {
+            SepArgs a = base;
+            a.inF = idx1f; a.inB = idx1b; a.in_pool = pool1; a.xc0 = xc0; a.xw = xw; a.dir = dir;
+            a.out_idx = dir > 0 ? idx2f : idx2b; a.out_pool = pool2; a.out_cap = p.cap2; a.out_counter = counters + 1;
+            a.poolflag = F_POOL2;
+            const long long nlines = (long long)xw * d;
+            cudaMemsetAsync(redo_count, 0, 4, s);
+            sep_dyn_kernel<PACKED, 2><<<(unsigned)((nlines + T - 1) / T), T, 0, s>>>(a);
+            sep_dyn_redo_kernel<PACKED, 2><<<NSLOTS / 32, 32, 0, s>>>(a);
+            launches += 2;
+        }
+        for (int dir = +1; dir >= -1; dir -= 2) {
+            SepArgs a = base;
+            a.inF = idx2f; a.inB = idx2b; a.in_pool = pool2; a.xc0 = xc0; a.xw = xw; a.dir = dir;
+            a.out = rsq;
+            const long long nlines = (long long)xw * h;
+            cudaMemsetAsync(redo_count, 0, 4, s);
+            sep_stair_kernel<PACKED><<<(unsigned)((nlines + T - 1) / T), T, 0, s>>>(a);
+            sep_stair_redo_kernel<PACKED><<<NSLOTS / 32, 32, 0, s>>>(a);
+            launches += 2;
+        }
+    }
+    return launches;
+}
+
+}  // namespace
+
+// variant: bit 0 = wide (u64) items, bit 1 = doubled pools
+size_t paint_sep_workspace_bytes(int w, int h, int d, int variant) {
+    return make_plan(w, h, d, variant & 1, (variant & 2) ? 2 : 1).total;
+}
+
+int launch_paint_sep(const uint32_t *ridge, int w, int h, int d, int variant, void *workspace, uint32_t *rsq,
+                     uint32_t *overflow_flag, cudaStream_t s) {
+    const int wide = variant & 1;
+    const Plan p = make_plan(w, h, d, wide, (variant & 2) ? 2 : 1);
+    char *ws = reinterpret_cast<char *>(workspace);
+    return wide ? run_sep<false>(ridge, w, h, d, p, ws, rsq, overflow_flag, s)
+                : run_sep<true>(ridge, w, h, d, p, ws, rsq, overflow_flag, s);
+}
+
+}  // namespace bjt

@@ -16,7 +16,8 @@ _SO = os.path.join(_HERE, "_build", "liblt_oracle.so")
 
 def build(force: bool = False) -> str:
     """Compile the oracle with gcc (oracle/Makefile)."""
-    srcs = [os.path.join(_HERE, f) for f in ("lt_oracle.c", "phantom_cpu.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("lt_oracle.c", "phantom_cpu.c", "sep_paint_model.cpp", "Makefile",
+                                              "../bonej2_b200/csrc/paint_sep_core.cuh")]
     stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
@@ -160,3 +161,24 @@ def phantom_raster(shapes_i32, w, h, d):
     out = np.empty((d, h, w), np.uint8)
     lib().lto_phantom_raster(_p(s, C.c_int32), int(s.shape[0]), w, h, d, _p(out, C.c_uint8))
     return out
+
+
+class _SpmStats(C.Structure):
+    _fields_ = [("overflow_act", C.c_long), ("overflow_front", C.c_long), ("max_active", C.c_long),
+                ("max_front", C.c_long), ("max_stair", C.c_long), ("items", (C.c_long * 2) * 2),
+                ("sum_active", C.c_double * 3), ("steps", C.c_long * 3)]
+
+
+def sep_paint_model(ridge_u32):
+    """CPU model of the separable painter (oracle/sep_paint_model.cpp, running the per-line code of
+    bonej2_b200/csrc/paint_sep_core.cuh): (painted r^2, stats dict)."""
+    r = _vol(ridge_u32, np.uint32)
+    d, h, w = r.shape
+    out = np.empty(r.shape, np.uint32)
+    st = _SpmStats()
+    rc = lib().spm_paint(_p(r, C.c_uint32), w, h, d, _p(out, C.c_uint32), C.byref(st))
+    info = dict(rc=rc, overflow_act=st.overflow_act, overflow_front=st.overflow_front, max_active=st.max_active,
+                max_front=st.max_front, max_stair=st.max_stair,
+                items_per_voxel=[[st.items[s][k] / r.size for k in range(2)] for s in range(2)],
+                mean_active=[st.sum_active[s] / max(1, st.steps[s]) for s in range(3)])
+    return out, info

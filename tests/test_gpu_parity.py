@@ -30,8 +30,14 @@ def _cmp_stats(g, o):
     if o.count == 0:
         assert math.isnan(g.mean)
         return
-    for f in ("mean", "sd", "min", "max"):
+    for f in ("mean", "min", "max"):
         assert math.isclose(getattr(g, f), getattr(o, f), rel_tol=RTOL, abs_tol=1e-12), f
+    # StackStatistics' one-pass sd = sqrt((n*sum2 - sum^2)/n/(n-1)) cancels catastrophically on a
+    # (near-)constant map: its own rounding noise is ~ sqrt(n * 2^-53) * mean, so below that
+    # level the reference value depends on its summation order.  Compare relative to the larger
+    # of sd and that noise floor.
+    noise = math.sqrt(max(o.count, 1) * 2.0 ** -52) * abs(o.mean)
+    assert abs(g.sd - o.sd) <= RTOL * abs(o.sd) + 4 * noise, "sd"
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
@@ -68,7 +74,7 @@ def test_stages(ctx, oracle, name, inverse):
     assert np.array_equal(rg_g > 0, rg_o > 0), "ridge set differs"
     assert np.array_equal(rg_g[rg_g > 0], sq[rg_g > 0])
     lt_o, rsq_o = oracle.paint(rg_o)
-    for path in (2, -1):
+    for path in (2, 0, 1, -1):
         assert np.array_equal(ctx.paint_rsq(rg_g, path=path), rsq_o), f"painted r^2 differs (path {path})"
     cl_o = oracle.cleanup(lt_o)
     cl_g, _ = ctx.cleanup(rsq_o, calibrate=False)
