@@ -29,13 +29,13 @@ class ThicknessError(RuntimeError):
 
 
 def sources():
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cpp")))
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a into the in-tree shared library (nvcc cross-compiles
     without a GPU)."""
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [HEADER]
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(_ROOT, "include", "*.h*"))
     stale = (not os.path.exists(SO_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in deps)
     if force or stale:
         nvcc = os.environ.get("NVCC", "nvcc")
