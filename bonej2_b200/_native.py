@@ -76,6 +76,7 @@ _SIGS = {
     "bjt_release_workspace": ([_VP], _I),
     "bjt_device_info": ([_VP, C.c_char_p, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)], _I),
     "bjt_set_paint_path": ([_VP, _I], _I),
+    "bjt_launch_count": ([_VP], C.c_int64),
     "bjt_host_alloc": ([C.c_size_t], _VP),
     "bjt_host_free": ([_VP], None),
     "bjt_thickness_u8": ([_VP, _VP, _I, _I, _I, _I, _I, _I, _D, _VP, C.POINTER(Stats), C.POINTER(Timing)], _I),
@@ -95,6 +96,7 @@ _SIGS = {
     "bjt_dev_ridge": ([_VP, _VP, _I, _I, _I, _VP], _I),
     "bjt_dev_paint": ([_VP, _VP, _I, _I, _I, _I, _VP], _I),
     "bjt_dev_finish": ([_VP, _VP, _VP, _I, _I, _I, _I, _I, _D, _VP, C.POINTER(Stats)], _I),
+    "bjt_dev_finish_range": ([_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _D, _VP, C.POINTER(Stats)], _I),
     "bjt_phantom_u8": ([_VP, _VP, _I, _I, _I, _I, _VP], _I),
     "bjt_dev_phantom_u8": ([_VP, _VP, _I, _I, _I, _I, _I, _I, _VP], _I),
 }
@@ -165,6 +167,10 @@ class Context:
     def set_paint_path(self, path: int):
         self._ck(lib().bjt_set_paint_path(self._h, int(path)))
 
+    def launch_count(self) -> int:
+        """kernels of this library launched through this context so far"""
+        return int(lib().bjt_launch_count(self._h))
+
     def release_workspace(self):
         self._ck(lib().bjt_release_workspace(self._h))
 
@@ -232,6 +238,28 @@ class Context:
         self._ck(lib().bjt_dev_thickness_u8(self._h, _ptr(d_in), w, h, d, int(inverse), int(mask), int(threshold),
                                             float(pixel_width), _ptr(d_out), C.byref(st), C.byref(tm)))
         return st, tm
+
+    # -- stage level, device pointers (ints); used by the z-slab sharded orchestration
+    def dev_edt_x(self, d_in, w, h, d, inverse, threshold, d_gx):
+        self._ck(lib().bjt_dev_edt_x(self._h, d_in, w, h, d, int(inverse), int(threshold), d_gx))
+
+    def dev_edt_y(self, d_gx, w, h, d, n_sentinel, d_gy):
+        self._ck(lib().bjt_dev_edt_y(self._h, d_gx, w, h, d, int(n_sentinel), d_gy))
+
+    def dev_edt_z(self, d_gy, w, h, d, n_sentinel, d_sq):
+        self._ck(lib().bjt_dev_edt_z(self._h, d_gy, w, h, d, int(n_sentinel), d_sq))
+
+    def dev_ridge(self, d_sq, w, h, d, d_ridge):
+        self._ck(lib().bjt_dev_ridge(self._h, d_sq, w, h, d, d_ridge))
+
+    def dev_paint(self, d_ridge, w, h, d, d_rsq, path=-1):
+        self._ck(lib().bjt_dev_paint(self._h, d_ridge, w, h, d, int(path), d_rsq))
+
+    def dev_finish_range(self, d_rsq, d_original, w, h, d, z_lo, z_hi, inverse, calibrate, pixel_width, d_out):
+        st = Stats()
+        self._ck(lib().bjt_dev_finish_range(self._h, d_rsq, d_original, w, h, d, int(z_lo), int(z_hi), int(inverse),
+                                            int(calibrate), float(pixel_width), d_out, C.byref(st)))
+        return st
 
     # -- stage level (host buffers)
     def edt_sq(self, vol_u8, inverse=False, threshold=128):

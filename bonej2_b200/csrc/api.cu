@@ -159,6 +159,8 @@ int bjt_device_info(bjt_ctx *c, char *name, int name_len, int *sm_count, int *cc
     return BJT_OK;
 }
 
+int64_t bjt_launch_count(const bjt_ctx *c) { return c ? c->launches : 0; }
+
 void *bjt_host_alloc(size_t bytes) {
     void *p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
@@ -307,15 +309,14 @@ static int dev_paint(bjt_ctx *c, const uint32_t *ridge, int w, int h, int d, int
     return BJT_OK;
 }
 
-static int dev_finish(bjt_ctx *c, const uint32_t *rsq, const uint8_t *d_original, int w, int h, int d, int inverse,
-                      int calibrate, double pixel_width, float *d_out, bjt_stats *stats) {
-    const size_t N = (size_t)w * h * d;
-    uint8_t *flags; StatsPartial *partials, *result;
-    const int np = finish_partials(w, h, d);
-    WS("flags", N, flags);
+static int dev_finish_range(bjt_ctx *c, const uint32_t *rsq, const uint8_t *d_original, int w, int h, int d, int z_lo,
+                            int z_hi, int inverse, int calibrate, double pixel_width, float *d_out, bjt_stats *stats) {
+    if (z_lo < 0 || z_hi > d || z_lo >= z_hi) return fail(c, BJT_E_ARG, "bad plane range [%d, %d) of %d", z_lo, z_hi, d);
+    StatsPartial *partials, *result;
+    const int np = finish_partials(w, h, z_hi - z_lo);
     WS("partials", (size_t)np * sizeof(StatsPartial), partials);
     WS("stats_result", sizeof(StatsPartial), result);
-    c->launches += launch_finish(rsq, d_original, w, h, d, inverse, calibrate, (float)pixel_width, flags, d_out,
+    c->launches += launch_finish(rsq, d_original, w, h, d, z_lo, z_hi, inverse, calibrate, (float)pixel_width, d_out,
                                  partials, np, result, c->stream); CKL();
     if (stats) {
         CK(cudaMemcpyAsync(c->h_stats, result, sizeof(StatsPartial), cudaMemcpyDeviceToHost, c->stream));
@@ -323,6 +324,11 @@ static int dev_finish(bjt_ctx *c, const uint32_t *rsq, const uint8_t *d_original
         stats_out(*c->h_stats, stats);
     }
     return BJT_OK;
+}
+
+static int dev_finish(bjt_ctx *c, const uint32_t *rsq, const uint8_t *d_original, int w, int h, int d, int inverse,
+                      int calibrate, double pixel_width, float *d_out, bjt_stats *stats) {
+    return dev_finish_range(c, rsq, d_original, w, h, d, 0, d, inverse, calibrate, pixel_width, d_out, stats);
 }
 
 // the whole chain on device buffers
@@ -641,6 +647,14 @@ int bjt_dev_finish(bjt_ctx *c, const uint32_t *d_rsq, const uint8_t *d_original,
     int rc = check_dims(c, w, h, d);
     if (rc) return rc;
     return dev_finish(c, d_rsq, d_original, w, h, d, inverse, calibrate, pixel_width, d_out, stats);
+}
+
+int bjt_dev_finish_range(bjt_ctx *c, const uint32_t *d_rsq, const uint8_t *d_original, int w, int h, int d, int z_lo,
+                         int z_hi, int inverse, int calibrate, double pixel_width, float *d_out, bjt_stats *stats) {
+    ENTER(c);
+    int rc = check_dims(c, w, h, d);
+    if (rc) return rc;
+    return dev_finish_range(c, d_rsq, d_original, w, h, d, z_lo, z_hi, inverse, calibrate, pixel_width, d_out, stats);
 }
 
 // ---- phantom ---------------------------------------------------------------------------------------

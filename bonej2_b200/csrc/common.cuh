@@ -65,10 +65,11 @@ int launch_paint_sep(const uint32_t *ridge, int w, int h, int d, int wide, void 
                      uint32_t *overflow_flag, cudaStream_t s);
 
 // 2*sqrt + cleanup + mask + NaN/calibrate + stats
-int launch_finish(const uint32_t *rsq, const uint8_t *original, int w, int h, int d, int inverse, int calibrate,
-                  float pixel_width, uint8_t *flags, float *out, StatsPartial *partials, int npartials,
+// output / statistics restricted to planes [z_lo, z_hi) of the local volume; `out` starts at plane z_lo
+int launch_finish(const uint32_t *rsq, const uint8_t *original, int w, int h, int d, int z_lo, int z_hi, int inverse,
+                  int calibrate, float pixel_width, float *out, StatsPartial *partials, int npartials,
                   StatsPartial *result, cudaStream_t s);
-int finish_partials(int w, int h, int d);
+int finish_partials(int w, int h, int nz);
 int launch_stats(const float *map, size_t n, StatsPartial *partials, int npartials, StatsPartial *result,
                  cudaStream_t s);
 int launch_check_binary(const uint8_t *in, size_t n, uint32_t *bad, cudaStream_t s);

@@ -223,7 +223,109 @@ __global__ void __launch_bounds__(256) edt_line_kernel(const TIn *__restrict__ i
     }
 }
 
+// ---- 4 columns per thread -------------------------------------------------------------------------------
+// Same recurrence, four adjacent columns (x .. x+3) per thread in lockstep over the union of their
+// candidate windows: one 8- or 16-byte load brings the candidates of all four, stores are 16 bytes, and
+// the four independent minimum chains give the scheduler something to overlap.  Candidates in front of a
+// column's own previous minimiser are strictly worse (monotone minimiser), so visiting them is harmless.
+struct Vec4 { uint32_t v[4]; };
+__device__ __forceinline__ Vec4 load4(const uint16_t *p, uint32_t n0) {
+    const uint2 r = __ldg(reinterpret_cast<const uint2 *>(p));
+    Vec4 o;
+    o.v[0] = f_of((uint16_t)(r.x & 0xFFFFu), n0); o.v[1] = f_of((uint16_t)(r.x >> 16), n0);
+    o.v[2] = f_of((uint16_t)(r.y & 0xFFFFu), n0); o.v[3] = f_of((uint16_t)(r.y >> 16), n0);
+    return o;
+}
+__device__ __forceinline__ Vec4 load4(const uint32_t *p, uint32_t) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+    Vec4 o;
+    o.v[0] = r.x; o.v[1] = r.y; o.v[2] = r.z; o.v[3] = r.w;
+    return o;
+}
+
+template <typename TIn, bool MARK>
+__global__ void __launch_bounds__(128) edt_line4_kernel(const TIn *__restrict__ in, uint32_t *__restrict__ out, int w4,
+                                                         long long ngroups, long long outer, long long stride, int L,
+                                                         uint32_t n0, uint8_t *__restrict__ present,
+                                                         uint32_t *__restrict__ maxval) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = t < ngroups;
+    uint32_t tmax = 0;
+    if (valid) {
+        const long long base = (t / w4) * outer + (t % w4) * 4;
+        const TIn *col = in + base;
+        uint32_t *oc = out + base;
+        const uint32_t NONE = 0x7FFFFFFFu;
+        int a[4];
+        uint32_t fa[4], prev[4];
+        bool dead[4];                                // no finite value on the rest of the line
+        Vec4 cur = load4(col, n0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { a[c] = 0; fa[c] = cur.v[c]; prev[c] = 0xFFFFFFFFu; dead[c] = false; }
+        for (int y = 0; y < L; ++y) {
+            const Vec4 fy = cur;
+            if (y + 1 < L) cur = load4(col + (long long)(y + 1) * stride, n0);     // prefetch the next position
+            uint32_t m[4], fbest[4];
+            int best[4];
+            uint32_t mmax = 0;
+            int start = L;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                best[c] = a[c]; fbest[c] = fa[c];
+                if (fy.v[c] == 0u) { m[c] = 0u; best[c] = y; fbest[c] = 0u; }
+                else if (dead[c]) { m[c] = 0u; }
+                else {
+                    const int da = y - a[c];
+                    m[c] = fa[c] >= n0 ? NONE : fa[c] + (uint32_t)(da * da);
+                    start = min(start, a[c] + 1);
+                }
+                mmax = max(mmax, m[c]);
+            }
+            if (mmax) {
+                for (int yp = start; yp < L; ++yp) {
+                    const int dy = yp - y;
+                    const uint32_t dy2 = (uint32_t)(dy * dy);
+                    if (dy > 0 && dy2 >= mmax) break;
+                    const Vec4 fv = load4(col + (long long)yp * stride, n0);
+                    uint32_t nm = 0;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t cand = fv.v[c] + dy2;
+                        if (fv.v[c] < n0 && cand < m[c]) { m[c] = cand; best[c] = yp; fbest[c] = fv.v[c]; }
+                        nm = max(nm, m[c]);
+                    }
+                    mmax = nm;
+                }
+            }
+            uint4 res;
+            uint32_t r[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (fy.v[c] != 0u && !dead[c] && m[c] == NONE) dead[c] = true;      // scanned to the end, nothing finite
+                r[c] = (fy.v[c] == 0u) ? 0u : (dead[c] ? n0 : (m[c] < n0 ? m[c] : n0));
+                if (!dead[c]) { a[c] = best[c]; fa[c] = fbest[c]; }
+                if (MARK) {
+                    if (r[c] != prev[c]) { present[r[c]] = 1; prev[c] = r[c]; }
+                    tmax = max(tmax, r[c]);
+                }
+            }
+            res.x = r[0]; res.y = r[1]; res.z = r[2]; res.w = r[3];
+            *reinterpret_cast<uint4 *>(oc + (long long)y * stride) = res;
+        }
+    }
+    if (MARK) {
+        tmax = __reduce_max_sync(0xFFFFFFFFu, tmax);
+        if ((threadIdx.x & 31) == 0 && tmax) atomicMax(maxval, tmax);
+    }
+}
+
 int launch_edt_y(const uint16_t *gx, int w, int h, int d, uint32_t n0, uint32_t *gy, cudaStream_t s) {
+    if (w % 4 == 0 && (uintptr_t)gx % 8 == 0 && (uintptr_t)gy % 16 == 0) {
+        const long long ng = (long long)(w / 4) * d;
+        edt_line4_kernel<uint16_t, false><<<(unsigned)((ng + 127) / 128), 128, 0, s>>>(gx, gy, w / 4, ng, (long long)w * h,
+                                                                                      (long long)w, h, n0, nullptr, nullptr);
+        return 1;
+    }
     const long long nlines = (long long)w * d;
     const unsigned grid = (unsigned)((nlines + 255) / 256);
     edt_line_kernel<uint16_t, false><<<grid, 256, 0, s>>>(gx, gy, w, nlines, (long long)w * h, (long long)w, h, n0,
@@ -233,6 +335,12 @@ int launch_edt_y(const uint16_t *gx, int w, int h, int d, uint32_t n0, uint32_t 
 
 int launch_edt_z(const uint32_t *gy, int w, int h, int d, uint32_t n0, uint32_t *sq, uint8_t *present,
                  uint32_t *maxval, cudaStream_t s) {
+    if (w % 4 == 0 && (uintptr_t)gy % 16 == 0 && (uintptr_t)sq % 16 == 0) {
+        const long long ng = (long long)(w / 4) * h;
+        edt_line4_kernel<uint32_t, true><<<(unsigned)((ng + 127) / 128), 128, 0, s>>>(gy, sq, w / 4, ng, (long long)w,
+                                                                                     (long long)w * h, d, n0, present, maxval);
+        return 1;
+    }
     const long long nlines = (long long)w * h;
     const unsigned grid = (unsigned)((nlines + 255) / 256);
     edt_line_kernel<uint32_t, true><<<grid, 256, 0, s>>>(gy, sq, w, nlines, (long long)w, (long long)w * h, d, n0,

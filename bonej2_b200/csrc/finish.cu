@@ -6,48 +6,23 @@
 //   ij.process.StackStatistics              count / sum / sum^2 / min / max in double    (A.7)
 // as driven by ThicknessWrapper.createMap / addMapResults (ThicknessWrapper.java:158-196).
 //
-// Two kernels.  flags: 0 = empty voxel, 1 = surface (non-zero with a zero 26-neighbour inside the
-// image), 2 = interior.  final: interior voxels keep 2*sqrt(R); surface voxels take the float32
-// mean of their interior neighbours, visited in the order faces, edges, corners (the order fixes
-// the last ulp); then mask, NaN, calibration and the statistics partials in the same pass.
+// One fused kernel.  A block owns 32 x 8 x 8 output voxels and stages the painted r^2 of the
+// (36 x 12 x 12) tile with its 2-voxel halo in shared memory (out-of-image cells hold a marker that
+// counts as "not zero", as the reference's look() returns -1 there).  From the tile it derives the
+// "interior" flag (non-zero, no zero 26-neighbour) on the 1-voxel halo, then the value of each output
+// voxel: interior voxels keep 2*sqrt(R); surface voxels take the float32 mean of their interior
+// neighbours visited in the order faces, edges, corners (the order fixes the last ulp); then mask,
+// NaN, calibration, and per-block partials of the statistics.  HBM sees r^2 once (plus halo re-reads
+// that hit L2), the original once and the map once: 9 B/voxel of actual traffic.
 #include "common.cuh"
 #include <math.h>
 
 namespace bjt {
 
-constexpr int FTX = 32, FTY = 8, FTZ = 4;
-
-__global__ void __launch_bounds__(FTX *FTY *FTZ) flags_kernel(const uint32_t *__restrict__ rsq, int w, int h, int d,
-                                                              uint8_t *__restrict__ flags) {
-    __shared__ uint8_t nz[FTZ + 2][FTY + 2][FTX + 2];   // 1 = non-zero or outside the image
-    const int bx = blockIdx.x * FTX, by = blockIdx.y * FTY, bz = blockIdx.z * FTZ;
-    const int tid = threadIdx.x + FTX * (threadIdx.y + FTY * threadIdx.z);
-    const size_t wh = (size_t)w * h;
-    for (int i = tid; i < (FTZ + 2) * (FTY + 2) * (FTX + 2); i += FTX * FTY * FTZ) {
-        const int lx = i % (FTX + 2), ly = (i / (FTX + 2)) % (FTY + 2), lz = i / ((FTX + 2) * (FTY + 2));
-        const int gx = bx + lx - 1, gy = by + ly - 1, gz = bz + lz - 1;
-        uint8_t v = 1;
-        if (gx >= 0 && gx < w && gy >= 0 && gy < h && gz >= 0 && gz < d)
-            v = __ldg(rsq + gz * wh + (size_t)gy * w + gx) != 0u;
-        nz[lz][ly][lx] = v;
-    }
-    __syncthreads();
-    const int x = bx + threadIdx.x, y = by + threadIdx.y, z = bz + threadIdx.z;
-    if (x >= w || y >= h || z >= d) return;
-    const int lx = threadIdx.x + 1, ly = threadIdx.y + 1, lz = threadIdx.z + 1;
-    uint8_t f = 0;
-    if (nz[lz][ly][lx]) {
-        int all = 1;
-#pragma unroll
-        for (int dz = -1; dz <= 1; ++dz)
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                for (int dx = -1; dx <= 1; ++dx) all &= nz[lz + dz][ly + dy][lx + dx];
-        f = all ? 2 : 1;
-    }
-    flags[z * wh + (size_t)y * w + x] = f;
-}
+constexpr int FTX = 32, FTY = 8, FTZ = 8;
+constexpr int HX = FTX + 4, HY = FTY + 4, HZ = FTZ + 4;       // r^2 tile with 2-voxel halo
+constexpr int IX = FTX + 2, IY = FTY + 2, IZ = FTZ + 2;       // interior flags with 1-voxel halo
+constexpr uint32_t OUTSIDE = 0xFFFFFFFFu;
 
 // neighbour visiting order of the cleanup average: 6 faces, 12 edges, 8 corners (dx, dy, dz)
 __constant__ int8_t NB26[26][3] = {
@@ -85,43 +60,78 @@ __device__ __forceinline__ void block_reduce_stats(double sum, double sum2, doub
     }
 }
 
-// Each block walks FZ consecutive z-tiles so the partial count stays small.
-__global__ void __launch_bounds__(FTX *FTY *FTZ) final_kernel(const uint32_t *__restrict__ rsq,
-                                                              const uint8_t *__restrict__ flags,
-                                                              const uint8_t *__restrict__ original, int w, int h, int d,
-                                                              int fgval, int calibrate, float pw, float *__restrict__ out,
-                                                              StatsPartial *__restrict__ partials) {
-    const int x = blockIdx.x * FTX + threadIdx.x, y = blockIdx.y * FTY + threadIdx.y, z = blockIdx.z * FTZ + threadIdx.z;
+// Output and statistics cover z in [z_lo, z_hi) of the local volume; `out` and nothing else is indexed
+// relative to z_lo (a sharded caller passes its slab plus halo planes and keeps the core).
+__global__ void __launch_bounds__(FTX *FTY) finish_kernel(const uint32_t *__restrict__ rsq,
+                                                          const uint8_t *__restrict__ original, int w, int h, int d,
+                                                          int z_lo, int z_hi, int fgval, int calibrate, float pw,
+                                                          float *__restrict__ out, StatsPartial *__restrict__ partials) {
+    __shared__ uint32_t R[HZ][HY][HX];
+    __shared__ uint8_t inter[IZ][IY][IX];
+    const int bx = blockIdx.x * FTX, by = blockIdx.y * FTY, bz = z_lo + blockIdx.z * FTZ;
+    const int tid = threadIdx.x + FTX * threadIdx.y;
     const size_t wh = (size_t)w * h;
+    for (int i = tid; i < HZ * HY * HX; i += FTX * FTY) {
+        const int lx = i % HX, ly = (i / HX) % HY, lz = i / (HX * HY);
+        const int gx = bx + lx - 2, gy = by + ly - 2, gz = bz + lz - 2;
+        uint32_t v = OUTSIDE;
+        if (gx >= 0 && gx < w && gy >= 0 && gy < h && gz >= 0 && gz < d) v = __ldg(rsq + gz * wh + (size_t)gy * w + gx);
+        R[lz][ly][lx] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < IZ * IY * IX; i += FTX * FTY) {
+        const int lx = i % IX, ly = (i / IX) % IY, lz = i / (IX * IY);
+        const uint32_t c = R[lz + 1][ly + 1][lx + 1];
+        uint8_t f = 0;
+        if (c != 0u && c != OUTSIDE) {
+            bool all = true;
+#pragma unroll
+            for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) all = all && (R[lz + dz][ly + dy][lx + dx] != 0u);
+            f = all ? 1 : 0;
+        }
+        inter[lz][ly][lx] = f;
+    }
+    __syncthreads();
     double sum = 0, sum2 = 0, mn = INFINITY, mx = -INFINITY;
     long long cnt = 0;
-    if (x < w && y < h && z < d) {
-        const size_t p = z * wh + (size_t)y * w + x;
-        const uint8_t f = flags[p];
-        float v = 0.0f;
-        if (f == 2) {
-            v = thickness_of(__ldg(rsq + p));
-        } else if (f == 1) {
-            float s = 0.0f;
-            int n = 0;
+    const int x = bx + threadIdx.x, y = by + threadIdx.y;
+    if (x < w && y < h) {
+        const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll 1
+        for (int tz = 0; tz < FTZ; ++tz) {
+            const int z = bz + tz;
+            if (z >= z_hi || z >= d) break;
+            const uint32_t c = R[tz + 2][ty + 2][tx + 2];
+            float v = 0.0f;
+            if (c != 0u) {
+                if (inter[tz + 1][ty + 1][tx + 1]) {
+                    v = thickness_of(c);
+                } else {
+                    float s = 0.0f;
+                    int n = 0;
 #pragma unroll
-            for (int q = 0; q < 26; ++q) {
-                const int xx = x + NB26[q][0], yy = y + NB26[q][1], zz = z + NB26[q][2];
-                if (xx < 0 || xx >= w || yy < 0 || yy >= h || zz < 0 || zz >= d) continue;
-                const size_t pq = zz * wh + (size_t)yy * w + xx;
-                if (__ldg(flags + pq) == 2) { s += thickness_of(__ldg(rsq + pq)); ++n; }
+                    for (int q = 0; q < 26; ++q) {
+                        const int dx = NB26[q][0], dy = NB26[q][1], dz = NB26[q][2];
+                        if (inter[tz + 1 + dz][ty + 1 + dy][tx + 1 + dx]) { s += thickness_of(R[tz + 2 + dz][ty + 2 + dy][tx + 2 + dx]); ++n; }
+                    }
+                    v = n > 0 ? s / (float)n : thickness_of(c);
+                }
             }
-            v = n > 0 ? s / (float)n : thickness_of(__ldg(rsq + p));
-        }
-        if (original && (int)__ldg(original + p) != fgval) v = 0.0f;
-        if (calibrate) {
-            if (v == 0.0f) v = __int_as_float(0x7FC00000);
-            v = v * pw;
-        }
-        if (out) out[p] = v;
-        if (v == v) {   // not NaN
-            const double dv = (double)v;
-            sum = dv; sum2 = dv * dv; mn = dv; mx = dv; cnt = 1;
+            const size_t p = z * wh + (size_t)y * w + x;
+            if (original && (int)__ldg(original + p) != fgval) v = 0.0f;
+            if (calibrate) {
+                if (v == 0.0f) v = __int_as_float(0x7FC00000);
+                v = v * pw;
+            }
+            if (out) out[p - (size_t)z_lo * wh] = v;
+            if (v == v) {   // not NaN
+                const double dv = (double)v;
+                sum += dv; sum2 += dv * dv; mn = fmin(mn, dv); mx = fmax(mx, dv); ++cnt;
+            }
         }
     }
     const int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
@@ -139,20 +149,19 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const StatsPartia
     block_reduce_stats(sum, sum2, mn, mx, cnt, result);
 }
 
-int finish_partials(int w, int h, int d) {
-    return ((w + FTX - 1) / FTX) * ((h + FTY - 1) / FTY) * ((d + FTZ - 1) / FTZ);
+int finish_partials(int w, int h, int nz) {
+    return ((w + FTX - 1) / FTX) * ((h + FTY - 1) / FTY) * ((nz + FTZ - 1) / FTZ);
 }
 
-int launch_finish(const uint32_t *rsq, const uint8_t *original, int w, int h, int d, int inverse, int calibrate,
-                  float pixel_width, uint8_t *flags, float *out, StatsPartial *partials, int npartials,
+int launch_finish(const uint32_t *rsq, const uint8_t *original, int w, int h, int d, int z_lo, int z_hi, int inverse,
+                  int calibrate, float pixel_width, float *out, StatsPartial *partials, int npartials,
                   StatsPartial *result, cudaStream_t s) {
-    dim3 grid((w + FTX - 1) / FTX, (h + FTY - 1) / FTY, (d + FTZ - 1) / FTZ);
-    dim3 block(FTX, FTY, FTZ);
-    flags_kernel<<<grid, block, 0, s>>>(rsq, w, h, d, flags);
-    final_kernel<<<grid, block, 0, s>>>(rsq, flags, original, w, h, d, inverse ? 0 : 255, calibrate, pixel_width, out,
-                                        partials);
+    dim3 grid((w + FTX - 1) / FTX, (h + FTY - 1) / FTY, (z_hi - z_lo + FTZ - 1) / FTZ);
+    dim3 block(FTX, FTY, 1);
+    finish_kernel<<<grid, block, 0, s>>>(rsq, original, w, h, d, z_lo, z_hi, inverse ? 0 : 255, calibrate, pixel_width, out,
+                                         partials);
     reduce_partials_kernel<<<1, 1024, 0, s>>>(partials, npartials, result);
-    return 3;
+    return 2;
 }
 
 // ---- statistics of an existing float map ---------------------------------------------------------
@@ -184,7 +193,7 @@ __global__ void check_binary_kernel(const uint8_t *__restrict__ in, size_t n, ui
     const uint4 *v = reinterpret_cast<const uint4 *>(in);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
         const uint4 q = __ldg(v + i);
-        // a byte is fine iff it equals 0x00 or 0xFF  <=>  byte ^ (byte >> 7 replicated) == 0
+        // a byte is fine iff it equals 0x00 or 0xFF  <=>  byte ^ (its top bit replicated) == 0
         const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {

@@ -1,0 +1,389 @@
+"""z-slab sharded Thickness: one process per GPU, torch.distributed for the plumbing.
+
+The volume [d][h][w] is cut into contiguous z-slabs, one per rank.  Per pipeline run:
+
+  EDT x, y          slab-local kernels
+  EDT z             all-to-all transpose z-slabs -> y-slabs, z pass on whole z lines, transpose back
+  ridge + paint     every rank fetches the squared-EDT planes within H = r_max + 2 of its slab (r_max from
+                    an all-reduce of the largest squared distance), computes the ridge and paints slab +
+                    halo locally: any ball that touches the slab +- 2 has its centre inside that range
+                    (the "max-radius halo exchange" of BASELINE.json's north_star)
+  cleanup .. stats  on slab +- 2 painted planes, output and statistics restricted to the slab
+                    (bjt_dev_finish_range); (n, sum, sum^2, min, max) are combined across ranks before
+                    mean and sd are formed, as ij.process.StackStatistics does on the whole stack
+
+The result is bitwise the single-GPU map (integer stages are order-independent, the cleanup sees the
+same neighbours).  The compute backend is pluggable so the exchange logic can be tested on CPU with
+world_size 2 over gloo (tests/test_sharded_cpu.py injects an oracle-backed backend); the product
+backend below is CUDA only -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+import time
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+
+def split_ranges(n: int, parts: int):
+    """contiguous near-equal ranges [(lo, hi)] of range(n)"""
+    base, rem = divmod(n, parts)
+    out, lo = [], 0
+    for i in range(parts):
+        hi = lo + base + (1 if i < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+@dataclass
+class PartialStats:
+    count: int
+    sum: float
+    sum2: float
+    min: float
+    max: float
+
+    def finalize(self):
+        """StackStatistics: mean = sum/n, sd = sqrt((n*sum2 - sum^2)/n/(n-1)) clamped at 0"""
+        n = float(self.count)
+        mean = self.sum / n if self.count else float("nan")
+        sd = 0.0
+        if self.count > 0:
+            v = (n * self.sum2 - self.sum * self.sum) / n
+            sd = math.sqrt(v / (n - 1.0)) if v > 0.0 else 0.0
+        return dict(count=self.count, mean=mean, sd=sd, min=self.min, max=self.max)
+
+
+class Comm:
+    """the few collectives the path needs, on whatever backend the process group has"""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.size = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def exchange(self, sends, recvs):
+        """sends / recvs: {peer: contiguous tensor}.  Point-to-point, works on nccl and gloo alike."""
+        if self.size == 1:
+            return
+        ops = []
+        for peer, t in sorted(recvs.items()):
+            ops.append(dist.P2POp(dist.irecv, t, peer, self.group))
+        for peer, t in sorted(sends.items()):
+            ops.append(dist.P2POp(dist.isend, t, peer, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def allreduce_max_int(self, v: int, device) -> int:
+        if self.size == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.int64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return int(t.item())
+
+    def combine_stats(self, st: PartialStats, device) -> PartialStats:
+        if self.size == 1:
+            return st
+        t = torch.tensor([float(st.count), st.sum, st.sum2, st.min, st.max], dtype=torch.float64, device=device)
+        all_t = [torch.empty_like(t) for _ in range(self.size)]
+        dist.all_gather(all_t, t, group=self.group)
+        rows = [x.cpu().tolist() for x in all_t]                      # rank order: the same sum on every rank
+        return PartialStats(int(sum(r[0] for r in rows)), sum(r[1] for r in rows), sum(r[2] for r in rows),
+                            min(r[3] for r in rows), max(r[4] for r in rows))
+
+    def barrier(self):
+        if self.size > 1:
+            dist.barrier(group=self.group)
+
+
+# ------------------------------------------------------------------------------------------------------
+# layout changes
+
+def transpose_z_to_y(comm: Comm, t, zs, ys):
+    """[dz_r][h][w] on every rank r  ->  [d][hy_r][w]: rank r ends up with all z of its y range"""
+    r = comm.rank
+    d_total = zs[-1][1]
+    w = t.shape[2]
+    out = t.new_empty((d_total, ys[r][1] - ys[r][0], w))
+    sends, recvs, bufs = {}, {}, {}
+    for p in range(comm.size):
+        chunk = t[:, ys[p][0]:ys[p][1], :]
+        if p == r:
+            out[zs[r][0]:zs[r][1]] = chunk
+        else:
+            if chunk.numel():
+                sends[p] = chunk.contiguous()
+            if (zs[p][1] - zs[p][0]) * (ys[r][1] - ys[r][0]) > 0:
+                recvs[p] = out[zs[p][0]:zs[p][1]]                   # contiguous: z is the slowest axis
+    comm.exchange(sends, recvs)
+    return out
+
+
+def transpose_y_to_z(comm: Comm, t, zs, ys, h):
+    """inverse of transpose_z_to_y: [d][hy_r][w] -> [dz_r][h][w]"""
+    r = comm.rank
+    w = t.shape[2]
+    out = t.new_empty((zs[r][1] - zs[r][0], h, w))
+    sends, recvs, tmp = {}, {}, {}
+    for p in range(comm.size):
+        chunk = t[zs[p][0]:zs[p][1]]                                  # what rank p's slab needs of my y range
+        if p == r:
+            out[:, ys[r][0]:ys[r][1], :] = chunk
+        else:
+            if chunk.numel():
+                sends[p] = chunk.contiguous()
+            n = (zs[r][1] - zs[r][0]) * (ys[p][1] - ys[p][0])
+            if n > 0:
+                tmp[p] = t.new_empty((zs[r][1] - zs[r][0], ys[p][1] - ys[p][0], w))
+                recvs[p] = tmp[p]
+    comm.exchange(sends, recvs)
+    for p, buf in tmp.items():
+        out[:, ys[p][0]:ys[p][1], :] = buf
+    return out
+
+
+def gather_planes(comm: Comm, slab, zs, needs):
+    """needs[r] = (lo, hi): the global plane range rank r wants.  Returns this rank's [hi-lo][h][w]."""
+    r = comm.rank
+    lo, hi = needs[r]
+    out = slab.new_empty((hi - lo,) + tuple(slab.shape[1:]))
+    sends, recvs = {}, {}
+    for p in range(comm.size):
+        # what I hold of p's wish
+        a, b = max(needs[p][0], zs[r][0]), min(needs[p][1], zs[r][1])
+        if p == r:
+            if b > a:
+                out[a - lo:b - lo] = slab[a - zs[r][0]:b - zs[r][0]]
+            continue
+        if b > a:
+            sends[p] = slab[a - zs[r][0]:b - zs[r][0]].contiguous()
+        # what p holds of my wish
+        a2, b2 = max(lo, zs[p][0]), min(hi, zs[p][1])
+        if b2 > a2:
+            recvs[p] = out[a2 - lo:b2 - lo]
+    comm.exchange(sends, recvs)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# the product backend: CUDA kernels through the C-ABI on torch device tensors
+
+class CudaStages:
+    def __init__(self, ctx, device):
+        self.ctx, self.device = ctx, device
+
+    def _i32(self, shape):
+        return torch.empty(shape, dtype=torch.int32, device=self.device)
+
+    def edt_x(self, slab_u8, inverse, threshold=128):
+        dz, h, w = slab_u8.shape
+        gx = torch.empty((dz, h, w), dtype=torch.int16, device=self.device)       # u16 bits
+        self.ctx.dev_edt_x(slab_u8.data_ptr(), w, h, dz, inverse, threshold, gx.data_ptr())
+        return gx
+
+    def edt_y(self, gx, n_sentinel):
+        dz, h, w = gx.shape
+        gy = self._i32((dz, h, w))
+        self.ctx.dev_edt_y(gx.data_ptr(), w, h, dz, n_sentinel, gy.data_ptr())
+        return gy
+
+    def edt_z(self, gy_t, n_sentinel):
+        d, hy, w = gy_t.shape
+        sq = self._i32((d, hy, w))
+        if hy > 0:
+            self.ctx.dev_edt_z(gy_t.data_ptr(), w, hy, d, n_sentinel, sq.data_ptr())
+        return sq
+
+    def max_value(self, t):
+        return int(t.max().item()) if t.numel() else 0
+
+    def ridge(self, sq_ext):
+        de, h, w = sq_ext.shape
+        out = self._i32((de, h, w))
+        self.ctx.dev_ridge(sq_ext.data_ptr(), w, h, de, out.data_ptr())
+        return out
+
+    def paint(self, ridge_ext):
+        de, h, w = ridge_ext.shape
+        out = self._i32((de, h, w))
+        self.ctx.dev_paint(ridge_ext.data_ptr(), w, h, de, out.data_ptr())
+        return out
+
+    def full(self, shape, value):
+        return torch.full(shape, value, dtype=torch.int32, device=self.device)
+
+    def finish(self, rsq_sub, orig_core_u8, z_lo, z_hi, inverse, mask, pixel_width):
+        ds, h, w = rsq_sub.shape
+        out = torch.empty((z_hi - z_lo, h, w), dtype=torch.float32, device=self.device)
+        # the kernel indexes the original with the coordinates of rsq_sub: shift the core pointer
+        optr = (orig_core_u8.data_ptr() - z_lo * h * w) if mask else None
+        st = self.ctx.dev_finish_range(rsq_sub.data_ptr(), optr, w, h, ds, z_lo, z_hi, inverse, True, pixel_width,
+                                       out.data_ptr())
+        return out, PartialStats(st.count, st.sum, st.sum2, st.min, st.max)
+
+
+# ------------------------------------------------------------------------------------------------------
+
+def no_result(n: int) -> int:
+    return 3 * (n + 1) * (n + 1)
+
+
+def thickness_slab(stages, comm: Comm, slab_u8, dims, inverse, mask=True, pixel_width=1.0, timings=None):
+    """One pipeline run (LocalThicknessWrapper.processImage + StackStatistics) on this rank's z-slab.
+    slab_u8: [dz][h][w] planes zs[rank] of the volume dims = (w, h, d).  Returns (map slab f32, stats dict)."""
+    w, h, d = dims
+    G, r = comm.size, comm.rank
+    zs, ys = split_ranges(d, G), split_ranges(h, G)
+    z0, z1 = zs[r]
+    n = max(w, h, d)
+    n0 = no_result(n)
+    t_ = time.perf_counter
+
+    def mark(name, t0):
+        if timings is not None:
+            if hasattr(stages, "device") and str(stages.device).startswith("cuda"):
+                torch.cuda.synchronize()
+            timings[name] = timings.get(name, 0.0) + (t_() - t0)
+
+    t0 = t_()
+    gx = stages.edt_x(slab_u8, inverse)
+    gy = stages.edt_y(gx, n)
+    del gx
+    mark("edt_xy", t0); t0 = t_()
+    gy_t = transpose_z_to_y(comm, gy, zs, ys)
+    del gy
+    mark("transpose", t0); t0 = t_()
+    sq_t = stages.edt_z(gy_t, n)
+    del gy_t
+    mark("edt_z", t0); t0 = t_()
+    sq = transpose_y_to_z(comm, sq_t, zs, ys, h)
+    del sq_t
+    mark("transpose", t0); t0 = t_()
+    gmax = comm.allreduce_max_int(stages.max_value(sq), slab_u8.device)
+
+    # planes of the painted map the cleanup of this slab reads: slab +- 2, clipped to the volume
+    s_lo, s_hi = max(0, z0 - 2), min(d, z1 + 2)
+    if gmax == 0:
+        rsq_sub = stages.full((s_hi - s_lo, h, w), 0)
+    elif gmax >= n0:
+        rsq_sub = stages.full((s_hi - s_lo, h, w), n0)                 # no background anywhere (sentinel)
+    else:
+        H = math.isqrt(gmax - 1) + 1 + 2                               # ceil(sqrt(r^2 max)) + 2
+        # ridge of planes [z0-H, z1+H) needs the squared EDT one plane further out
+        needs = []
+        for (a, b) in zs:
+            needs.append((max(0, a - H - 1), min(d, b + H + 1)))
+        e_lo, e_hi = needs[r]
+        sq_ext = gather_planes(comm, sq, zs, needs)
+        mark("halo", t0); t0 = t_()
+        ridge_ext = stages.ridge(sq_ext)
+        del sq_ext
+        # the outermost fetched planes have an incomplete neighbourhood unless they are volume faces;
+        # they lie beyond reach (H + 1 > r_max + 2) and are dropped
+        if e_lo > 0:
+            ridge_ext[0] = 0
+        if e_hi < d:
+            ridge_ext[-1] = 0
+        mark("ridge", t0); t0 = t_()
+        rsq_ext = stages.paint(ridge_ext)
+        del ridge_ext
+        rsq_sub = rsq_ext[s_lo - e_lo:s_hi - e_lo]
+        mark("paint", t0); t0 = t_()
+    out, part = stages.finish(rsq_sub, slab_u8, z0 - s_lo, z1 - s_lo, inverse, mask, pixel_width)
+    stats = comm.combine_stats(part, slab_u8.device).finalize()
+    mark("finish", t0)
+    return out, stats
+
+
+# ------------------------------------------------------------------------------------------------------
+# bench.py --gpus N (N > 1)
+
+def bench(args, rank, world, local_rank, dist_mod):
+    from . import _native
+    from .phantom import phantom_shapes
+
+    n = args.size
+    dims = (n, n, n)
+    dev = torch.device("cuda", local_rank)
+    ctx = _native.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    comm = Comm()
+    stages = CudaStages(ctx, dev)
+    zs = split_ranges(n, world)
+    z0, z1 = zs[rank]
+    dz = z1 - z0
+    shapes = phantom_shapes(n, n, n, 1)
+    slab = torch.empty((dz, n, n), dtype=torch.uint8, device=dev)
+    ctx.dev_phantom(shapes, n, n, n, z0, dz, slab.data_ptr())
+
+    def step(timings=None):
+        th = thickness_slab(stages, comm, slab, dims, False, True, 1.0, timings)
+        sp = thickness_slab(stages, comm, slab, dims, True, True, 1.0, timings)
+        return th, sp
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize(); comm.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    timings = {}
+    ev0.record(stream)
+    for _ in range(args.steps):
+        th, sp = step(timings)
+    ev1.record(stream)
+    torch.cuda.synchronize(); comm.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], dtype=torch.float64, device=dev)
+    dist_mod.all_reduce(ms, op=dist_mod.ReduceOp.MAX)
+    dev_ms = float(ms.item())
+
+    # end to end: page-locked host slab in, both map slabs back out, every step
+    nb = dz * n * n
+    h_in = torch.empty((dz, n, n), dtype=torch.uint8, pin_memory=True)
+    h_th = torch.empty((dz, n, n), dtype=torch.float32, pin_memory=True)
+    h_sp = torch.empty((dz, n, n), dtype=torch.float32, pin_memory=True)
+    h_in.copy_(slab)
+    slab2 = torch.empty_like(slab)
+    launches0 = ctx.launch_count()
+    e2e = []
+    for i in range(args.warmup + args.steps):
+        torch.cuda.synchronize(); comm.barrier()
+        t0 = time.perf_counter()
+        slab2.copy_(h_in, non_blocking=True)
+        th = thickness_slab(stages, comm, slab2, dims, False, True, 1.0)
+        h_th.copy_(th[0], non_blocking=True)
+        sp = thickness_slab(stages, comm, slab2, dims, True, True, 1.0)
+        h_sp.copy_(sp[0], non_blocking=True)
+        torch.cuda.synchronize(); comm.barrier()
+        if i >= args.warmup:
+            e2e.append(time.perf_counter() - t0)
+    launches = (ctx.launch_count() - launches0) // (args.warmup + args.steps)
+    em = torch.tensor([1e3 * sum(e2e) / len(e2e)], dtype=torch.float64, device=dev)
+    dist_mod.all_reduce(em, op=dist_mod.ReduceOp.MAX)
+    e2e_ms = float(em.item())
+
+    N = n ** 3
+    per = {k: 1e3 * v / args.steps for k, v in timings.items()}
+    dom = max(per, key=per.get) if per else "paint"
+    alg_edt = 21.0 * N * 2 / world
+    edt_ms = per.get("edt_xy", 0.0) + per.get("edt_z", 0.0)
+    return {
+        "metric": "thickness_map_gvoxels_per_s", "value": N / (dev_ms * 1e-3) / 1e9, "unit": "Gvoxel/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u32/f32", "data": "synthetic",
+        "config": {"workload": f"BoneJ Thickness Tb.Th+Tb.Sp (mapChoice Both), mask on, {n}^3 synthetic trabecular phantom, "
+                               f"z-slabs over {world} GPUs (BASELINE.json configs[2])", "volume": [n, n, n],
+                   "parallelism": f"z-slab x{world}", "l2_policy": "inputs exceed the 126 MB L2"},
+        "e2e": {"value": N / (e2e_ms * 1e-3) / 1e9, "unit": "Gvoxel/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": N, "d2h_bytes_per_step": 8 * N},
+        "gpu_launches": int(launches) * args.steps,
+        "roofline": {"kernel": "edt (x+y+z passes, rank 0, per step)", "bound": "hbm",
+                     "achieved": alg_edt / (edt_ms * 1e-3) / 1e9 if edt_ms > 0 else 0.0, "peak": None, "unit": "GB/s",
+                     "frac": None, "traffic": None},
+        "stages_rank0_ms": {k: round(v, 3) for k, v in per.items()}, "dominant_stage": dom,
+        "results": {"tb_th": th[1], "tb_sp": sp[1]},
+        "cpu_baseline": None,
+    }

@@ -61,6 +61,8 @@ int  bjt_release_workspace(bjt_ctx *ctx);              /* free cached device buf
 int  bjt_device_info(bjt_ctx *ctx, char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor);
 /* paint_path override for tests: -1 automatic (default), 0/1/2 force that path */
 int  bjt_set_paint_path(bjt_ctx *ctx, int path);
+/* kernels of this library launched through this context so far */
+int64_t bjt_launch_count(const bjt_ctx *ctx);
 /* page-locked host memory (what a JNI direct ByteBuffer / the bench wraps so copies are DMA) */
 void *bjt_host_alloc(size_t bytes);
 void  bjt_host_free(void *p);
@@ -117,6 +119,12 @@ int bjt_dev_ridge(bjt_ctx *ctx, const uint32_t *d_sq, int w, int h, int d, uint3
 int bjt_dev_paint(bjt_ctx *ctx, const uint32_t *d_ridge, int w, int h, int d, int path, uint32_t *d_rsq);
 int bjt_dev_finish(bjt_ctx *ctx, const uint32_t *d_rsq, const uint8_t *d_original, int w, int h, int d,
                    int inverse, int calibrate, double pixel_width, float *d_out, bjt_stats *stats);
+/* same on a slab with halo planes: the map and the statistics cover planes [z_lo, z_hi) of the local
+ * volume only (d_out holds z_hi - z_lo planes); planes outside serve as cleanup neighbours.  stats->sum,
+ * sum2, count, min, max are what ranks combine before forming mean and sd. */
+int bjt_dev_finish_range(bjt_ctx *ctx, const uint32_t *d_rsq, const uint8_t *d_original, int w, int h, int d,
+                         int z_lo, int z_hi, int inverse, int calibrate, double pixel_width, float *d_out,
+                         bjt_stats *stats);
 
 /* ---- synthetic trabecular phantom (workload of BASELINE.json) ------------------- */
 /* shapes: n records of 16 int32 (bonej2_b200/phantom.py); out: u8 [d][h][w] in {0,255}          */

@@ -1,0 +1,77 @@
+"""bonej2_b200.sharded with the CUDA backend: one rank on one GPU must reproduce the oracle (and so the
+single-call path); with >= 2 GPUs two NCCL ranks must reproduce it too, bitwise."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from tests import shapes
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cmp(got, st, ref):
+    assert np.array_equal(np.isnan(got), np.isnan(ref["map"]))
+    ok = ~np.isnan(got)
+    assert np.allclose(got[ok], ref["map"][ok], rtol=1e-5, atol=0)
+    assert st["count"] == ref["stats"].count
+    if st["count"]:
+        assert abs(st["mean"] - ref["stats"].mean) <= 1e-5 * abs(ref["stats"].mean)
+        assert st["max"] == pytest.approx(ref["stats"].max, rel=1e-6)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_single_rank_matches_oracle(ctx, oracle, inverse):
+    from bonej2_b200 import sharded
+    vol = shapes.random_blobs((40, 36, 44), 9)
+    dev = torch.device("cuda", 0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    slab = torch.from_numpy(vol).to(dev)
+    d, h, w = vol.shape
+    out, st = sharded.thickness_slab(sharded.CudaStages(ctx, dev), sharded.Comm(), slab, (w, h, d), inverse, True, 0.7)
+    _cmp(out.cpu().numpy(), st, oracle.process_image(vol, inverse=inverse, mask=True, pixel_width=0.7))
+
+
+def _worker(rank, world, port, vol_path, out_dir, inverse):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from bonej2_b200 import _native, sharded
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    vol = np.load(vol_path)
+    d, h, w = vol.shape
+    zs = sharded.split_ranges(d, world)
+    dev = torch.device("cuda", rank)
+    c = _native.Context(rank)
+    c.set_stream(torch.cuda.current_stream().cuda_stream)
+    slab = torch.from_numpy(vol[zs[rank][0]:zs[rank][1]].copy()).to(dev)
+    out, st = sharded.thickness_slab(sharded.CudaStages(c, dev), sharded.Comm(), slab, (w, h, d), inverse, True, 1.0)
+    np.save(os.path.join(out_dir, f"map_{rank}.npy"), out.cpu().numpy())
+    if rank == 0:
+        np.save(os.path.join(out_dir, "stats.npy"), np.array([st["count"], st["mean"], st["sd"], st["min"], st["max"]]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("inverse", [False, True])
+def test_two_ranks_nccl_bitwise(oracle, tmp_path, inverse):
+    import torch.multiprocessing as mp
+    from bonej2_b200 import _native
+    from bonej2_b200.phantom import phantom_shapes
+    n = 96
+    vol = oracle.phantom_raster(phantom_shapes(n, n, n, 2), n, n, n)
+    vol_path = os.path.join(tmp_path, "vol.npy")
+    np.save(vol_path, vol)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(2, port, vol_path, str(tmp_path), inverse), nprocs=2, join=True)
+    got = np.concatenate([np.load(os.path.join(tmp_path, f"map_{r}.npy")) for r in range(2)], axis=0)
+    with _native.Context(0) as c:
+        one, st1, _ = c.thickness(vol, inverse=inverse, mask=True)
+    assert np.array_equal(np.nan_to_num(got, nan=-1.0), np.nan_to_num(one, nan=-1.0)), "2-GPU map != 1-GPU map"
+    st = np.load(os.path.join(tmp_path, "stats.npy"))
+    assert int(st[0]) == st1.count and abs(st[1] - st1.mean) <= 1e-9 * abs(st1.mean)

@@ -1,0 +1,99 @@
+"""N > 1 path on CPU: two processes over gloo run bonej2_b200.sharded.thickness_slab with the
+oracle-backed stage backend; the assembled result must equal the oracle on the whole volume (maps
+bitwise, statistics to 1e-12).  Exercises the z<->y transposes, the r_max halo gather with clipping,
+the no-background / no-foreground shortcuts and the statistics combination."""
+import math
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, vol_path, out_dir, inverse, mask):
+    sys.path.insert(0, ROOT)
+    from bonej2_b200 import sharded
+    from tests.sharded_cpu_backend import OracleStages
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    vol = np.load(vol_path)
+    d, h, w = vol.shape
+    zs = sharded.split_ranges(d, world)
+    slab = torch.from_numpy(vol[zs[rank][0]:zs[rank][1]].copy())
+    comm = sharded.Comm()
+    out, stats = sharded.thickness_slab(OracleStages(), comm, slab, (w, h, d), inverse, mask, 0.5)
+    np.save(os.path.join(out_dir, f"map_{rank}.npy"), out.numpy())
+    if rank == 0:
+        np.save(os.path.join(out_dir, "stats.npy"), np.array([stats["count"], stats["mean"], stats["sd"], stats["min"], stats["max"]]))
+    dist.destroy_process_group()
+
+
+def _run(vol, inverse, mask, tmp_path, world=2):
+    vol_path = os.path.join(tmp_path, "vol.npy")
+    np.save(vol_path, vol)
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, vol_path, str(tmp_path), inverse, mask), nprocs=world, join=True)
+    maps = [np.load(os.path.join(tmp_path, f"map_{r}.npy")) for r in range(world)]
+    return np.concatenate(maps, axis=0), np.load(os.path.join(tmp_path, "stats.npy"))
+
+
+def _check(vol, inverse, mask, tmp_path, world=2):
+    from oracle import lt_oracle
+    got, st = _run(vol, inverse, mask, tmp_path, world)
+    ref = lt_oracle.process_image(vol, inverse=inverse, mask=mask, pixel_width=0.5)
+    assert np.array_equal(np.isnan(got), np.isnan(ref["map"]))
+    ok = ~np.isnan(got)
+    assert np.array_equal(got[ok], ref["map"][ok])
+    assert int(st[0]) == ref["stats"].count
+    if ref["stats"].count:
+        assert math.isclose(st[1], ref["stats"].mean, rel_tol=1e-12)
+        assert math.isclose(st[2], ref["stats"].sd, rel_tol=1e-9, abs_tol=1e-9)
+        assert st[4] == ref["stats"].max
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_two_ranks_blobs(tmp_path, inverse):
+    from tests import shapes
+    _check(shapes.random_blobs((17, 14, 19), 3), inverse, True, str(tmp_path))
+
+
+def test_two_ranks_big_radius_halo_clipped(tmp_path):
+    """r_max larger than a slab: the halo gather reaches across the whole volume"""
+    vol = np.zeros((12, 10, 10), np.uint8)
+    vol[:, 1:9, 1:9] = 255
+    vol[0] = 0
+    _check(vol, False, False, str(tmp_path))
+
+
+def test_two_ranks_no_background(tmp_path):
+    _check(np.full((4, 3, 5), 255, np.uint8), False, False, str(tmp_path))
+
+
+def test_two_ranks_no_foreground(tmp_path):
+    _check(np.zeros((4, 3, 5), np.uint8), False, True, str(tmp_path))
+
+
+def test_three_ranks_uneven(tmp_path):
+    from tests import shapes
+    _check(shapes.random_blobs((11, 7, 9), 5), True, True, str(tmp_path), world=3)
+
+
+def test_split_ranges():
+    from bonej2_b200.sharded import split_ranges
+    assert split_ranges(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    assert split_ranges(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]

@@ -1,0 +1,24 @@
+"""print selected metrics of an .ncu-rep: python tools_ncu_metrics.py file.ncu-rep [pattern...]"""
+import csv, subprocess, sys
+rep = sys.argv[1]
+pats = sys.argv[2:] or ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__inst_executed.avg.per_cycle_active",
+    "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "launch__registers_per_thread", "launch__occupancy_limit", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__average_warps_issue_stalled", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+    "smsp__inst_executed_op_local", "l1tex__t_sectors_pipe_lsu_mem_local"]
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+H = rows[0]
+for r in rows[2:]:
+    name = r[H.index("Kernel Name")][:70]
+    print("==", name)
+    for h, v in zip(H, r):
+        if any(p in h for p in pats):
+            try:
+                fv = float(v.replace(",", ""))
+                if "stalled" in h and fv < 0.3: continue
+            except ValueError:
+                pass
+            print(f"   {h:85s} {v}")
