@@ -18,10 +18,13 @@
 // Items are (slack, R).  PACKED: u32 = R << 16 | slack when the largest r^2 is below 65536;
 // otherwise u64.
 //
-// Capacities.  The fast kernels keep a line's active set in the thread's local frame (CAP items).
-// Lines that need more (a few, in very large pores) are recorded and redone by a second kernel
-// whose active sets live in a strided global scratch (CAP_BIG items, NSLOTS lines at a time).
-// Anything beyond that, or a full pool, raises a flag and the caller falls back to the scatter.
+// Active sets.  A line's active set is long-lived state that is touched at every step, while the
+// list traffic streams through L1; to keep the former from being evicted by the latter, PACKED
+// kernels hold the first S_SM entries of each buffer in shared memory (48-bit entries in u64,
+// interleaved by thread) and only the tail in the thread's local frame.  Lines that outgrow the
+// frame (a few, in very large pores) are recorded and redone by a second kernel whose active sets
+// live in a global scratch; anything beyond that, or a full pool, raises a flag and the caller
+// falls back to the scatter painter -- never silently.
 #include "common.cuh"
 #include "paint_sep_core.cuh"
 
@@ -29,10 +32,15 @@ namespace bjt {
 
 namespace {
 
-constexpr int XC = 256;                 // x-slab width of stages 2 and 3
+constexpr int XC = 512;                 // x-slab width of stages 2 and 3
 constexpr unsigned long long OFF_MASK = (1ull << 40) - 1ull;
-constexpr int CAP_FAST = 320, FMAX_FAST = 128, CAP_STAIR_FAST = 64;
-constexpr int CAP_BIG = 4096, FMAX_BIG = 1024, NSLOTS = 1024;
+constexpr int TPB = 128;                // threads per block of the line kernels
+constexpr int S_SM = 12;                // entries per buffer kept in shared memory (PACKED kernels)
+constexpr int CAP_TAIL = 628;           // entries per buffer in the local frame behind them
+constexpr int CAP_WIDE = 128;           // local-frame capacity of the wide (u64 item) kernels
+constexpr int FMAX_FAST = 128;
+constexpr int CAP_STAIR = 96;         // local-frame capacity of the stage-3 staircase
+constexpr int CAP_BIG = 4096, FMAX_BIG = 1024, NSLOTS = 2048;
 
 enum : uint32_t { F_POOL1 = 1u, F_POOL2 = 2u, F_ACTIVE = 4u, F_FRONT = 8u };
 
@@ -54,6 +62,30 @@ template <> struct ItemIO<false> {
     }
 };
 struct PlainIO { static __device__ __forceinline__ SepItem get(const SepItem *p, int k) { return p[k]; } };
+
+// PACKED active-set storage: R < 2^16, rho0 < 2^16, |t| < 2^15 -> one u64 per entry.
+// Entry (half, i): i < S_SM in shared memory at sm[(half * S_SM + i) * TPB] (sm already offset by the
+// thread index, so a warp touches 32 consecutive u64), the rest in the local frame.
+struct HybridStore {
+    unsigned long long *sm;
+    unsigned long long loc[2][CAP_TAIL];
+    __device__ __forceinline__ int cap() const { return S_SM + CAP_TAIL; }
+    static __device__ __forceinline__ unsigned long long enc(const SepEntry &e) {
+        return (unsigned long long)e.R | ((unsigned long long)e.rho0 << 16) | ((unsigned long long)(uint32_t)(e.t + 32768) << 32);
+    }
+    static __device__ __forceinline__ SepEntry dec(unsigned long long v) {
+        SepEntry e;
+        e.R = (uint32_t)(v & 0xFFFFu); e.rho0 = (uint32_t)((v >> 16) & 0xFFFFu); e.t = (int)(uint32_t)(v >> 32) - 32768;
+        return e;
+    }
+    __device__ __forceinline__ SepEntry load(int half, int i) const {
+        return dec(i < S_SM ? sm[(half * S_SM + i) * TPB] : loc[half][i - S_SM]);
+    }
+    __device__ __forceinline__ void store(int half, int i, const SepEntry &e) {
+        if (i < S_SM) sm[(half * S_SM + i) * TPB] = enc(e);
+        else loc[half][i - S_SM] = enc(e);
+    }
+};
 
 // warp-aggregated append of nf items per lane; returns the lane's offset or ~0 on pool overflow
 __device__ __forceinline__ unsigned long long warp_alloc(int nf, unsigned long long *counter, unsigned long long cap,
@@ -99,7 +131,7 @@ struct SepArgs {
     uint32_t *flags;
     int *redo_list;          // lines whose fast capacities were too small
     int *redo_count;
-    uint32_t *scratch;       // strided stores of the redo kernels
+    char *scratch;           // stores of the redo kernels
 };
 
 // one line of stage 1 (STAGE == 1: line = row (y,z), position = x) or stage 2 (line = (lx, z), position = y).
@@ -122,19 +154,32 @@ __device__ __forceinline__ bool dyn_line(const SepArgs &a, long long line, bool 
     bool ok = true;
     const typename IO::T *ipool = reinterpret_cast<const typename IO::T *>(a.in_pool);
     typename IO::T *opool = reinterpret_cast<typename IO::T *>(a.out_pool);
+    // the inputs of the next position are requested before this position is processed
+    const long long step_in = a.dir > 0 ? in_stride : -in_stride;
+    long long vi = in_base + (long long)(a.dir > 0 ? 0 : L - 1) * in_stride;
+    uint32_t r_next = 0;
+    unsigned long long eF_next = 0ull, eB_next = 0ull;
+    if (valid) {
+        if (STAGE == 1) r_next = __ldg(a.ridge + vi);
+        else { eF_next = __ldg(a.inF + vi); eB_next = __ldg(a.inB + vi); }
+    }
     for (int step = 0; step < L; ++step) {
         const int t = a.dir > 0 ? step : L - 1 - step;
         int nf = 0;
         if (valid) {
-            const long long vi = in_base + (long long)t * in_stride;
+            const uint32_t r = r_next;
+            const unsigned long long eF = eF_next, eB = eB_next;
+            if (step + 1 < L) {
+                vi += step_in;
+                if (STAGE == 1) r_next = __ldg(a.ridge + vi);
+                else { eF_next = __ldg(a.inF + vi); eB_next = __ldg(a.inB + vi); }
+            }
             if (STAGE == 1) {
-                const uint32_t r = __ldg(a.ridge + vi);
                 if (r | (uint32_t)A.n) {
                     SepItem one; one.rho = r; one.R = r;
                     nf = A.template step<SepItem, PlainIO>(t, a.dir, a.dir < 0, &one, r ? 1 : 0, (const SepItem *)nullptr, 0, fr, fmax, ok);
                 }
             } else {
-                const unsigned long long eF = __ldg(a.inF + vi), eB = __ldg(a.inB + vi);
                 if (eF | eB | (unsigned long long)A.n)
                     nf = A.template step<typename IO::T, IO>(t, a.dir, a.dir < 0, ipool + (eF & OFF_MASK), (int)(eF >> 40),
                                                              ipool + (eB & OFF_MASK), (int)(eB >> 40), fr, fmax, ok);
@@ -165,13 +210,17 @@ __device__ __forceinline__ bool stair_line(const SepArgs &a, long long line, Sta
     const typename IO::T *ipool = reinterpret_cast<const typename IO::T *>(a.in_pool);
     S.clear();
     bool ok = true;
+    const long long step_in = a.dir > 0 ? in_stride : -in_stride;
+    long long vi = in_base + (long long)(a.dir > 0 ? 0 : a.d - 1) * in_stride;
+    unsigned long long eF_next = __ldg(a.inF + vi), eB_next = __ldg(a.inB + vi);
     for (int step = 0; step < a.d; ++step) {
         const int z = a.dir > 0 ? step : a.d - 1 - step;
         const int u = a.dir > 0 ? z : -z;
-        const long long vi = in_base + (long long)z * in_stride;
+        const unsigned long long eF = eF_next, eB = eB_next;
+        if (step + 1 < a.d) { vi += step_in; eF_next = __ldg(a.inF + vi); eB_next = __ldg(a.inB + vi); }
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
-            const unsigned long long e = __ldg((which ? a.inB : a.inF) + vi);
+            const unsigned long long e = which ? eB : eF;
             const typename IO::T *p = ipool + (e & OFF_MASK);
             const int cnt = (int)(e >> 40);
             for (int k = 0; k < cnt; ++k) {
@@ -192,16 +241,25 @@ __device__ __forceinline__ void record_redo(const SepArgs &a, long long line) {
     a.redo_list[slot] = (int)line;
 }
 
+template <bool PACKED> struct FastActive;
+template <> struct FastActive<true> { typedef SepActive<HybridStore> T; };
+template <> struct FastActive<false> { typedef SepActive<SepLocalStore<CAP_WIDE> > T; };
+
 template <bool PACKED, int STAGE>
-__global__ void __launch_bounds__(128) sep_dyn_kernel(SepArgs a) {
+__global__ void __launch_bounds__(TPB) sep_dyn_kernel(SepArgs a) {
+    __shared__ unsigned long long sm[PACKED ? 2 * S_SM * TPB : 1];
     const long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nlines = STAGE == 1 ? (long long)a.h * a.d : (long long)a.xw * a.d;
     const bool valid = line < nlines;
-    SepActive<SepLocalStore<CAP_FAST> > A;
+    typename FastActive<PACKED>::T A;
+    if constexpr (PACKED) A.st.sm = sm + threadIdx.x;
     SepItem fr[FMAX_FAST];
     const bool ok = dyn_line<PACKED, STAGE>(a, line, valid, A, fr, FMAX_FAST);
     if (valid && !ok) record_redo(a, line);
 }
+
+// per-slot scratch of the redo kernels: 2 * CAP_BIG entries, then FMAX_BIG front items
+constexpr size_t SLOT_BYTES = (size_t)2 * CAP_BIG * sizeof(SepEntry) + (size_t)FMAX_BIG * sizeof(SepItem);
 
 // redo: NSLOTS threads, each takes failed lines slot, slot + NSLOTS, ...
 template <bool PACKED, int STAGE>
@@ -209,10 +267,10 @@ __global__ void __launch_bounds__(32) sep_dyn_redo_kernel(SepArgs a) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const int count = *a.redo_count;
     if (count == 0) return;
-    SepActive<SepStridedStore> A;
-    A.st.base = a.scratch + slot; A.st.capacity = CAP_BIG; A.st.stride = NSLOTS;
-    SepItem *fr = reinterpret_cast<SepItem *>(a.scratch + (size_t)NSLOTS * SepStridedStore::words_per_slot(CAP_BIG)) +
-                  (size_t)slot * FMAX_BIG;
+    SepActive<SepFlatStore> A;
+    char *mine = a.scratch + (size_t)slot * SLOT_BYTES;
+    A.st.base = reinterpret_cast<SepEntry *>(mine); A.st.capacity = CAP_BIG;
+    SepItem *fr = reinterpret_cast<SepItem *>(mine + (size_t)2 * CAP_BIG * sizeof(SepEntry));
     for (int base = 0; base < count; base += NSLOTS) {      // warp-uniform trip count
         const int idx = base + slot;
         const bool valid = idx < count;
@@ -223,10 +281,10 @@ __global__ void __launch_bounds__(32) sep_dyn_redo_kernel(SepArgs a) {
 }
 
 template <bool PACKED>
-__global__ void __launch_bounds__(128) sep_stair_kernel(SepArgs a) {
+__global__ void __launch_bounds__(TPB) sep_stair_kernel(SepArgs a) {
     const long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (line >= (long long)a.xw * a.h) return;
-    SepStair<SepLocalStore<CAP_STAIR_FAST, 1, 2> > S;
+    SepStair<SepStairLocal<CAP_STAIR> > S;
     if (!stair_line<PACKED>(a, line, S)) record_redo(a, line);
 }
 
@@ -234,8 +292,10 @@ template <bool PACKED>
 __global__ void __launch_bounds__(32) sep_stair_redo_kernel(SepArgs a) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const int count = *a.redo_count;
-    SepStair<SepStridedStore> S;
-    S.st.base = a.scratch + slot; S.st.capacity = CAP_BIG; S.st.stride = NSLOTS;
+    SepStair<SepStairFlat> S;
+    S.st.R = reinterpret_cast<uint32_t *>(a.scratch + (size_t)slot * SLOT_BYTES);
+    S.st.E = reinterpret_cast<int32_t *>(S.st.R + 2 * CAP_BIG);
+    S.st.capacity = 2 * CAP_BIG;
     for (int idx = slot; idx < count; idx += NSLOTS)
         if (!stair_line<PACKED>(a, a.redo_list[idx], S)) atomicOr(a.flags, (uint32_t)F_ACTIVE);
 }
@@ -263,7 +323,7 @@ Plan make_plan(int w, int h, int d, int wide, int scale) {
     p.off_idx2f = take(p.nslab * 8); p.off_idx2b = take(p.nslab * 8);
     p.off_pool1 = take(p.cap1 * isz); p.off_pool2 = take(p.cap2 * isz);
     p.off_redo = take(p.maxlines * sizeof(int));
-    p.off_scratch = take((size_t)NSLOTS * (SepStridedStore::words_per_slot(CAP_BIG) * 4 + (size_t)FMAX_BIG * sizeof(SepItem)));
+    p.off_scratch = take((size_t)NSLOTS * SLOT_BYTES);
     p.total = o;
     return p;
 }
@@ -277,14 +337,13 @@ int run_sep(const uint32_t *ridge, int w, int h, int d, const Plan &p, char *ws,
     SepArgs base{};
     base.w = w; base.h = h; base.d = d; base.flags = flags;
     base.redo_list = reinterpret_cast<int *>(ws + p.off_redo); base.redo_count = redo_count;
-    base.scratch = reinterpret_cast<uint32_t *>(ws + p.off_scratch);
+    base.scratch = ws + p.off_scratch;
     unsigned long long *idx1f = reinterpret_cast<unsigned long long *>(ws + p.off_idx1f);
     unsigned long long *idx1b = reinterpret_cast<unsigned long long *>(ws + p.off_idx1b);
     unsigned long long *idx2f = reinterpret_cast<unsigned long long *>(ws + p.off_idx2f);
     unsigned long long *idx2b = reinterpret_cast<unsigned long long *>(ws + p.off_idx2b);
     void *pool1 = ws + p.off_pool1, *pool2 = ws + p.off_pool2;
     cudaMemsetAsync(counters, 0, 256, s);
-    const int T = 128;
     // stage 1: both directions share pool 1
     for (int dir = +1; dir >= -1; dir -= 2) {
         SepArgs a = base;
@@ -293,7 +352,7 @@ int run_sep(const uint32_t *ridge, int w, int h, int d, const Plan &p, char *ws,
         a.poolflag = F_POOL1;
         const long long nlines = (long long)h * d;
         cudaMemsetAsync(redo_count, 0, 4, s);
-        sep_dyn_kernel<PACKED, 1><<<(unsigned)((nlines + T - 1) / T), T, 0, s>>>(a);
+        sep_dyn_kernel<PACKED, 1><<<(unsigned)((nlines + TPB - 1) / TPB), TPB, 0, s>>>(a);
         sep_dyn_redo_kernel<PACKED, 1><<<NSLOTS / 32, 32, 0, s>>>(a);
         launches += 2;
     }
@@ -307,7 +366,7 @@ int run_sep(const uint32_t *ridge, int w, int h, int d, const Plan &p, char *ws,
             a.poolflag = F_POOL2;
             const long long nlines = (long long)xw * d;
             cudaMemsetAsync(redo_count, 0, 4, s);
-            sep_dyn_kernel<PACKED, 2><<<(unsigned)((nlines + T - 1) / T), T, 0, s>>>(a);
+            sep_dyn_kernel<PACKED, 2><<<(unsigned)((nlines + TPB - 1) / TPB), TPB, 0, s>>>(a);
             sep_dyn_redo_kernel<PACKED, 2><<<NSLOTS / 32, 32, 0, s>>>(a);
             launches += 2;
         }
@@ -317,7 +376,7 @@ int run_sep(const uint32_t *ridge, int w, int h, int d, const Plan &p, char *ws,
             a.out = rsq;
             const long long nlines = (long long)xw * h;
             cudaMemsetAsync(redo_count, 0, 4, s);
-            sep_stair_kernel<PACKED><<<(unsigned)((nlines + T - 1) / T), T, 0, s>>>(a);
+            sep_stair_kernel<PACKED><<<(unsigned)((nlines + TPB - 1) / TPB), TPB, 0, s>>>(a);
             sep_stair_redo_kernel<PACKED><<<NSLOTS / 32, 32, 0, s>>>(a);
             launches += 2;
         }

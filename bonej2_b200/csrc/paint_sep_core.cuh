@@ -28,6 +28,9 @@ namespace bjt {
 
 struct SepItem { uint32_t rho, R; };
 
+// one active item: tag R, slack rho0 when it arrived, arrival position t
+struct SepEntry { uint32_t R, rho0; int32_t t; };
+
 BJT_HD uint32_t sep_isqrt(uint32_t v) {
     // exact floor(sqrt(v)), v < 2^31
 #if defined(__CUDA_ARCH__)
@@ -40,21 +43,34 @@ BJT_HD uint32_t sep_isqrt(uint32_t v) {
     return r;
 }
 
-// ---- storage policies: fixed arrays in the thread's frame, or strided views of a scratch buffer -----
-template <int CAP, int HALVES = 2, int FIELDS = 4>
-struct SepLocalStore {
-    uint32_t a[HALVES][FIELDS][CAP];
+// an integer >= floor(sqrt(v)) (and <= floor + 2): one conversion, one square root, no loop.
+// A correctly rounded float sqrt is never below the largest integer <= the true root.
+BJT_HD int sep_sqrt_upper(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)v));     // error of a few ulp: + 2 keeps it an upper bound
+    return (int)r + 2;
+#else
+    return (int)__builtin_sqrtf((float)v) + 1;
+#endif
+}
+
+// ---- storage policies --------------------------------------------------------------------------------
+// A store holds two buffers ("halves") of up to cap() entries; step() reads one and writes the other.
+template <int CAP>
+struct SepLocalStore {                 // fixed arrays in the thread's frame
+    SepEntry a[2][CAP];
     BJT_HD int cap() const { return CAP; }
-    BJT_HD uint32_t &at(int half, int field, int i) { return a[half][field][i]; }
+    BJT_HD SepEntry load(int half, int i) const { return a[half][i]; }
+    BJT_HD void store(int half, int i, const SepEntry &e) { a[half][i] = e; }
 };
 
-struct SepStridedStore {            // element (half, field, i) of a slot at base[((half*4+field)*cap + i) * stride]
-    uint32_t *base;
+struct SepFlatStore {                  // a contiguous scratch region of 2 * capacity entries
+    SepEntry *base;
     int capacity;
-    long long stride;
     BJT_HD int cap() const { return capacity; }
-    BJT_HD uint32_t &at(int half, int field, int i) { return base[((long long)(half * 4 + field) * capacity + i) * stride]; }
-    static BJT_HD long long words_per_slot(int capacity_) { return 8ll * capacity_; }
+    BJT_HD SepEntry load(int half, int i) const { return base[(long long)half * capacity + i]; }
+    BJT_HD void store(int half, int i, const SepEntry &e) { base[(long long)half * capacity + i] = e; }
 };
 
 struct SepUnpackPlain { static BJT_HD SepItem get(const SepItem *p, int k) { return p[k]; } };
@@ -65,14 +81,15 @@ struct SepUnpackPlain { static BJT_HD SepItem get(const SepItem *p, int k) { ret
 // One call of step() handles one position of the line: it merges the active set (sorted by R
 // descending) with the items arriving here (two lists, each sorted by R descending) in a single
 // pass, keeps a running "best slack so far" holder b, and for every visited item x decides:
+//   slack_x <  0    : x has expired
 //   slack_x >  best : x is on the front at this position (emitted), x becomes b
 //   slack_x <= best : b dominates x now (R_b >= R_x).  x is dropped for good when b is not older
-//                     than x (the gap then only grows) or when b still dominates x at x's own last
-//                     position (the gap shrinks linearly, so it holds all the way); else x stays.
+//                     than x (the gap then only grows) or when b still dominates x at (or beyond)
+//                     x's own last position (the gap shrinks linearly, so it holds all the way);
+//                     else x stays.
 // Dropping needs a proof of redundancy, keeping never hurts: the result is exact.
 template <class Store>
 struct SepActive {
-    enum { F_T = 0, F_E = 1, F_RHO = 2, F_R = 3 };
     int n, cur;
     Store st;
 
@@ -94,37 +111,37 @@ struct SepActive {
         uint32_t best_R = 0, best_rho0 = 0;
         bool last_emitted = false;
         SepItem af, ab;
-        af.R = 0; af.rho = 0; ab.R = 0; ab.rho = 0;
+        SepEntry ea;
+        af.R = 0; af.rho = 0; ab.R = 0; ab.rho = 0; ea.R = 0; ea.rho0 = 0; ea.t = 0;
         if (nlf > 0) af = Unpack::get(lf, 0);
         if (nlb > 0) ab = Unpack::get(lb, 0);
+        if (n > 0) ea = st.load(src, 0);
         while (true) {
-            while (i < n && (dir > 0 ? (int)st.at(src, F_E, i) < tc : (int)st.at(src, F_E, i) > tc)) ++i;   // expired
-            const uint32_t Ra = i < n ? st.at(src, F_R, i) : 0u;
+            const uint32_t Ra = i < n ? ea.R : 0u;
             const uint32_t Rf = jf < nlf ? af.R : 0u, Rb = jb < nlb ? ab.R : 0u;
             if (!(Ra | Rf | Rb)) break;
-            int ti, ei = 0;
-            uint32_t r0, Ri;
+            SepEntry x;
             bool fresh;
-            if (Rf >= Ra && Rf >= Rb) { ti = tc; r0 = af.rho; Ri = Rf; fresh = true; ++jf; if (jf < nlf) af = Unpack::get(lf, jf); }
-            else if (Rb >= Ra) { ti = tc; r0 = ab.rho; Ri = Rb; fresh = true; ++jb; if (jb < nlb) ab = Unpack::get(lb, jb); }
-            else { ti = (int)st.at(src, F_T, i); ei = (int)st.at(src, F_E, i); r0 = st.at(src, F_RHO, i); Ri = Ra; fresh = false; ++i; }
-            const int s = fresh ? (int)r0 : slack_at(tc, ti, r0);
+            if (Rf >= Ra && Rf >= Rb) { x.t = tc; x.rho0 = af.rho; x.R = Rf; fresh = true; ++jf; if (jf < nlf) af = Unpack::get(lf, jf); }
+            else if (Rb >= Ra) { x.t = tc; x.rho0 = ab.rho; x.R = Rb; fresh = true; ++jb; if (jb < nlb) ab = Unpack::get(lb, jb); }
+            else { x = ea; fresh = false; ++i; if (i < n) ea = st.load(src, i); }
+            const int s = fresh ? (int)x.rho0 : slack_at(tc, x.t, x.rho0);
+            if (s < 0) continue;                                           // expired
             if (s > best) {
-                if (best >= 0 && best_R == Ri && last_emitted) --nf;      // same tag, more slack: replace
-                best = s; best_t = ti; best_R = Ri; best_rho0 = r0;
-                last_emitted = !(skip_own && ti == tc);
+                if (best >= 0 && best_R == x.R && last_emitted) --nf;      // same tag, more slack: replace
+                best = s; best_t = x.t; best_R = x.R; best_rho0 = x.rho0;
+                last_emitted = !(skip_own && x.t == tc);
                 if (last_emitted) {
-                    if (nf < fmax) { out[nf].rho = (uint32_t)s; out[nf].R = Ri; }
+                    if (nf < fmax) { out[nf].rho = (uint32_t)s; out[nf].R = x.R; }
                     ++nf;
                 }
-                if (fresh) ei = tc + dir * (int)sep_isqrt(r0);
             } else {
-                if (dir > 0 ? best_t >= ti : best_t <= ti) continue;       // dominated by an item that is not older
-                if (fresh) ei = tc + dir * (int)sep_isqrt(r0);
-                if (slack_at(ei, best_t, best_rho0) >= slack_at(ei, ti, r0)) continue;   // dominated for life
+                if (dir > 0 ? best_t >= x.t : best_t <= x.t) continue;     // dominated by an item that is not older
+                const int ex = x.t + dir * sep_sqrt_upper(x.rho0);         // at or beyond x's last position
+                if (slack_at(ex, best_t, best_rho0) >= slack_at(ex, x.t, x.rho0)) continue;   // dominated for life
             }
             if (w >= cap) { ok = false; continue; }
-            st.at(dst, F_T, w) = (uint32_t)ti; st.at(dst, F_E, w) = (uint32_t)ei; st.at(dst, F_RHO, w) = r0; st.at(dst, F_R, w) = Ri;
+            st.store(dst, w, x);
             ++w;
         }
         n = w; cur = dst;
@@ -133,53 +150,72 @@ struct SepActive {
 };
 
 // ---------------------------------------------------------------------------------------------
-// static staircase (stage 3): R descending, reach E (last covered coordinate in sweep direction) ascending
-template <class Store>      // uses fields 0 = R, 1 = E of half 0
+// static staircase (stage 3): R descending, reach E (last covered coordinate in sweep direction) ascending.
+// Store concept: cap(), getR(i), getE(i), put(i, R, E).
+template <int CAP>
+struct SepStairLocal {
+    uint32_t R[CAP];
+    int32_t E[CAP];
+    BJT_HD int cap() const { return CAP; }
+    BJT_HD uint32_t getR(int i) const { return R[i]; }
+    BJT_HD int getE(int i) const { return E[i]; }
+    BJT_HD void put(int i, uint32_t r, int e) { R[i] = r; E[i] = e; }
+};
+
+struct SepStairFlat {                  // scratch region: capacity R values, then capacity E values
+    uint32_t *R;
+    int32_t *E;
+    int capacity;
+    BJT_HD int cap() const { return capacity; }
+    BJT_HD uint32_t getR(int i) const { return R[i]; }
+    BJT_HD int getE(int i) const { return E[i]; }
+    BJT_HD void put(int i, uint32_t r, int e) { R[i] = r; E[i] = e; }
+};
+
+template <class Store>
 struct SepStair {
     int n;
     Store st;
 
     BJT_HD void clear() { n = 0; }
-    BJT_HD uint32_t &Rr(int i) { return st.at(0, 0, i); }
-    BJT_HD uint32_t &Er(int i) { return st.at(0, 1, i); }
 
     // u = coordinate in sweep direction (z forward, -z backward).  Returns false on overflow.
     BJT_HD bool arrive(int u, uint32_t rho, uint32_t Rn) {
         // cheap reject against the head: R_n <= R_head and reach_n <= reach_head
-        if (n > 0 && Rn <= Rr(0)) {
-            const int span = (int)Er(0) - u;
+        if (n > 0 && Rn <= st.getR(0)) {
+            const int span = st.getE(0) - u;
             if (span >= 0 && rho < (uint32_t)(span + 1) * (uint32_t)(span + 1)) return true;
         }
         const int En = u + (int)sep_isqrt(rho);
         int pos = 0;
-        while (pos < n && Rr(pos) > Rn) ++pos;
-        if (pos > 0 && (int)Er(pos - 1) >= En) return true;              // a larger tag reaches at least as far
-        if (pos < n && Rr(pos) == Rn && (int)Er(pos) >= En) return true;
+        while (pos < n && st.getR(pos) > Rn) ++pos;
+        if (pos > 0 && st.getE(pos - 1) >= En) return true;            // a larger tag reaches at least as far
+        if (pos < n && st.getR(pos) == Rn && st.getE(pos) >= En) return true;
         int k = pos;
-        while (k < n && (int)Er(k) <= En) ++k;                            // R <= R_n and reach <= reach_n: redundant
+        while (k < n && st.getE(k) <= En) ++k;                          // R <= R_n and reach <= reach_n: redundant
         const int removed = k - pos;
         if (removed == 0) {
             if (n >= st.cap()) return false;
-            for (int i = n; i > pos; --i) { Rr(i) = Rr(i - 1); Er(i) = Er(i - 1); }
+            for (int i = n; i > pos; --i) st.put(i, st.getR(i - 1), st.getE(i - 1));
             ++n;
         } else if (removed > 1) {
             const int sh = removed - 1;
-            for (int i = k; i < n; ++i) { Rr(i - sh) = Rr(i); Er(i - sh) = Er(i); }
+            for (int i = k; i < n; ++i) st.put(i - sh, st.getR(i), st.getE(i));
             n -= sh;
         }
-        Rr(pos) = Rn; Er(pos) = (uint32_t)En;
+        st.put(pos, Rn, En);
         return true;
     }
 
     // value at coordinate u (after this position's arrivals): largest tag still reaching u
     BJT_HD uint32_t query(int u) {
         int h = 0;
-        while (h < n && (int)Er(h) < u) ++h;
+        while (h < n && st.getE(h) < u) ++h;
         if (h > 0) {
-            for (int i = h; i < n; ++i) { Rr(i - h) = Rr(i); Er(i - h) = Er(i); }
+            for (int i = h; i < n; ++i) st.put(i - h, st.getR(i), st.getE(i));
             n -= h;
         }
-        return n > 0 ? Rr(0) : 0u;
+        return n > 0 ? st.getR(0) : 0u;
     }
 };
 

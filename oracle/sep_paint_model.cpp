@@ -67,7 +67,7 @@ void dyn_line(const uint32_t *src, const Lists *inF, const Lists *inB, size_t ba
 }
 
 void stair_line(const Lists &inF, const Lists &inB, size_t base, int L, int dir, uint32_t *out, spm_stats_t *st) {
-    static SepStair<SepLocalStore<CAP, 1, 2> > S;
+    static SepStair<SepStairLocal<CAP> > S;
     S.clear();
     for (int step = 0; step < L; ++step) {
         const int x = dir > 0 ? step : L - 1 - step;
