@@ -22,6 +22,7 @@ using namespace bjt;
 struct bjt_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // downloads that overlap the next run
     bool own_stream = false;
     char err[512] = {0};
     std::mutex mu;
@@ -106,6 +107,7 @@ int bjt_create(bjt_ctx **out, int device) {
         return BJT_E_CUDA;
     }
     c->own_stream = true;
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) c->copy_stream = nullptr;
     for (auto &ev : c->ev) cudaEventCreate(&ev);
     *out = c;
     return BJT_OK;
@@ -128,6 +130,7 @@ void bjt_destroy(bjt_ctx *c) {
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }
 
@@ -439,27 +442,36 @@ static int host_run(bjt_ctx *c, const uint8_t *in, const uint8_t *const *in_slic
         CK(cudaMemcpyAsync(d_in + z * wh, in_slices[z], wh, cudaMemcpyHostToDevice, c->stream));
     }
     CK(cudaEventRecord(c->ev[9], c->stream));
+    // "Both": the download of the first map runs on the copy stream while the second run computes into
+    // a second device buffer
+    const bool overlap = both && out0 && c->copy_stream;
     for (int run = 0; run < (both ? 2 : 1); ++run) {
         const int inv = both ? run : inverse;
         float *out = run == 0 ? out0 : out1;
         bjt_timing *tm = run == 0 ? tm0 : tm1;
         const bool want_map = out || (run == 0 && out_slices);
-        rc = dev_pipeline(c, d_in, w, h, d, inv, mask, threshold, pixel_width, want_map ? d_out : nullptr,
-                          run == 0 ? st0 : st1, tm);
+        float *d_dst = d_out;
+        if (run == 1 && overlap) WS("out2", N * sizeof(float), d_dst);
+        rc = dev_pipeline(c, d_in, w, h, d, inv, mask, threshold, pixel_width, want_map ? d_dst : nullptr,
+                          run == 0 ? st0 : st1, tm);      // returns with the compute stream idle
         if (rc) return rc;
-        CK(cudaEventRecord(c->ev[10], c->stream));
-        if (out) CK(cudaMemcpyAsync(out, d_out, N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        cudaStream_t cs = (run == 0 && overlap) ? c->copy_stream : c->stream;
+        CK(cudaEventRecord(c->ev[10 + 2 * run], cs));
+        if (out) CK(cudaMemcpyAsync(out, d_dst, N * sizeof(float), cudaMemcpyDeviceToHost, cs));
         else if (run == 0 && out_slices) for (int z = 0; z < d; ++z) {
             if (!out_slices[z]) return fail(c, BJT_E_ARG, "null output slice %d", z);
-            CK(cudaMemcpyAsync(out_slices[z], d_out + z * wh, wh * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(out_slices[z], d_dst + z * wh, wh * sizeof(float), cudaMemcpyDeviceToHost, cs));
         }
-        CK(cudaEventRecord(c->ev[11], c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        if (tm) {
-            if (run == 0) cudaEventElapsedTime(&tm->ms_h2d, c->ev[8], c->ev[9]);
-            cudaEventElapsedTime(&tm->ms_d2h, c->ev[10], c->ev[11]);
-            tm->ms_total += tm->ms_h2d + tm->ms_d2h;
-        }
+        CK(cudaEventRecord(c->ev[11 + 2 * run], cs));
+        if (!(run == 0 && overlap)) CK(cudaStreamSynchronize(cs));
+    }
+    if (overlap) CK(cudaStreamSynchronize(c->copy_stream));
+    for (int run = 0; run < (both ? 2 : 1); ++run) {
+        bjt_timing *tm = run == 0 ? tm0 : tm1;
+        if (!tm) continue;
+        if (run == 0) cudaEventElapsedTime(&tm->ms_h2d, c->ev[8], c->ev[9]);
+        cudaEventElapsedTime(&tm->ms_d2h, c->ev[10 + 2 * run], c->ev[11 + 2 * run]);
+        tm->ms_total += tm->ms_h2d + tm->ms_d2h;
     }
     return BJT_OK;
 }

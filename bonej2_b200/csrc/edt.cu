@@ -243,6 +243,8 @@ __device__ __forceinline__ Vec4 load4(const uint32_t *p, uint32_t) {
     return o;
 }
 
+constexpr int PF = 8;      // prefetch distance (line positions)
+
 template <typename TIn, bool MARK>
 __global__ void __launch_bounds__(128) edt_line4_kernel(const TIn *__restrict__ in, uint32_t *__restrict__ out, int w4,
                                                          long long ngroups, long long outer, long long stride, int L,
@@ -264,7 +266,9 @@ __global__ void __launch_bounds__(128) edt_line4_kernel(const TIn *__restrict__ 
         for (int c = 0; c < 4; ++c) { a[c] = 0; fa[c] = cur.v[c]; prev[c] = 0xFFFFFFFFu; dead[c] = false; }
         for (int y = 0; y < L; ++y) {
             const Vec4 fy = cur;
-            if (y + 1 < L) cur = load4(col + (long long)(y + 1) * stride, n0);     // prefetch the next position
+            if (y + 1 < L) cur = load4(col + (long long)(y + 1) * stride, n0);     // the next position, in registers
+            if (y + PF < L)                                                        // and a few further ones into L1
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(col + (long long)(y + PF) * stride));
             uint32_t m[4], fbest[4];
             int best[4];
             uint32_t mmax = 0;

@@ -21,16 +21,10 @@ namespace bjt {
 
 constexpr int FTX = 32, FTY = 8, FTZ = 8;
 constexpr int HX = FTX + 4, HY = FTY + 4, HZ = FTZ + 4;       // r^2 tile with 2-voxel halo
-constexpr int IX = FTX + 2, IY = FTY + 2, IZ = FTZ + 2;       // interior flags with 1-voxel halo
+constexpr int IY = FTY + 2, IZ = FTZ + 2;                      // interior flag rows with 1-voxel halo
 constexpr uint32_t OUTSIDE = 0xFFFFFFFFu;
 
-// neighbour visiting order of the cleanup average: 6 faces, 12 edges, 8 corners (dx, dy, dz)
-__constant__ int8_t NB26[26][3] = {
-    {0, 0, -1}, {0, 0, 1}, {0, -1, 0}, {0, 1, 0}, {-1, 0, 0}, {1, 0, 0},
-    {0, 1, -1}, {0, 1, 1}, {1, -1, 0}, {1, 1, 0}, {-1, 0, 1}, {1, 0, 1},
-    {0, -1, -1}, {0, -1, 1}, {-1, -1, 0}, {-1, 1, 0}, {-1, 0, -1}, {1, 0, -1},
-    {1, 1, 1}, {1, -1, 1}, {-1, 1, 1}, {-1, -1, 1},
-    {1, 1, -1}, {1, -1, -1}, {-1, 1, -1}, {-1, -1, -1}};
+// neighbour visiting order of the cleanup average (A.4): 6 faces, 12 edges, 8 corners -- see BJT_NBR below
 
 __device__ __forceinline__ float thickness_of(uint32_t R) { return 2.0f * sqrtf((float)R); }   // == (float)(2*sqrt((double)R)), R < 2^24
 
@@ -62,67 +56,121 @@ __device__ __forceinline__ void block_reduce_stats(double sum, double sum2, doub
 
 // Output and statistics cover z in [z_lo, z_hi) of the local volume; `out` and nothing else is indexed
 // relative to z_lo (a sharded caller passes its slab plus halo planes and keeps the core).
-__global__ void __launch_bounds__(FTX *FTY) finish_kernel(const uint32_t *__restrict__ rsq,
+__global__ void __launch_bounds__(FTX *FTY, 4) finish_kernel(const uint32_t *__restrict__ rsq,
                                                           const uint8_t *__restrict__ original, int w, int h, int d,
                                                           int z_lo, int z_hi, int fgval, int calibrate, float pw,
                                                           float *__restrict__ out, StatsPartial *__restrict__ partials) {
-    __shared__ uint32_t R[HZ][HY][HX];
-    __shared__ uint8_t inter[IZ][IY][IX];
+    __shared__ float S[HZ][HY][HX];            // 2*sqrt(r^2) of every tile cell (0 for empty and outside cells)
+    // one 64-bit word per tile row (z, y): bit x set = cell is not zero (outside the image counts as not
+    // zero) / cell is inside the image / cell is interior
+    __shared__ unsigned long long nzrow[HZ][HY], inrow[HZ][HY], itrow[HZ][HY];
+    __shared__ uint8_t og[FTZ][FTY][FTX];
     const int bx = blockIdx.x * FTX, by = blockIdx.y * FTY, bz = z_lo + blockIdx.z * FTZ;
     const int tid = threadIdx.x + FTX * threadIdx.y;
+    const int lane = tid & 31, warp = tid >> 5;
     const size_t wh = (size_t)w * h;
-    for (int i = tid; i < HZ * HY * HX; i += FTX * FTY) {
-        const int lx = i % HX, ly = (i / HX) % HY, lz = i / (HX * HY);
-        const int gx = bx + lx - 2, gy = by + ly - 2, gz = bz + lz - 2;
-        uint32_t v = OUTSIDE;
-        if (gx >= 0 && gx < w && gy >= 0 && gy < h && gz >= 0 && gz < d) v = __ldg(rsq + gz * wh + (size_t)gy * w + gx);
-        R[lz][ly][lx] = v;
+    // a warp loads whole tile rows (36 cells: lanes 0..31, then lanes 0..3) and ballots the masks
+    constexpr int NWARP = (FTX * FTY) / 32, RPW = (HZ * HY) / NWARP;      // 18 rows per warp
+    static_assert(RPW * NWARP == HZ * HY, "tile rows must divide evenly over the warps");
+    const int gx0 = bx + lane - 2, gx1 = bx + lane + 30;
+    constexpr int BATCH = RPW / 2;             // two batches of 9 rows: 18 independent requests in flight per lane
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        uint32_t v0[BATCH], v1[BATCH];
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+            const int r = warp + (b * BATCH + k) * NWARP;
+            const int lz = r / HY, ly = r % HY;
+            const int gy = by + ly - 2, gz = bz + lz - 2;
+            const bool row_in = gy >= 0 && gy < h && gz >= 0 && gz < d;
+            const uint32_t *src = rsq + (row_in ? gz * wh + (size_t)gy * w : 0);
+            v0[k] = (row_in && gx0 >= 0 && gx0 < w) ? __ldg(src + gx0) : OUTSIDE;
+            v1[k] = (lane < 4 && row_in && gx1 >= 0 && gx1 < w) ? __ldg(src + gx1) : OUTSIDE;
+        }
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+            const int r = warp + (b * BATCH + k) * NWARP;
+            const int lz = r / HY, ly = r % HY;
+            const int gy = by + ly - 2, gz = bz + lz - 2;
+            const bool row_in = gy >= 0 && gy < h && gz >= 0 && gz < d;
+            const bool in0 = row_in && gx0 >= 0 && gx0 < w, in1 = lane < 4 && row_in && gx1 >= 0 && gx1 < w;
+            S[lz][ly][lane] = (v0[k] == OUTSIDE || v0[k] == 0u) ? 0.0f : thickness_of(v0[k]);
+            if (lane < 4) S[lz][ly][32 + lane] = (v1[k] == OUTSIDE || v1[k] == 0u) ? 0.0f : thickness_of(v1[k]);
+            const unsigned nz0 = __ballot_sync(0xFFFFFFFFu, v0[k] != 0u), nz1 = __ballot_sync(0xFFFFFFFFu, lane < 4 && v1[k] != 0u);
+            const unsigned i0 = __ballot_sync(0xFFFFFFFFu, in0), i1 = __ballot_sync(0xFFFFFFFFu, in1);
+            if (lane == 0) {
+                nzrow[lz][ly] = (unsigned long long)nz0 | ((unsigned long long)nz1 << 32);
+                inrow[lz][ly] = (unsigned long long)i0 | ((unsigned long long)i1 << 32);
+            }
+        }
+    }
+    // the mask bytes of the block's 32 x 8 x 8 voxels
+    {
+        const int x = bx + threadIdx.x, y = by + threadIdx.y;
+        uint8_t o[FTZ];
+#pragma unroll
+        for (int tz = 0; tz < FTZ; ++tz) {
+            const int z = bz + tz;
+            o[tz] = (uint8_t)fgval;
+            if (original && x < w && y < h && z < z_hi && z < d) o[tz] = __ldg(original + z * wh + (size_t)y * w + x);
+        }
+#pragma unroll
+        for (int tz = 0; tz < FTZ; ++tz) og[tz][threadIdx.y][threadIdx.x] = o[tz];
     }
     __syncthreads();
-    for (int i = tid; i < IZ * IY * IX; i += FTX * FTY) {
-        const int lx = i % IX, ly = (i / IX) % IY, lz = i / (IX * IY);
-        const uint32_t c = R[lz + 1][ly + 1][lx + 1];
-        uint8_t f = 0;
-        if (c != 0u && c != OUTSIDE) {
-            bool all = true;
+    // interior(x) = inside && not zero && all 27 cells around it not zero: AND of the 9 neighbouring rows,
+    // each already ANDed with its two x-shifts
+    if (tid < IZ * IY) {
+        const int lz = 1 + tid / IY, ly = 1 + tid % IY;
+        unsigned long long all = ~0ull;
 #pragma unroll
-            for (int dz = 0; dz < 3; ++dz)
+        for (int dz = -1; dz <= 1; ++dz)
 #pragma unroll
-                for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) all = all && (R[lz + dz][ly + dy][lx + dx] != 0u);
-            f = all ? 1 : 0;
-        }
-        inter[lz][ly][lx] = f;
+            for (int dy = -1; dy <= 1; ++dy) {
+                const unsigned long long m = nzrow[lz + dz][ly + dy];
+                all &= m & (m >> 1) & (m << 1);
+            }
+        itrow[lz][ly] = all & inrow[lz][ly];
     }
     __syncthreads();
     double sum = 0, sum2 = 0, mn = INFINITY, mx = -INFINITY;
     long long cnt = 0;
     const int x = bx + threadIdx.x, y = by + threadIdx.y;
     if (x < w && y < h) {
-        const int tx = threadIdx.x, ty = threadIdx.y;
+        const int cx = threadIdx.x + 2, cy = threadIdx.y + 2;
 #pragma unroll 1
         for (int tz = 0; tz < FTZ; ++tz) {
             const int z = bz + tz;
             if (z >= z_hi || z >= d) break;
-            const uint32_t c = R[tz + 2][ty + 2][tx + 2];
-            float v = 0.0f;
-            if (c != 0u) {
-                if (inter[tz + 1][ty + 1][tx + 1]) {
-                    v = thickness_of(c);
-                } else {
-                    float s = 0.0f;
-                    int n = 0;
+            const int cz = tz + 2;
+            const float c = S[cz][cy][cx];
+            float v = c;
+            if (c != 0.0f && !((itrow[cz][cy] >> cx) & 1ull)) {
+                // surface voxel: float32 mean of the interior neighbours, faces, edges, corners in turn.
+                // The 9 flag rows sit in registers; adding 0.0f for the other neighbours is exact.
+                unsigned long long rows[3][3];
 #pragma unroll
-                    for (int q = 0; q < 26; ++q) {
-                        const int dx = NB26[q][0], dy = NB26[q][1], dz = NB26[q][2];
-                        if (inter[tz + 1 + dz][ty + 1 + dy][tx + 1 + dx]) { s += thickness_of(R[tz + 2 + dz][ty + 2 + dy][tx + 2 + dx]); ++n; }
-                    }
-                    v = n > 0 ? s / (float)n : thickness_of(c);
-                }
+                for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) rows[dz][dy] = itrow[cz + dz - 1][cy + dy - 1] >> (cx - 1);
+                float s = 0.0f;
+                int n = 0;
+#define BJT_NBR(dx, dy, dz)                                                         \
+    {                                                                              \
+        const bool in_ = (rows[(dz) + 1][(dy) + 1] >> ((dx) + 1)) & 1ull;          \
+        s += in_ ? S[cz + (dz)][cy + (dy)][cx + (dx)] : 0.0f;                      \
+        n += in_ ? 1 : 0;                                                          \
+    }
+                BJT_NBR(0, 0, -1) BJT_NBR(0, 0, 1) BJT_NBR(0, -1, 0) BJT_NBR(0, 1, 0) BJT_NBR(-1, 0, 0) BJT_NBR(1, 0, 0)
+                BJT_NBR(0, 1, -1) BJT_NBR(0, 1, 1) BJT_NBR(1, -1, 0) BJT_NBR(1, 1, 0) BJT_NBR(-1, 0, 1) BJT_NBR(1, 0, 1)
+                BJT_NBR(0, -1, -1) BJT_NBR(0, -1, 1) BJT_NBR(-1, -1, 0) BJT_NBR(-1, 1, 0) BJT_NBR(-1, 0, -1) BJT_NBR(1, 0, -1)
+                BJT_NBR(1, 1, 1) BJT_NBR(1, -1, 1) BJT_NBR(-1, 1, 1) BJT_NBR(-1, -1, 1)
+                BJT_NBR(1, 1, -1) BJT_NBR(1, -1, -1) BJT_NBR(-1, 1, -1) BJT_NBR(-1, -1, -1)
+#undef BJT_NBR
+                v = n > 0 ? s / (float)n : c;
             }
             const size_t p = z * wh + (size_t)y * w + x;
-            if (original && (int)__ldg(original + p) != fgval) v = 0.0f;
+            if ((int)og[tz][threadIdx.y][threadIdx.x] != fgval) v = 0.0f;
             if (calibrate) {
                 if (v == 0.0f) v = __int_as_float(0x7FC00000);
                 v = v * pw;

@@ -87,9 +87,13 @@ struct HybridStore {
     }
 };
 
-// warp-aggregated append of nf items per lane; returns the lane's offset or ~0 on pool overflow
+// warp-aggregated append of nf items per lane; returns the lane's offset or ~0 on pool overflow.
+// A warp takes CHUNK items at a time from the global counter (one same-address atomic per chunk, not
+// per step) and hands them out from registers; chunk_base / chunk_left are warp-uniform.
+constexpr int CHUNK = 4096;
 __device__ __forceinline__ unsigned long long warp_alloc(int nf, unsigned long long *counter, unsigned long long cap,
-                                                         uint32_t *flags, uint32_t flagbit) {
+                                                         uint32_t *flags, uint32_t flagbit,
+                                                         unsigned long long &chunk_base, int &chunk_left) {
     const int lane = threadIdx.x & 31;
     int incl = nf;
 #pragma unroll
@@ -99,14 +103,22 @@ __device__ __forceinline__ unsigned long long warp_alloc(int nf, unsigned long l
     }
     const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
     if (total == 0) return 0ull;
-    unsigned long long base = 0ull;
-    if (lane == 0) base = atomicAdd(counter, (unsigned long long)total);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (base + (unsigned long long)total > cap) {
-        if (lane == 0) atomicOr(flags, flagbit);
-        return ~0ull;
+    if (total > chunk_left) {
+        const int take = total > CHUNK ? total : CHUNK;
+        unsigned long long base = 0ull;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)take);
+        chunk_base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        chunk_left = take;
+        if (chunk_base + (unsigned long long)take > cap) {
+            if (lane == 0) atomicOr(flags, flagbit);
+            chunk_left = 0;
+            return ~0ull;
+        }
     }
-    return base + (unsigned long long)(incl - nf);
+    const unsigned long long off = chunk_base + (unsigned long long)(incl - nf);
+    chunk_base += (unsigned long long)total;
+    chunk_left -= total;
+    return off;
 }
 
 struct SepArgs {
@@ -154,6 +166,8 @@ __device__ __forceinline__ bool dyn_line(const SepArgs &a, long long line, bool 
     bool ok = true;
     const typename IO::T *ipool = reinterpret_cast<const typename IO::T *>(a.in_pool);
     typename IO::T *opool = reinterpret_cast<typename IO::T *>(a.out_pool);
+    unsigned long long chunk_base = 0ull;
+    int chunk_left = 0;
     // the inputs of the next position are requested before this position is processed
     const long long step_in = a.dir > 0 ? in_stride : -in_stride;
     long long vi = in_base + (long long)(a.dir > 0 ? 0 : L - 1) * in_stride;
@@ -186,7 +200,7 @@ __device__ __forceinline__ bool dyn_line(const SepArgs &a, long long line, bool 
             }
             if (nf > fmax) { ok = false; nf = fmax; }
         }
-        const unsigned long long off = warp_alloc(nf, a.out_counter, a.out_cap, a.flags, a.poolflag);
+        const unsigned long long off = warp_alloc(nf, a.out_counter, a.out_cap, a.flags, a.poolflag, chunk_base, chunk_left);
         if (valid) {
             unsigned long long entry = 0ull;
             if (nf > 0 && off != ~0ull) {
@@ -314,8 +328,9 @@ Plan make_plan(int w, int h, int d, int wide, int scale) {
     const size_t l1 = (size_t)h * d, l2 = (size_t)xw * d, l3 = (size_t)xw * h;
     p.maxlines = l1 > l2 ? (l1 > l3 ? l1 : l3) : (l2 > l3 ? l2 : l3);
     const size_t isz = wide ? 8 : 4;
-    p.cap1 = (unsigned long long)p.n * (unsigned)(4 * scale) + 65536;      // items
-    p.cap2 = (unsigned long long)p.nslab * (unsigned)(12 * scale) + 65536;
+    // items; every warp may leave up to one CHUNK unused per sweep
+    p.cap1 = (unsigned long long)p.n * (unsigned)(4 * scale) + (unsigned long long)(l1 / 32 + 1) * CHUNK * 2 + 65536;
+    p.cap2 = (unsigned long long)p.nslab * (unsigned)(12 * scale) + (unsigned long long)(l2 / 32 + 1) * CHUNK * 2 + 65536;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
     p.off_counters = take(256);

@@ -144,9 +144,14 @@ __global__ void __launch_bounds__(RTX *RTY *RTZ) ridge_kernel(const uint32_t *__
         }
         ridge[z * wh + (size_t)y * w + x] = is_ridge ? v : 0u;
     }
-    // block count of ridge points
+    // block count of ridge points: one atomic per block (a per-warp atomic on one address serialises in L2)
+    __shared__ unsigned int block_count;
+    if (tid == 0) block_count = 0;
+    __syncthreads();
     const unsigned ballot = __ballot_sync(0xFFFFFFFFu, is_ridge);
-    if ((tid & 31) == 0 && ballot) atomicAdd(count, (unsigned long long)__popc(ballot));
+    if ((tid & 31) == 0 && ballot) atomicAdd(&block_count, (unsigned)__popc(ballot));
+    __syncthreads();
+    if (tid == 0 && block_count) atomicAdd(count, (unsigned long long)block_count);
 }
 
 int launch_ridge(const uint32_t *sq, int w, int h, int d, const uint32_t *t1, const uint32_t *t2, const uint32_t *t3,
