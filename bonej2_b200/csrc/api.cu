@@ -192,17 +192,15 @@ static void stats_out(const StatsPartial &r, bjt_stats *st) {
 static int dev_edt(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, int inverse, int thresh, int n_sentinel,
                    uint16_t *gx, uint32_t *gy, uint32_t *sq, uint32_t *maxval_host, cudaEvent_t *evs) {
     const uint32_t n0 = no_result(n_sentinel);
-    uint8_t *present; uint32_t *scal;
-    WS("present", (size_t)n0 + 1, present);
+    uint32_t *scal;
     WS("scalars", 256, scal);
-    CK(cudaMemsetAsync(present, 0, (size_t)n0 + 1, c->stream));
     CK(cudaMemsetAsync(scal, 0, 256, c->stream));
     if (evs) CK(cudaEventRecord(evs[0], c->stream));
     c->launches += launch_edt_x(d_in, w, h, d, inverse, thresh, gx, c->stream); CKL();
     if (evs) CK(cudaEventRecord(evs[1], c->stream));
     c->launches += launch_edt_y(gx, w, h, d, n0, gy, c->stream); CKL();
     if (evs) CK(cudaEventRecord(evs[2], c->stream));
-    c->launches += launch_edt_z(gy, w, h, d, n0, sq, present, scal, c->stream); CKL();
+    c->launches += launch_edt_z(gy, w, h, d, n0, sq, nullptr, scal, c->stream); CKL();
     if (evs) CK(cudaEventRecord(evs[3], c->stream));
     if (maxval_host) {
         CK(cudaMemcpyAsync(c->h_scal, scal, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -212,19 +210,30 @@ static int dev_edt(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, int inv
     return BJT_OK;
 }
 
-// present table (zeroed or filled by the z pass) -> thresholds -> ridge.  maxval: largest sq value.
-static int dev_ridge(bjt_ctx *c, const uint32_t *sq, int w, int h, int d, uint32_t maxval, const uint8_t *present,
-                     uint32_t *ridge, int64_t *n_ridge) {
+// thresholds -> ridge.  maxval: largest value of sq.  Up to 65536 the thresholds are simply computed for
+// every r^2 in 1..maxval (values that do not occur are never looked up); beyond that only for the values
+// that occur, found with a presence table.
+static int dev_ridge(bjt_ctx *c, const uint32_t *sq, int w, int h, int d, uint32_t maxval, uint32_t *ridge,
+                     int64_t *n_ridge) {
+    const size_t N = (size_t)w * h * d;
     uint32_t *values, *t1, *t2, *t3, *scal;
     const size_t tb = ((size_t)maxval + 1) * sizeof(uint32_t);
-    WS("values", tb, values); WS("t1", tb, t1); WS("t2", tb, t2); WS("t3", tb, t3);
+    WS("t1", tb, t1); WS("t2", tb, t2); WS("t3", tb, t3);
     WS("scalars", 256, scal);
     CK(cudaMemsetAsync(scal + 2, 0, 16, c->stream));   // [2] = nvalues, [4..5] = ridge count (u64)
-    c->launches += launch_collect_values(present, maxval, values, scal + 2, c->stream); CKL();
-    CK(cudaMemcpyAsync(c->h_scal + 2, scal + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    const uint32_t nvalues = c->h_scal[2];
-    c->launches += launch_ridge_template(values, nvalues, t1, t2, t3, c->stream); CKL();
+    if (maxval <= 65536u) {
+        c->launches += launch_ridge_template(nullptr, maxval, t1, t2, t3, c->stream); CKL();
+    } else {
+        uint8_t *present;
+        WS("values", tb, values);
+        WS("present", (size_t)maxval + 1, present);
+        CK(cudaMemsetAsync(present, 0, (size_t)maxval + 1, c->stream));
+        c->launches += launch_mark_present(sq, N, present, scal + 6, c->stream); CKL();
+        c->launches += launch_collect_values(present, maxval, values, scal + 2, c->stream); CKL();
+        CK(cudaMemcpyAsync(c->h_scal + 2, scal + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->launches += launch_ridge_template(values, c->h_scal[2], t1, t2, t3, c->stream); CKL();
+    }
     c->launches += launch_ridge(sq, w, h, d, t1, t2, t3, ridge, (unsigned long long *)(scal + 4), c->stream); CKL();
     if (n_ridge) {
         CK(cudaMemcpyAsync(c->h_scal + 4, scal + 4, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -234,20 +243,16 @@ static int dev_ridge(bjt_ctx *c, const uint32_t *sq, int w, int h, int d, uint32
     return BJT_OK;
 }
 
-// ridge of an arbitrary squared map on the device: largest value, presence table, thresholds, test
+// ridge of an arbitrary squared map on the device: largest value first, then as above
 static int dev_ridge_full(bjt_ctx *c, const uint32_t *sq, int w, int h, int d, uint32_t *ridge, int64_t *n_ridge) {
     const size_t N = (size_t)w * h * d;
-    uint32_t *scal; uint8_t *present;
+    uint32_t *scal;
     WS("scalars", 256, scal);
     CK(cudaMemsetAsync(scal, 0, 4, c->stream));
     c->launches += launch_mark_present(sq, N, nullptr, scal, c->stream); CKL();
     CK(cudaMemcpyAsync(c->h_scal, scal, 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    const uint32_t maxval = c->h_scal[0];
-    WS("present", (size_t)maxval + 1, present);
-    CK(cudaMemsetAsync(present, 0, (size_t)maxval + 1, c->stream));
-    c->launches += launch_mark_present(sq, N, present, scal, c->stream); CKL();
-    return dev_ridge(c, sq, w, h, d, maxval, present, ridge, n_ridge);
+    return dev_ridge(c, sq, w, h, d, c->h_scal[0], ridge, n_ridge);
 }
 
 static int dev_paint(bjt_ctx *c, const uint32_t *ridge, int w, int h, int d, int path, int64_t n_ridge_known,
@@ -356,7 +361,6 @@ static int dev_pipeline(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, in
     int rc = dev_edt(c, d_in, w, h, d, inverse, thresh, n, gx, bufA, bufB, &maxval, c->ev);
     if (rc) return rc;
     if (c->h_scal[12]) return fail(c, BJT_E_NOT_BINARY, "input is not a binary 0/255 image");
-    uint8_t *present; WS("present", (size_t)n0 + 1, present);
 
     int64_t n_ridge = 0;
     int path_used = 3;
@@ -372,7 +376,7 @@ static int dev_pipeline(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, in
         CK(cudaEventRecord(c->ev[4], c->stream));
         CK(cudaEventRecord(c->ev[5], c->stream));
     } else {
-        rc = dev_ridge(c, bufB, w, h, d, maxval, present, bufA, &n_ridge);
+        rc = dev_ridge(c, bufB, w, h, d, maxval, bufA, &n_ridge);
         if (rc) return rc;
         CK(cudaEventRecord(c->ev[4], c->stream));
         rc = dev_paint(c, bufA, w, h, d, -1, n_ridge, (int64_t)maxval, bufB, &path_used);
@@ -627,11 +631,10 @@ int bjt_dev_edt_z(bjt_ctx *c, const uint32_t *d_gy, int w, int h, int d, int n_s
     int rc = check_dims(c, w, h, d);
     if (rc) return rc;
     const uint32_t n0 = no_result(n_sentinel);
-    uint8_t *present; uint32_t *scal;
-    WS("present", (size_t)n0 + 1, present); WS("scalars", 256, scal);
-    CK(cudaMemsetAsync(present, 0, (size_t)n0 + 1, c->stream));
+    uint32_t *scal;
+    WS("scalars", 256, scal);
     CK(cudaMemsetAsync(scal, 0, 4, c->stream));
-    c->launches += launch_edt_z(d_gy, w, h, d, n0, d_sq, present, scal, c->stream); CKL();
+    c->launches += launch_edt_z(d_gy, w, h, d, n0, d_sq, nullptr, scal, c->stream); CKL();
     return BJT_OK;
 }
 

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256) edt_line_kernel(const TIn *__restrict__ i
                 }
                 if (m == NONE) {                    // no finite candidate on the rest of the line
                     for (int yy = y; yy < L; ++yy) oc[(long long)yy * stride] = n0;
-                    if (MARK) present[n0] = 1;
+                    if (MARK && present) present[n0] = 1;
                     tmax = n0;
                     break;
                 }
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) edt_line_kernel(const TIn *__restrict__ i
             }
             oc[(long long)y * stride] = res;
             if (MARK) {
-                if (res != prev) { present[res] = 1; prev = res; }
+                if (present && res != prev) { present[res] = 1; prev = res; }
                 tmax = max(tmax, res);
             }
         }
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(128) edt_line4_kernel(const TIn *__restrict__ 
                 r[c] = (fy.v[c] == 0u) ? 0u : (dead[c] ? n0 : (m[c] < n0 ? m[c] : n0));
                 if (!dead[c]) { a[c] = best[c]; fa[c] = fbest[c]; }
                 if (MARK) {
-                    if (r[c] != prev[c]) { present[r[c]] = 1; prev[c] = r[c]; }
+                    if (present && r[c] != prev[c]) { present[r[c]] = 1; prev[c] = r[c]; }
                     tmax = max(tmax, r[c]);
                 }
             }
@@ -323,7 +323,84 @@ __global__ void __launch_bounds__(128) edt_line4_kernel(const TIn *__restrict__ 
     }
 }
 
+// ---- whole lines in shared memory ---------------------------------------------------------------------
+// A block stages TX adjacent lines completely in shared memory ([L][TX] squared values, loaded as
+// contiguous TX-element row pieces), then every warp takes line positions t and computes, for its TX
+// columns at once, h(t) = min_d f(t+d) + d^2 by walking d = 1, 2, ... outwards on both sides until d^2
+// has reached the running minimum of every lane (one vote per step).  No candidate read leaves the SM,
+// nothing depends on a load from global memory inside the loop, and the results go out as contiguous
+// row pieces straight from registers.  HBM traffic is exactly one read and one write per voxel.
+template <typename TIn, int TX, bool WANT_MAX>
+__global__ void __launch_bounds__(1024) edt_tile_kernel(const TIn *__restrict__ in, uint32_t *__restrict__ out, int groups,
+                                                         long long outer, long long stride, int L, uint32_t n0,
+                                                         uint32_t *__restrict__ maxval) {
+    extern __shared__ uint32_t sm_raw[];                 // [L + 2][TX]: rows -1 and L hold BIG (beyond the line)
+    constexpr int RPW = 32 / TX;                         // line positions per warp step
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int xx = lane % TX, rsub = lane / TX;
+    const long long base = (long long)(blockIdx.x / groups) * outer + (long long)(blockIdx.x % groups) * TX;
+    const uint32_t BIG = 0x3FFFFFFFu;
+    uint32_t *sm = sm_raw + TX;                          // sm[t * TX + xx], t in [-1, L]
+    if (threadIdx.x < TX) { sm[-TX + (int)threadIdx.x] = BIG; sm[L * TX + threadIdx.x] = BIG; }
+    for (int r0 = warp * RPW; r0 < L; r0 += nwarps * RPW) {
+        const int t = r0 + rsub;
+        if (t < L) sm[t * TX + xx] = f_of(__ldg(in + base + (long long)t * stride + xx), n0);
+    }
+    __syncthreads();
+    uint32_t tmax = 0;
+    for (int r0 = warp * RPW; r0 < L; r0 += nwarps * RPW) {
+        const int t = r0 + rsub;
+        const bool valid = t < L;
+        const int tc = valid ? t : 0;
+        uint32_t m = valid ? sm[t * TX + xx] : 0u;
+        // two distances per vote; positions beyond the line ends clamp onto the BIG rows
+        for (int dlt = 1;; dlt += 2) {
+            const uint32_t d2 = (uint32_t)(dlt * dlt);
+            if (!__any_sync(0xFFFFFFFFu, d2 < m)) break;
+            const uint32_t d2b = d2 + 2u * (uint32_t)dlt + 1u;
+            const uint32_t lo = sm[max(tc - dlt, -1) * TX + xx], hi = sm[min(tc + dlt, L) * TX + xx];
+            const uint32_t lo2 = sm[max(tc - dlt - 1, -1) * TX + xx], hi2 = sm[min(tc + dlt + 1, L) * TX + xx];
+            m = min(m, min(min(lo, hi) + d2, min(lo2, hi2) + d2b));
+        }
+        if (valid) {
+            const uint32_t res = m < n0 ? m : n0;
+            out[base + (long long)t * stride + xx] = res;
+            if (WANT_MAX) tmax = max(tmax, res);
+        }
+    }
+    if (WANT_MAX) {
+        tmax = __reduce_max_sync(0xFFFFFFFFu, tmax);
+        if (lane == 0 && tmax) atomicMax(maxval, tmax);
+    }
+}
+
+// returns false when the shape does not fit (caller falls back to the per-thread line kernels)
+template <typename TIn, bool WANT_MAX>
+static bool launch_edt_tile(const TIn *in, uint32_t *out, int w, long long nouter, long long outer, long long stride,
+                            int L, uint32_t n0, uint32_t *maxval, cudaStream_t s) {
+    const size_t budget = 100 * 1024;      // two blocks per SM: one loads its tile while the other computes
+    int tx = 32;
+    while (tx > 4 && (size_t)(L + 2) * tx * 4 > budget) tx >>= 1;
+    if ((size_t)(L + 2) * tx * 4 > budget || w % tx != 0) return false;
+    const size_t smem = (size_t)(L + 2) * tx * 4;
+    const int groups = w / tx;
+    const unsigned grid = (unsigned)(nouter * groups);
+    const int threads = 1024;
+#define BJT_LAUNCH_TILE(TXV)                                                                                        \
+    {                                                                                                               \
+        cudaFuncSetAttribute(edt_tile_kernel<TIn, TXV, WANT_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        edt_tile_kernel<TIn, TXV, WANT_MAX><<<grid, threads, smem, s>>>(in, out, groups, outer, stride, L, n0, maxval);     \
+    }
+    if (tx == 32) BJT_LAUNCH_TILE(32)
+    else if (tx == 16) BJT_LAUNCH_TILE(16)
+    else if (tx == 8) BJT_LAUNCH_TILE(8)
+    else BJT_LAUNCH_TILE(4)
+#undef BJT_LAUNCH_TILE
+    return true;
+}
+
 int launch_edt_y(const uint16_t *gx, int w, int h, int d, uint32_t n0, uint32_t *gy, cudaStream_t s) {
+    if (launch_edt_tile<uint16_t, false>(gx, gy, w, d, (long long)w * h, (long long)w, h, n0, nullptr, s)) return 1;
     if (w % 4 == 0 && (uintptr_t)gx % 8 == 0 && (uintptr_t)gy % 16 == 0) {
         const long long ng = (long long)(w / 4) * d;
         edt_line4_kernel<uint16_t, false><<<(unsigned)((ng + 127) / 128), 128, 0, s>>>(gx, gy, w / 4, ng, (long long)w * h,
@@ -339,6 +416,7 @@ int launch_edt_y(const uint16_t *gx, int w, int h, int d, uint32_t n0, uint32_t 
 
 int launch_edt_z(const uint32_t *gy, int w, int h, int d, uint32_t n0, uint32_t *sq, uint8_t *present,
                  uint32_t *maxval, cudaStream_t s) {
+    if (!present && launch_edt_tile<uint32_t, true>(gy, sq, w, h, (long long)w, (long long)w * h, d, n0, maxval, s)) return 1;
     if (w % 4 == 0 && (uintptr_t)gy % 16 == 0 && (uintptr_t)sq % 16 == 0) {
         const long long ng = (long long)(w / 4) * h;
         edt_line4_kernel<uint32_t, true><<<(unsigned)((ng + 127) / 128), 128, 0, s>>>(gy, sq, w / 4, ng, (long long)w,

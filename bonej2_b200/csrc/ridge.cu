@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(128) ridge_template_kernel(const uint32_t *__r
                                                              uint32_t *__restrict__ t3) {
     const uint32_t vi = blockIdx.x;
     if (vi >= nvalues) return;
-    const uint32_t rsq = values[vi];
+    const uint32_t rsq = values ? values[vi] : vi + 1u;      // no list: every r^2 in 1..nvalues
     const uint32_t r = isqrt_floor(rsq);      // k, j beyond floor(sqrt) never satisfy k^2+j^2 <= r^2
     const uint32_t side = r + 1;
     uint32_t m1 = 0, m2 = 0, m3 = 0;
