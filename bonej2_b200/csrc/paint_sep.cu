@@ -191,11 +191,11 @@ __device__ __forceinline__ bool dyn_line(const SepArgs &a, long long line, bool 
             if (STAGE == 1) {
                 if (r | (uint32_t)A.n) {
                     SepItem one; one.rho = r; one.R = r;
-                    nf = A.template step<SepItem, PlainIO>(t, a.dir, a.dir < 0, &one, r ? 1 : 0, (const SepItem *)nullptr, 0, fr, fmax, ok);
+                    nf = A.template step<SepItem, PlainIO, false>(t, a.dir, a.dir < 0, &one, r ? 1 : 0, (const SepItem *)nullptr, 0, fr, fmax, ok);
                 }
             } else {
                 if (eF | eB | (unsigned long long)A.n)
-                    nf = A.template step<typename IO::T, IO>(t, a.dir, a.dir < 0, ipool + (eF & OFF_MASK), (int)(eF >> 40),
+                    nf = A.template step<typename IO::T, IO, true>(t, a.dir, a.dir < 0, ipool + (eF & OFF_MASK), (int)(eF >> 40),
                                                              ipool + (eB & OFF_MASK), (int)(eB >> 40), fr, fmax, ok);
             }
             if (nf > fmax) { ok = false; nf = fmax; }

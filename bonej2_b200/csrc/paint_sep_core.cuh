@@ -101,13 +101,17 @@ struct SepActive {
     }
 
     // Returns the front size (may exceed fmax; only fmax are stored).  ok is cleared on capacity overflow.
-    template <class RawT, class Unpack>
+    // REACH = false: emitted items are (slack, R), the Pareto front in slack.
+    // REACH = true (the stage feeding stage 3, which only asks how far an item reaches): emitted items are
+    //   (floor(sqrt(slack)), R) and an item is emitted only if it reaches strictly further than every
+    //   emitted item with a larger tag -- equal reach with a smaller tag can never win there.
+    template <class RawT, class Unpack, bool REACH>
     BJT_HD int step(int tc, int dir, bool skip_own, const RawT *lf, int nlf, const RawT *lb, int nlb, SepItem *out,
                     int fmax, bool &ok) {
         const int src = cur, dst = cur ^ 1;
         const int cap = st.cap();
         int i = 0, jf = 0, jb = 0, w = 0, nf = 0;
-        int best = -1, best_t = 0;
+        int best = -1, best_t = 0, last_e = -1;
         uint32_t best_R = 0, best_rho0 = 0;
         bool last_emitted = false;
         SepItem af, ab;
@@ -128,12 +132,31 @@ struct SepActive {
             const int s = fresh ? (int)x.rho0 : slack_at(tc, x.t, x.rho0);
             if (s < 0) continue;                                           // expired
             if (s > best) {
-                if (best >= 0 && best_R == x.R && last_emitted) --nf;      // same tag, more slack: replace
+                const bool same_tag = best >= 0 && best_R == x.R && last_emitted;
                 best = s; best_t = x.t; best_R = x.R; best_rho0 = x.rho0;
-                last_emitted = !(skip_own && x.t == tc);
-                if (last_emitted) {
-                    if (nf < fmax) { out[nf].rho = (uint32_t)s; out[nf].R = x.R; }
-                    ++nf;
+                const bool may_emit = !(skip_own && x.t == tc);
+                if (!REACH) {
+                    if (same_tag) --nf;                                    // same tag, more slack: replace
+                    last_emitted = may_emit;
+                    if (may_emit) {
+                        if (nf < fmax) { out[nf].rho = (uint32_t)s; out[nf].R = x.R; }
+                        ++nf;
+                    }
+                } else {
+                    const int e = (int)sep_isqrt((uint32_t)s);
+                    if (same_tag) {                                        // same tag: lengthen the entry in place
+                        if (nf - 1 < fmax) out[nf - 1].rho = (uint32_t)e;
+                        last_e = e;
+                    } else if (e > last_e) {
+                        last_e = e;                                        // an own arrival counts: the other sweep emits it
+                        last_emitted = may_emit;
+                        if (may_emit) {
+                            if (nf < fmax) { out[nf].rho = (uint32_t)e; out[nf].R = x.R; }
+                            ++nf;
+                        }
+                    } else {
+                        last_emitted = false;
+                    }
                 }
             } else {
                 if (dir > 0 ? best_t >= x.t : best_t <= x.t) continue;     // dominated by an item that is not older
@@ -179,14 +202,12 @@ struct SepStair {
 
     BJT_HD void clear() { n = 0; }
 
-    // u = coordinate in sweep direction (z forward, -z backward).  Returns false on overflow.
-    BJT_HD bool arrive(int u, uint32_t rho, uint32_t Rn) {
+    // u = coordinate in sweep direction (z forward, -z backward); e = how far the item reaches.
+    // Returns false on overflow.
+    BJT_HD bool arrive(int u, uint32_t e, uint32_t Rn) {
+        const int En = u + (int)e;
         // cheap reject against the head: R_n <= R_head and reach_n <= reach_head
-        if (n > 0 && Rn <= st.getR(0)) {
-            const int span = st.getE(0) - u;
-            if (span >= 0 && rho < (uint32_t)(span + 1) * (uint32_t)(span + 1)) return true;
-        }
-        const int En = u + (int)sep_isqrt(rho);
+        if (n > 0 && Rn <= st.getR(0) && En <= st.getE(0)) return true;
         int pos = 0;
         while (pos < n && st.getR(pos) > Rn) ++pos;
         if (pos > 0 && st.getE(pos - 1) >= En) return true;            // a larger tag reaches at least as far

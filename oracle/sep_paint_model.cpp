@@ -49,9 +49,9 @@ void dyn_line(const uint32_t *src, const Lists *inF, const Lists *inB, size_t ba
         int nf;
         if (src) {
             SepItem one; one.rho = src[v]; one.R = src[v];
-            nf = A.step<SepItem, SepUnpackPlain>(t, dir, dir < 0, &one, src[v] ? 1 : 0, nullptr, 0, fr, FMAX, ok);
+            nf = A.step<SepItem, SepUnpackPlain, false>(t, dir, dir < 0, &one, src[v] ? 1 : 0, nullptr, 0, fr, FMAX, ok);
         } else {
-            nf = A.step<SepItem, SepUnpackPlain>(t, dir, dir < 0, inF->pool.data() + inF->off[v], (int)inF->cnt[v],
+            nf = A.step<SepItem, SepUnpackPlain, true>(t, dir, dir < 0, inF->pool.data() + inF->off[v], (int)inF->cnt[v],
                                                   inB->pool.data() + inB->off[v], (int)inB->cnt[v], fr, FMAX, ok);
         }
         if (!ok) st->overflow_act++;

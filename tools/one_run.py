@@ -1,7 +1,7 @@
 """one Thickness call on a synthetic phantom (profiling helper): python tools_one_run.py N inverse [reps] [paint_path]"""
 import sys, time
 import numpy as np
-sys.path.insert(0, '.')
+sys.path.insert(0, '.'); sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from bonej2_b200 import _native
 from bonej2_b200.phantom import phantom_shapes
 n = int(sys.argv[1]); inv = int(sys.argv[2]); reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
