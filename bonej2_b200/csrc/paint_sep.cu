@@ -36,9 +36,9 @@ constexpr int XC = 512;                 // x-slab width of stages 2 and 3
 constexpr unsigned long long OFF_MASK = (1ull << 40) - 1ull;
 constexpr int TPB = 128;                // threads per block of the line kernels
 constexpr int S_SM = 12;                // entries per buffer kept in shared memory (PACKED kernels)
-constexpr int CAP_TAIL = 628;           // entries per buffer in the local frame behind them
+constexpr int CAP_TAIL = 1012;          // entries per buffer in the local frame behind them
 constexpr int CAP_WIDE = 128;           // local-frame capacity of the wide (u64 item) kernels
-constexpr int FMAX_FAST = 128;
+constexpr int FMAX_FAST = 256;
 constexpr int CAP_STAIR = 96;         // local-frame capacity of the stage-3 staircase
 constexpr int CAP_BIG = 4096, FMAX_BIG = 1024, NSLOTS = 2048;
 

@@ -1,0 +1,114 @@
+"""Hyperstack front-end for batched Thickness (BASELINE.json configs[4]).
+
+`ThicknessWrapper` itself refuses images with channel or time axes (ThicknessWrapper.java:236-243); the
+other BoneJ wrappers handle them by splitting into {X, Y, Z} subspaces with
+HyperstackUtils.split3DSubspaces (Modern/wrapperPlugins/.../wrapperUtils/HyperstackUtils.java:99-136,
+291-320) and labelling result rows `name + " " + subspace` (e.g. SurfaceAreaWrapper.java:136-144).  This
+module does the same split -- first split axis fastest, labels as Subspace.toString (:398-433) with
+ResultUtils.toConventionalIndex (1-based for Z, Channel, Time) -- and runs the CUDA Thickness path once
+per subspace, optionally spreading subspaces over several GPUs (they are independent).  There is no CPU
+path: each subspace goes through the C-ABI like any other volume.
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native
+from .wrapper import CHANNEL, TIME, UNKNOWN, X, Y, Z
+
+AXIS_NAMES = {X: "X", Y: "Y", Z: "Z", CHANNEL: "Channel", TIME: "Time"}
+
+
+def _conventional_index(axis_type, index: int) -> int:
+    """ResultUtils.toConventionalIndex (ResultUtils.java:201-209)"""
+    return index + 1 if axis_type in (Z, CHANNEL, TIME) else index
+
+
+@dataclass
+class Subspace:
+    data: np.ndarray            # [z][y][x] view (contiguous copy)
+    positions: tuple            # position along each split axis, in split-axis order
+    axis_types: tuple
+    label: str                  # Subspace.toString(): "Channel: 1, Time: 2"
+
+
+def split_3d_subspaces(data: np.ndarray, axes, axis_names=None):
+    """Yield the {X, Y, Z} subspaces of an N-d array in HyperstackUtils order.
+
+    data : numpy array, slowest axis first (numpy order), i.e. data.shape == reversed(sizes of `axes`)
+    axes : axis types, first axis fastest (imglib2 order), e.g. [X, Y, CHANNEL, Z, TIME]
+    Axes of the same type get a subscript "(2)", "(3)" ... as in HyperstackUtils.mapTypeSubscripts.
+    """
+    axes = list(axes)
+    n = len(axes)
+    if data.ndim != n:
+        raise ValueError("one axis type per array dimension")
+    spatial = [i for i, a in enumerate(axes) if a in (X, Y, Z)]
+    if not spatial:
+        return
+    split = [i for i in range(n) if i not in spatial]
+    sizes = [data.shape[n - 1 - i] for i in range(n)]          # size of imglib2 axis i
+    seen, subs = {}, []
+    for i in split:
+        seen[axes[i]] = seen.get(axes[i], 0) + 1
+        subs.append(seen[axes[i]])
+    names = axis_names or AXIS_NAMES
+    # first split axis varies fastest: iterate the cartesian product with the LAST split axis outermost
+    ranges = [range(sizes[i]) for i in reversed(split)]
+    for combo in itertools.product(*ranges):
+        pos = tuple(reversed(combo))                              # in split-axis order
+        index = [slice(None)] * n
+        for i, p in zip(split, pos):
+            index[n - 1 - i] = p
+        view = data[tuple(index)]
+        if view.size == 0:
+            continue
+        # remaining axes are the spatial ones in imglib2 order; bring to [z][y][x]
+        rem = [axes[i] for i in spatial]                          # fastest first
+        order = [rem.index(t) for t in (X, Y, Z) if t in rem]     # imglib2 positions of x, y, z
+        arr = np.transpose(view, [len(rem) - 1 - o for o in reversed(order)])
+        while arr.ndim < 3:
+            arr = arr[np.newaxis]
+        parts = []
+        for i, p, s in zip(split, pos, subs):
+            t = axes[i]
+            nm = names.get(t, "Unknown") + (f"({s})" if s > 1 else "")
+            parts.append(f"{nm}: {_conventional_index(t, p)}")
+        yield Subspace(np.ascontiguousarray(arr), pos, tuple(axes[i] for i in split), ", ".join(parts))
+
+
+def thickness_hyperstack(data, axes, name="image", map_choice="Both", mask=True, pixel_width=1.0, unit="",
+                         devices=(0,), want_maps=False):
+    """Thickness on every {X, Y, Z} subspace.  Returns rows [(label, {header: value})] in subspace order
+    (and the maps when want_maps).  Subspaces are dealt round-robin to the given CUDA devices."""
+    if map_choice not in ("Trabecular thickness", "Trabecular separation", "Both"):
+        raise ValueError("Unexpected map choice")
+    unit_header = f"({unit or 'pixel'})"
+    ctxs = [_native.Context(d) for d in devices]
+    rows, maps = [], []
+    try:
+        for k, sub in enumerate(split_3d_subspaces(np.asarray(data), axes)):
+            ctx = ctxs[k % len(ctxs)]
+            vol = sub.data
+            if vol.dtype != np.uint8:
+                raise ValueError("Need a binary image")
+            label = f"{name} {sub.label}".strip()
+            vals, out = {}, {}
+            runs = [("Tb.Th", False)] if map_choice == "Trabecular thickness" else \
+                   [("Tb.Sp", True)] if map_choice == "Trabecular separation" else [("Tb.Th", False), ("Tb.Sp", True)]
+            for prefix, inverse in runs:
+                m, st, _ = ctx.thickness(vol, inverse=inverse, mask=mask, pixel_width=pixel_width, want_map=want_maps)
+                mean, sd, mx = (st.mean, st.sd, st.max) if st.count else (float("nan"),) * 3
+                vals[f"{prefix} Mean {unit_header}"] = mean
+                vals[f"{prefix} Std Dev {unit_header}"] = sd
+                vals[f"{prefix} Max {unit_header}"] = mx
+                out[prefix] = m
+            rows.append((label, vals))
+            maps.append(out)
+    finally:
+        for c in ctxs:
+            c.close()
+    return (rows, maps) if want_maps else rows
