@@ -1,0 +1,86 @@
+"""BASELINE.json configurations.  configs[0] (256^3, Tb.Th + Tb.Sp, mask on) is compared with the CPU
+oracle in full; at 512^3, where the brute-force oracle would take minutes, the CUDA path is checked
+through size-independent properties: two independent painters agree bit for bit, two independent EDT
+kernels agree, sqrt(EDT) is 1-Lipschitz, every foreground voxel of a run gets a value (count = number
+of foreground voxels) and the two runs partition the volume."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _phantom(ctx, n, seed=1):
+    from bonej2_b200.phantom import phantom_shapes
+    return ctx.phantom(phantom_shapes(n, n, n, seed), n, n, n)
+
+
+def test_config0_256_both_mask_on(ctx, oracle):
+    vol = _phantom(ctx, 256)
+    assert np.array_equal(vol, oracle.phantom_raster(__import__("bonej2_b200.phantom", fromlist=["x"]).phantom_shapes(256, 256, 256, 1), 256, 256, 256))
+    (m_th, s_th, _), (m_sp, s_sp, _) = ctx.thickness_both(vol, mask=True)
+    for inverse, m, st in ((False, m_th, s_th), (True, m_sp, s_sp)):
+        o = oracle.process_image(vol, inverse=inverse, mask=True, taps=True)
+        assert np.array_equal(ctx.edt_sq(vol, inverse=inverse), o["sq"]), "squared EDT not bit-exact"
+        assert np.array_equal(np.isnan(m), np.isnan(o["map"]))
+        ok = ~np.isnan(m)
+        assert np.allclose(m[ok], o["map"][ok], rtol=1e-5, atol=0)
+        assert st.count == o["stats"].count
+        for f in ("mean", "sd", "max"):
+            assert math.isclose(getattr(st, f), getattr(o["stats"], f), rel_tol=1e-5), f
+
+
+@pytest.fixture(scope="module")
+def vol512(ctx):
+    return _phantom(ctx, 512)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_512_properties(ctx, vol512, inverse):
+    vol = vol512
+    sq = ctx.edt_sq(vol, inverse=inverse)
+    fg = (vol == 0) if inverse else (vol == 255)
+    # background of the run is 0, foreground strictly positive
+    assert np.array_equal(sq > 0, fg)
+    # sqrt(EDT) is 1-Lipschitz along every axis: |sqrt(a) - sqrt(b)| <= 1  <=>  a <= b + 2 sqrt(b) + 1
+    r = np.sqrt(sq.astype(np.float64))
+    for ax in range(3):
+        a = np.moveaxis(r, ax, 0)
+        assert np.all(np.abs(a[1:] - a[:-1]) <= 1.0 + 1e-9)
+    # an independent kernel (per-thread line scans, taken when the width is not a multiple of 4) agrees on a crop
+    crop = np.ascontiguousarray(vol[:64, :70, :509])
+    sq_crop_line = ctx.edt_sq(crop, inverse=inverse)
+    crop4 = np.ascontiguousarray(vol[:64, :70, :512])
+    # same planes, wider by 3 columns: the narrower crop can only have distances >= (fewer background voxels)
+    assert np.all(sq_crop_line >= ctx.edt_sq(crop4, inverse=inverse)[:, :, :509])
+    # two independent painters agree bit for bit
+    ridge = ctx.ridge(sq)
+    assert np.all(ridge[ridge > 0] == sq[ridge > 0]) and not np.any(ridge[~fg])
+    sep = ctx.paint_rsq(ridge, path=0)
+    assert np.array_equal(sep, ctx.paint_rsq(ridge, path=2)), "separable and scatter painters differ"
+    # every foreground voxel is painted with at least its own squared distance
+    assert np.all(sep[fg] >= sq[fg])
+    del sep, ridge, r
+    # full pipeline: count = number of foreground voxels of the run (mask on), max is the largest painted ball
+    m, st, tm = ctx.thickness(vol, inverse=inverse, mask=True)
+    assert st.count == int(fg.sum())
+    assert np.array_equal(~np.isnan(m), fg)
+    assert math.isclose(st.max, float(np.nanmax(m)), rel_tol=1e-6) and st.min >= 2.0
+    assert tm.paint_path == 0
+
+
+def test_512_line_kernel_equals_tile_kernel(ctx, vol512):
+    """same volume, two shapes that take the two EDT code paths: pad the width to 516 (tile) vs 514 (line)"""
+    base = vol512[:48, :48, :]
+    a = np.zeros((48, 48, 516), np.uint8); a[:, :, :512] = base
+    b = np.zeros((48, 48, 514), np.uint8); b[:, :, :512] = base
+    for inverse in (False, True):
+        sa, sb = ctx.edt_sq(a, inverse=inverse), ctx.edt_sq(b, inverse=inverse)
+        if not inverse:
+            assert np.array_equal(sa[:, :, :512], sb[:, :, :512])        # extra background columns beyond 512
+        else:
+            # inverted: the padding is foreground; compare where the padding cannot matter (distance to the
+            # padding is at least 2, so any value <= 4 is decided by voxels both shapes share)
+            sel = sa[:, :, :500] <= 4
+            assert np.array_equal(sa[:, :, :500][sel], sb[:, :, :500][sel])
