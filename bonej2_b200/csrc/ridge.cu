@@ -99,57 +99,74 @@ int launch_ridge_template_compact(const uint32_t *values, uint32_t nvalues, uint
 }
 
 // ---- ridge test ------------------------------------------------------------------------------------
-// Block = 32 x 8 x 4 voxels; the (34 x 10 x 6) halo tile of sq is staged in shared memory so every
-// neighbour read is an LDS.  Out-of-image halo cells hold 0 (0 never reaches a threshold, T_c > r^2 >= 1).
-constexpr int RTX = 32, RTY = 8, RTZ = 4;
+// A voxel p is dropped when a face / edge / corner neighbour q has sq(q) >= T1 / T2 / T3 [sq(p)], i.e. when
+//   max over the 6 face neighbours >= T1  or  max over the 12 edge neighbours >= T2  or  max over the 8
+//   corner neighbours >= T3.
+// Block = 32 x 8 columns, each thread walks RTZ planes of its column.  The (34 x 10 x (RTZ+2)) halo tile of
+// sq sits in shared memory (whole tile rows loaded by a warp; out-of-image cells hold 0, which never
+// reaches a threshold since T_c > r^2 >= 1).  Per plane a thread reduces its 3 x 3 in-plane neighbourhood
+// to (centre A, max of the 4 in-plane face neighbours B, max of the 4 in-plane diagonals C); the three
+// maxima of plane z then follow from the (A, B, C) of planes z-1, z, z+1:
+//   face = max(B[z], A[z-1], A[z+1])   edge = max(C[z], B[z-1], B[z+1])   corner = max(C[z-1], C[z+1]).
+constexpr int RTX = 32, RTY = 8, RTZ = 8;
+constexpr int RHX = RTX + 2, RHY = RTY + 2, RHZ = RTZ + 2;
 
-__global__ void __launch_bounds__(RTX *RTY *RTZ) ridge_kernel(const uint32_t *__restrict__ sq, int w, int h, int d,
-                                                              const uint32_t *__restrict__ t1,
-                                                              const uint32_t *__restrict__ t2,
-                                                              const uint32_t *__restrict__ t3,
-                                                              uint32_t *__restrict__ ridge,
-                                                              unsigned long long *__restrict__ count) {
-    __shared__ uint32_t tile[RTZ + 2][RTY + 2][RTX + 2];
+__global__ void __launch_bounds__(RTX *RTY) ridge_kernel(const uint32_t *__restrict__ sq, int w, int h, int d,
+                                                         const uint32_t *__restrict__ t1,
+                                                         const uint32_t *__restrict__ t2,
+                                                         const uint32_t *__restrict__ t3,
+                                                         uint32_t *__restrict__ ridge,
+                                                         unsigned long long *__restrict__ count) {
+    __shared__ uint32_t tile[RHZ][RHY][RHX];
     const int bx = blockIdx.x * RTX, by = blockIdx.y * RTY, bz = blockIdx.z * RTZ;
-    const int tid = threadIdx.x + RTX * (threadIdx.y + RTY * threadIdx.z);
+    const int tid = threadIdx.x + RTX * threadIdx.y;
+    const int lane = tid & 31, warp = tid >> 5;
     const size_t wh = (size_t)w * h;
-    for (int i = tid; i < (RTZ + 2) * (RTY + 2) * (RTX + 2); i += RTX * RTY * RTZ) {
-        const int lx = i % (RTX + 2), ly = (i / (RTX + 2)) % (RTY + 2), lz = i / ((RTX + 2) * (RTY + 2));
-        const int gx = bx + lx - 1, gy = by + ly - 1, gz = bz + lz - 1;
-        uint32_t v = 0;
-        if (gx >= 0 && gx < w && gy >= 0 && gy < h && gz >= 0 && gz < d) v = __ldg(sq + gz * wh + (size_t)gy * w + gx);
-        tile[lz][ly][lx] = v;
+    constexpr int NWARP = (RTX * RTY) / 32, NROW = RHZ * RHY;
+    const int gx0 = bx + lane - 1, gx1 = bx + lane + 31;
+    for (int r = warp; r < NROW; r += NWARP) {          // independent iterations: the loads overlap
+        const int lz = r / RHY, ly = r % RHY;
+        const int gy = by + ly - 1, gz = bz + lz - 1;
+        const bool row_in = gy >= 0 && gy < h && gz >= 0 && gz < d;
+        const uint32_t *src = sq + (row_in ? gz * wh + (size_t)gy * w : 0);
+        tile[lz][ly][lane] = (row_in && gx0 >= 0 && gx0 < w) ? __ldg(src + gx0) : 0u;
+        if (lane < 2) tile[lz][ly][32 + lane] = (row_in && gx1 < w) ? __ldg(src + gx1) : 0u;
     }
     __syncthreads();
-    const int x = bx + threadIdx.x, y = by + threadIdx.y, z = bz + threadIdx.z;
-    bool is_ridge = false;
-    uint32_t v = 0;
-    if (x < w && y < h && z < d) {
-        const int lx = threadIdx.x + 1, ly = threadIdx.y + 1, lz = threadIdx.z + 1;
-        v = tile[lz][ly][lx];
-        if (v > 0) {
-            const uint32_t th[3] = {__ldg(t1 + v), __ldg(t2 + v), __ldg(t3 + v)};
-            bool keep = true;
+    const int x = bx + threadIdx.x, y = by + threadIdx.y;
+    const int lx = threadIdx.x + 1, ly = threadIdx.y + 1;
+    unsigned nridge = 0;
+    uint32_t A0, B0, C0, A1, B1, C1, A2, B2, C2;
+    auto plane = [&](int lz, uint32_t &A, uint32_t &B, uint32_t &C) {
+        A = tile[lz][ly][lx];
+        B = max(max(tile[lz][ly][lx - 1], tile[lz][ly][lx + 1]), max(tile[lz][ly - 1][lx], tile[lz][ly + 1][lx]));
+        C = max(max(tile[lz][ly - 1][lx - 1], tile[lz][ly - 1][lx + 1]), max(tile[lz][ly + 1][lx - 1], tile[lz][ly + 1][lx + 1]));
+    };
+    plane(0, A0, B0, C0);
+    plane(1, A1, B1, C1);
 #pragma unroll
-            for (int dz = -1; dz <= 1; ++dz)
-#pragma unroll
-                for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        const int c = (dx != 0) + (dy != 0) + (dz != 0);
-                        if (c == 0) continue;
-                        if (tile[lz + dz][ly + dy][lx + dx] >= th[c - 1]) keep = false;
-                    }
-            is_ridge = keep;
+    for (int tz = 0; tz < RTZ; ++tz) {
+        plane(tz + 2, A2, B2, C2);
+        const int z = bz + tz;
+        if (x < w && y < h && z < d) {
+            const uint32_t v = A1;
+            bool is_ridge = false;
+            if (v > 0) {
+                const uint32_t face = max(B1, max(A0, A2)), edge = max(C1, max(B0, B2)), corner = max(C0, C2);
+                is_ridge = !(face >= __ldg(t1 + v) || edge >= __ldg(t2 + v) || corner >= __ldg(t3 + v));
+            }
+            ridge[z * wh + (size_t)y * w + x] = is_ridge ? v : 0u;
+            nridge += is_ridge ? 1u : 0u;
         }
-        ridge[z * wh + (size_t)y * w + x] = is_ridge ? v : 0u;
+        A0 = A1; B0 = B1; C0 = C1;
+        A1 = A2; B1 = B2; C1 = C2;
     }
     // block count of ridge points: one atomic per block (a per-warp atomic on one address serialises in L2)
     __shared__ unsigned int block_count;
     if (tid == 0) block_count = 0;
     __syncthreads();
-    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, is_ridge);
-    if ((tid & 31) == 0 && ballot) atomicAdd(&block_count, (unsigned)__popc(ballot));
+    nridge = __reduce_add_sync(0xFFFFFFFFu, nridge);
+    if (lane == 0 && nridge) atomicAdd(&block_count, nridge);
     __syncthreads();
     if (tid == 0 && block_count) atomicAdd(count, (unsigned long long)block_count);
 }
@@ -157,7 +174,7 @@ __global__ void __launch_bounds__(RTX *RTY *RTZ) ridge_kernel(const uint32_t *__
 int launch_ridge(const uint32_t *sq, int w, int h, int d, const uint32_t *t1, const uint32_t *t2, const uint32_t *t3,
                  uint32_t *ridge, unsigned long long *count, cudaStream_t s) {
     dim3 grid((w + RTX - 1) / RTX, (h + RTY - 1) / RTY, (d + RTZ - 1) / RTZ);
-    dim3 block(RTX, RTY, RTZ);
+    dim3 block(RTX, RTY, 1);
     ridge_kernel<<<grid, block, 0, s>>>(sq, w, h, d, t1, t2, t3, ridge, count);
     return 1;
 }
