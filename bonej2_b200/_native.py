@@ -77,6 +77,8 @@ _SIGS = {
     "bjt_device_info": ([_VP, C.c_char_p, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)], _I),
     "bjt_set_paint_path": ([_VP, _I], _I),
     "bjt_launch_count": ([_VP], C.c_int64),
+    "bjt_debug_set_paint_limits": ([_VP, _I, _I], _I),
+    "bjt_debug_paint_redo_lines": ([_VP], C.c_int64),
     "bjt_host_alloc": ([C.c_size_t], _VP),
     "bjt_host_free": ([_VP], None),
     "bjt_thickness_u8": ([_VP, _VP, _I, _I, _I, _I, _I, _I, _D, _VP, C.POINTER(Stats), C.POINTER(Timing)], _I),
@@ -166,6 +168,12 @@ class Context:
 
     def set_paint_path(self, path: int):
         self._ck(lib().bjt_set_paint_path(self._h, int(path)))
+
+    def debug_set_paint_limits(self, active_cap=0, front_cap=0):
+        self._ck(lib().bjt_debug_set_paint_limits(self._h, int(active_cap), int(front_cap)))
+
+    def debug_paint_redo_lines(self) -> int:
+        return int(lib().bjt_debug_paint_redo_lines(self._h))
 
     def launch_count(self) -> int:
         """kernels of this library launched through this context so far"""

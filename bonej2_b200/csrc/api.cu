@@ -164,6 +164,24 @@ int bjt_device_info(bjt_ctx *c, char *name, int name_len, int *sm_count, int *cc
 
 int64_t bjt_launch_count(const bjt_ctx *c) { return c ? c->launches : 0; }
 
+int bjt_debug_set_paint_limits(bjt_ctx *c, int active_cap, int front_cap) {
+    if (!c) return BJT_E_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    paint_sep_set_limits(active_cap, front_cap);
+    return BJT_OK;
+}
+
+int64_t bjt_debug_paint_redo_lines(bjt_ctx *c) {
+    if (!c) return -1;
+    std::lock_guard<std::mutex> lk(c->mu);
+    auto it = c->bufs.find("paint_sep");
+    if (it == c->bufs.end() || !it->second.p) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    return (int64_t)paint_sep_redo_lines(it->second.p);
+}
+
 void *bjt_host_alloc(size_t bytes) {
     void *p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;

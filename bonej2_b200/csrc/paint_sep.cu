@@ -44,6 +44,10 @@ constexpr int CAP_BIG = 4096, FMAX_BIG = 1024, NSLOTS = 2048;
 
 enum : uint32_t { F_POOL1 = 1u, F_POOL2 = 2u, F_ACTIVE = 4u, F_FRONT = 8u };
 
+// test hook: caps on the fast kernels' capacities (paint_sep_set_limits) so that small volumes can drive
+// lines into the redo kernels; the defaults never bind
+__constant__ int c_cap_limit = 1 << 30, c_fmax_limit = 1 << 30;
+
 template <bool PACKED> struct ItemIO;
 template <> struct ItemIO<true> {
     typedef uint32_t T;
@@ -69,7 +73,7 @@ struct PlainIO { static __device__ __forceinline__ SepItem get(const SepItem *p,
 struct HybridStore {
     unsigned long long *sm;
     unsigned long long loc[2][CAP_TAIL];
-    __device__ __forceinline__ int cap() const { return S_SM + CAP_TAIL; }
+    __device__ __forceinline__ int cap() const { return min(S_SM + CAP_TAIL, c_cap_limit); }
     static __device__ __forceinline__ unsigned long long enc(const SepEntry &e) {
         return (unsigned long long)e.R | ((unsigned long long)e.rho0 << 16) | ((unsigned long long)(uint32_t)(e.t + 32768) << 32);
     }
@@ -143,6 +147,7 @@ struct SepArgs {
     uint32_t *flags;
     int *redo_list;          // lines whose fast capacities were too small
     int *redo_count;
+    unsigned long long *redo_total;     // lines sent to the redo kernels in this run (diagnostics, tests)
     char *scratch;           // stores of the redo kernels
 };
 
@@ -257,7 +262,13 @@ __device__ __forceinline__ void record_redo(const SepArgs &a, long long line) {
 
 template <bool PACKED> struct FastActive;
 template <> struct FastActive<true> { typedef SepActive<HybridStore> T; };
-template <> struct FastActive<false> { typedef SepActive<SepLocalStore<CAP_WIDE> > T; };
+struct WideStore : SepLocalStore<CAP_WIDE> {
+    __device__ __forceinline__ int cap() const { return min(CAP_WIDE, c_cap_limit); }
+};
+struct StairStore : SepStairLocal<CAP_STAIR> {
+    __device__ __forceinline__ int cap() const { return min(CAP_STAIR, c_cap_limit); }
+};
+template <> struct FastActive<false> { typedef SepActive<WideStore> T; };
 
 template <bool PACKED, int STAGE>
 __global__ void __launch_bounds__(TPB) sep_dyn_kernel(SepArgs a) {
@@ -268,7 +279,7 @@ __global__ void __launch_bounds__(TPB) sep_dyn_kernel(SepArgs a) {
     typename FastActive<PACKED>::T A;
     if constexpr (PACKED) A.st.sm = sm + threadIdx.x;
     SepItem fr[FMAX_FAST];
-    const bool ok = dyn_line<PACKED, STAGE>(a, line, valid, A, fr, FMAX_FAST);
+    const bool ok = dyn_line<PACKED, STAGE>(a, line, valid, A, fr, min(FMAX_FAST, c_fmax_limit));
     if (valid && !ok) record_redo(a, line);
 }
 
@@ -281,6 +292,7 @@ __global__ void __launch_bounds__(32) sep_dyn_redo_kernel(SepArgs a) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const int count = *a.redo_count;
     if (count == 0) return;
+    if (slot == 0) atomicAdd(a.redo_total, (unsigned long long)count);
     SepActive<SepFlatStore> A;
     char *mine = a.scratch + (size_t)slot * SLOT_BYTES;
     A.st.base = reinterpret_cast<SepEntry *>(mine); A.st.capacity = CAP_BIG;
@@ -298,7 +310,7 @@ template <bool PACKED>
 __global__ void __launch_bounds__(TPB) sep_stair_kernel(SepArgs a) {
     const long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (line >= (long long)a.xw * a.h) return;
-    SepStair<SepStairLocal<CAP_STAIR> > S;
+    SepStair<StairStore> S;
     if (!stair_line<PACKED>(a, line, S)) record_redo(a, line);
 }
 
@@ -306,6 +318,7 @@ template <bool PACKED>
 __global__ void __launch_bounds__(32) sep_stair_redo_kernel(SepArgs a) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const int count = *a.redo_count;
+    if (slot == 0 && count) atomicAdd(a.redo_total, (unsigned long long)count);
     SepStair<SepStairFlat> S;
     S.st.R = reinterpret_cast<uint32_t *>(a.scratch + (size_t)slot * SLOT_BYTES);
     S.st.E = reinterpret_cast<int32_t *>(S.st.R + 2 * CAP_BIG);
@@ -352,6 +365,7 @@ int run_sep(const uint32_t *ridge, int w, int h, int d, const Plan &p, char *ws,
     SepArgs base{};
     base.w = w; base.h = h; base.d = d; base.flags = flags;
     base.redo_list = reinterpret_cast<int *>(ws + p.off_redo); base.redo_count = redo_count;
+    base.redo_total = counters + 5;
     base.scratch = ws + p.off_scratch;
     unsigned long long *idx1f = reinterpret_cast<unsigned long long *>(ws + p.off_idx1f);
     unsigned long long *idx1b = reinterpret_cast<unsigned long long *>(ws + p.off_idx1b);
@@ -400,6 +414,19 @@ int run_sep(const uint32_t *ridge, int w, int h, int d, const Plan &p, char *ws,
 }
 
 }  // namespace
+
+void paint_sep_set_limits(int cap, int fmax) {
+    const int c = cap > 0 ? cap : 1 << 30, f = fmax > 0 ? fmax : 1 << 30;
+    cudaMemcpyToSymbol(c_cap_limit, &c, sizeof(int));
+    cudaMemcpyToSymbol(c_fmax_limit, &f, sizeof(int));
+}
+
+// lines the last run on this workspace sent to the redo kernels (synchronous read)
+unsigned long long paint_sep_redo_lines(const void *workspace) {
+    unsigned long long v = 0;
+    cudaMemcpy(&v, reinterpret_cast<const unsigned long long *>(workspace) + 5, 8, cudaMemcpyDeviceToHost);
+    return v;
+}
 
 // variant: bit 0 = wide (u64) items, bit 1 = doubled pools
 size_t paint_sep_workspace_bytes(int w, int h, int d, int variant) {

@@ -63,6 +63,11 @@ int  bjt_device_info(bjt_ctx *ctx, char *name, int name_len, int *sm_count, int 
 int  bjt_set_paint_path(bjt_ctx *ctx, int path);
 /* kernels of this library launched through this context so far */
 int64_t bjt_launch_count(const bjt_ctx *ctx);
+/* test hook: cap the fast painter kernels' per-line capacities (0 = default) so that small volumes exercise
+ * the redo kernels; results must not change */
+int  bjt_debug_set_paint_limits(bjt_ctx *ctx, int active_cap, int front_cap);
+/* lines the last separable paint of this context sent to its redo kernels */
+int64_t bjt_debug_paint_redo_lines(bjt_ctx *ctx);
 /* page-locked host memory (what a JNI direct ByteBuffer / the bench wraps so copies are DMA) */
 void *bjt_host_alloc(size_t bytes);
 void  bjt_host_free(void *p);

@@ -142,3 +142,22 @@ def test_stats_kernel(ctx, oracle):
     m = rng.random((17, 33, 65)).astype(np.float32) * 40
     m[rng.random(m.shape) < 0.4] = np.nan
     _cmp_stats(ctx.stats(m), oracle.stats(m))
+
+
+@pytest.mark.parametrize("caps", [(2, 1), (3, 2), (6, 3)])
+def test_painter_redo_kernels(ctx, oracle, caps):
+    """with the fast kernels' capacities capped, most lines go through the redo kernels (global scratch);
+    the painted map must not change"""
+    vol = _phantom(oracle, 64, 1)
+    try:
+        ctx.debug_set_paint_limits(*caps)
+        for inverse in (False, True):
+            dist, sq = oracle.edt(vol, inverse=inverse)
+            rg = oracle.ridge(dist)
+            _, rsq = oracle.paint(rg)
+            ridge = np.where(rg > 0, sq, 0).astype(np.uint32)
+            for path in (0, 1):
+                assert np.array_equal(ctx.paint_rsq(ridge, path=path), rsq)
+                assert ctx.debug_paint_redo_lines() > 50
+    finally:
+        ctx.debug_set_paint_limits(0, 0)
