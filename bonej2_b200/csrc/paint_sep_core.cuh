@@ -24,6 +24,14 @@
 #define BJT_HD inline
 #endif
 
+// statistics hook of the CPU model's instrumented builds; compiles to nothing elsewhere
+#ifndef BJT_SEP_COUNT
+#define BJT_SEP_COUNT(k)
+#endif
+#ifndef BJT_SEP_TRACE
+#define BJT_SEP_TRACE(kind, x, tc, dir)
+#endif
+
 namespace bjt {
 
 struct SepItem { uint32_t rho, R; };
@@ -130,8 +138,11 @@ struct SepActive {
             else if (Rb >= Ra) { x.t = tc; x.rho0 = ab.rho; x.R = Rb; fresh = true; ++jb; if (jb < nlb) ab = Unpack::get(lb, jb); }
             else { x = ea; fresh = false; ++i; if (i < n) ea = st.load(src, i); }
             const int s = fresh ? (int)x.rho0 : slack_at(tc, x.t, x.rho0);
-            if (s < 0) continue;                                           // expired
+            BJT_SEP_COUNT(0);
+            BJT_SEP_TRACE(i + jf + jb == 1 ? 0 : 1, x, tc, dir);
+            if (s < 0) { BJT_SEP_COUNT(1); continue; }                     // expired
             if (s > best) {
+                BJT_SEP_COUNT(2);
                 const bool same_tag = best >= 0 && best_R == x.R && last_emitted;
                 best = s; best_t = x.t; best_R = x.R; best_rho0 = x.rho0;
                 const bool may_emit = !(skip_own && x.t == tc);
@@ -159,9 +170,11 @@ struct SepActive {
                     }
                 }
             } else {
-                if (dir > 0 ? best_t >= x.t : best_t <= x.t) continue;     // dominated by an item that is not older
+                if (dir > 0 ? best_t >= x.t : best_t <= x.t) { BJT_SEP_COUNT(3); continue; }   // dominated by an item that is not older
                 const int ex = x.t + dir * sep_sqrt_upper(x.rho0);         // at or beyond x's last position
-                if (slack_at(ex, best_t, best_rho0) >= slack_at(ex, x.t, x.rho0)) continue;   // dominated for life
+                if (slack_at(ex, best_t, best_rho0) >= slack_at(ex, x.t, x.rho0)) { BJT_SEP_COUNT(4); continue; }   // dominated for life
+                BJT_SEP_COUNT(5);
+                BJT_SEP_TRACE(2, x, tc, dir);
             }
             if (w >= cap) { ok = false; continue; }
             st.store(dst, w, x);
