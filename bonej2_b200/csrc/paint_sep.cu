@@ -67,27 +67,32 @@ template <> struct ItemIO<false> {
 };
 struct PlainIO { static __device__ __forceinline__ SepItem get(const SepItem *p, int k) { return p[k]; } };
 
-// PACKED active-set storage: R < 2^16, rho0 < 2^16, |t| < 2^15 -> one u64 per entry.
-// Entry (half, i): i < S_SM in shared memory at sm[(half * S_SM + i) * TPB] (sm already offset by the
-// thread index, so a warp touches 32 consecutive u64), the rest in the local frame.
+// PACKED active-set storage: R < 2^16, rho0 < 2^16, |t| < 2^15 -> one u64 per entry, low word laid out
+// like a packed item (R << 16 | rho0), high word t + 32768.
+// Entry (half, i): i < S_SM in shared memory at word (half * S_SM + i) * TPB of the thread's column (a warp
+// touches 32 consecutive u64), the rest in the local frame.
 struct HybridStore {
-    unsigned long long *sm;
+    typedef unsigned long long Entry;
+    uint32_t sm;                           // shared-window address of the thread's column
     unsigned long long loc[2][CAP_TAIL];
+    static __device__ __forceinline__ Entry make(uint32_t R, uint32_t rho0, int t) {
+        return (unsigned long long)((R << 16) | rho0) | ((unsigned long long)(uint32_t)(t + 32768) << 32);
+    }
+    static __device__ __forceinline__ uint32_t R(Entry e) { return (uint32_t)e >> 16; }
+    static __device__ __forceinline__ uint32_t rho0(Entry e) { return (uint32_t)e & 0xFFFFu; }
+    static __device__ __forceinline__ int t(Entry e) { return (int)(uint32_t)(e >> 32) - 32768; }
     __device__ __forceinline__ int cap() const { return min(S_SM + CAP_TAIL, c_cap_limit); }
-    static __device__ __forceinline__ unsigned long long enc(const SepEntry &e) {
-        return (unsigned long long)e.R | ((unsigned long long)e.rho0 << 16) | ((unsigned long long)(uint32_t)(e.t + 32768) << 32);
+    __device__ __forceinline__ Entry load(int half, int i) const {
+        if (i < S_SM) {
+            Entry v;
+            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(sm + (uint32_t)((half * S_SM + i) * TPB * 8)));
+            return v;
+        }
+        return loc[half][i - S_SM];
     }
-    static __device__ __forceinline__ SepEntry dec(unsigned long long v) {
-        SepEntry e;
-        e.R = (uint32_t)(v & 0xFFFFu); e.rho0 = (uint32_t)((v >> 16) & 0xFFFFu); e.t = (int)(uint32_t)(v >> 32) - 32768;
-        return e;
-    }
-    __device__ __forceinline__ SepEntry load(int half, int i) const {
-        return dec(i < S_SM ? sm[(half * S_SM + i) * TPB] : loc[half][i - S_SM]);
-    }
-    __device__ __forceinline__ void store(int half, int i, const SepEntry &e) {
-        if (i < S_SM) sm[(half * S_SM + i) * TPB] = enc(e);
-        else loc[half][i - S_SM] = enc(e);
+    __device__ __forceinline__ void store(int half, int i, Entry e) {
+        if (i < S_SM) asm volatile("st.shared.u64 [%0], %1;" ::"r"(sm + (uint32_t)((half * S_SM + i) * TPB * 8)), "l"(e) : "memory");
+        else loc[half][i - S_SM] = e;
     }
 };
 
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(TPB) sep_dyn_kernel(SepArgs a) {
     const long long nlines = STAGE == 1 ? (long long)a.h * a.d : (long long)a.xw * a.d;
     const bool valid = line < nlines;
     typename FastActive<PACKED>::T A;
-    if constexpr (PACKED) A.st.sm = sm + threadIdx.x;
+    if constexpr (PACKED) A.st.sm = (uint32_t)__cvta_generic_to_shared(sm + threadIdx.x);
     SepItem fr[FMAX_FAST];
     const bool ok = dyn_line<PACKED, STAGE>(a, line, valid, A, fr, min(FMAX_FAST, c_fmax_limit));
     if (valid && !ok) record_redo(a, line);

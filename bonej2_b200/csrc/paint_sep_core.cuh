@@ -39,41 +39,50 @@ struct SepItem { uint32_t rho, R; };
 // one active item: tag R, slack rho0 when it arrived, arrival position t
 struct SepEntry { uint32_t R, rho0; int32_t t; };
 
-BJT_HD uint32_t sep_isqrt(uint32_t v) {
-    // exact floor(sqrt(v)), v < 2^31
+BJT_HD float sep_sqrt_fast(float v) {
 #if defined(__CUDA_ARCH__)
-    uint32_t r = (uint32_t)sqrtf((float)v);
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));            // a few ulp off at most
+    return r;
 #else
-    uint32_t r = (uint32_t)__builtin_sqrtf((float)v);
+    return __builtin_sqrtf(v);
 #endif
-    while (r * r > v) --r;
-    while ((r + 1u) * (r + 1u) <= v) ++r;
+}
+
+// exact floor(sqrt(v)), v < 2^31: the float root is off by far less than 1 (rounding of v: 2^-24 relative,
+// the approximation: a few ulp), so its truncation is the answer or one beside it
+BJT_HD uint32_t sep_isqrt(uint32_t v) {
+    uint32_t r = (uint32_t)sep_sqrt_fast((float)v);
+    if (r * r > v) --r;
+    else if ((r + 1u) * (r + 1u) <= v) ++r;
     return r;
 }
 
 // an integer >= floor(sqrt(v)) (and <= floor + 2): one conversion, one square root, no loop.
 // A correctly rounded float sqrt is never below the largest integer <= the true root.
-BJT_HD int sep_sqrt_upper(uint32_t v) {
-#if defined(__CUDA_ARCH__)
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)v));     // error of a few ulp: + 2 keeps it an upper bound
-    return (int)r + 2;
-#else
-    return (int)__builtin_sqrtf((float)v) + 1;
-#endif
-}
+BJT_HD int sep_sqrt_upper(uint32_t v) { return (int)sep_sqrt_fast((float)v) + 2; }
 
 // ---- storage policies --------------------------------------------------------------------------------
 // A store holds two buffers ("halves") of up to cap() entries; step() reads one and writes the other.
+// Entries are opaque to step(): the policy names the type and its accessors, so a packed store moves
+// one word around and never re-encodes it.
+struct SepEntryOps {                   // plain struct entries
+    typedef SepEntry Entry;
+    static BJT_HD Entry make(uint32_t R, uint32_t rho0, int t) { Entry e; e.R = R; e.rho0 = rho0; e.t = t; return e; }
+    static BJT_HD uint32_t R(const Entry &e) { return e.R; }
+    static BJT_HD uint32_t rho0(const Entry &e) { return e.rho0; }
+    static BJT_HD int t(const Entry &e) { return e.t; }
+};
+
 template <int CAP>
-struct SepLocalStore {                 // fixed arrays in the thread's frame
+struct SepLocalStore : SepEntryOps {   // fixed arrays in the thread's frame
     SepEntry a[2][CAP];
     BJT_HD int cap() const { return CAP; }
     BJT_HD SepEntry load(int half, int i) const { return a[half][i]; }
     BJT_HD void store(int half, int i, const SepEntry &e) { a[half][i] = e; }
 };
 
-struct SepFlatStore {                  // a contiguous scratch region of 2 * capacity entries
+struct SepFlatStore : SepEntryOps {    // a contiguous scratch region of 2 * capacity entries
     SepEntry *base;
     int capacity;
     BJT_HD int cap() const { return capacity; }
@@ -98,59 +107,69 @@ struct SepUnpackPlain { static BJT_HD SepItem get(const SepItem *p, int k) { ret
 // Dropping needs a proof of redundancy, keeping never hurts: the result is exact.
 template <class Store>
 struct SepActive {
+    typedef typename Store::Entry E;
     int n, cur;
     Store st;
 
     BJT_HD void clear() { n = 0; cur = 0; }
-
-    BJT_HD static int slack_at(int tt, int ti, uint32_t r0) {
-        const int dt = tt - ti;
-        return (int)r0 - dt * dt;              // |values| < 2^27 for extents <= 8192
-    }
 
     // Returns the front size (may exceed fmax; only fmax are stored).  ok is cleared on capacity overflow.
     // REACH = false: emitted items are (slack, R), the Pareto front in slack.
     // REACH = true (the stage feeding stage 3, which only asks how far an item reaches): emitted items are
     //   (floor(sqrt(slack)), R) and an item is emitted only if it reaches strictly further than every
     //   emitted item with a larger tag -- equal reach with a smaller tag can never win there.
+    // Visiting order: R descending; on equal R the forward list, then the backward list, then the active set.
     template <class RawT, class Unpack, bool REACH>
     BJT_HD int step(int tc, int dir, bool skip_own, const RawT *lf, int nlf, const RawT *lb, int nlb, SepItem *out,
                     int fmax, bool &ok) {
         const int src = cur, dst = cur ^ 1;
         const int cap = st.cap();
         int i = 0, jf = 0, jb = 0, w = 0, nf = 0;
-        int best = -1, best_t = 0, last_e = -1;
-        uint32_t best_R = 0, best_rho0 = 0;
+        int best = -1, last_e = -1;
         bool last_emitted = false;
-        SepItem af, ab;
-        SepEntry ea;
-        af.R = 0; af.rho = 0; ab.R = 0; ab.rho = 0; ea.R = 0; ea.rho0 = 0; ea.t = 0;
-        if (nlf > 0) af = Unpack::get(lf, 0);
-        if (nlb > 0) ab = Unpack::get(lb, 0);
+        const E none = Store::make(0u, 0u, tc);                            // R == 0: the source is exhausted
+        E bx = none;                                                       // holder of `best`
+        E ea = none, ef = none, eb = none;                                 // heads of the three sources
         if (n > 0) ea = st.load(src, 0);
+        if (nlf > 0) { const SepItem a = Unpack::get(lf, 0); ef = Store::make(a.R, a.rho, tc); }
+        if (nlb > 0) { const SepItem a = Unpack::get(lb, 0); eb = Store::make(a.R, a.rho, tc); }
         while (true) {
-            const uint32_t Ra = i < n ? ea.R : 0u;
-            const uint32_t Rf = jf < nlf ? af.R : 0u, Rb = jb < nlb ? ab.R : 0u;
-            if (!(Ra | Rf | Rb)) break;
-            SepEntry x;
-            bool fresh;
-            if (Rf >= Ra && Rf >= Rb) { x.t = tc; x.rho0 = af.rho; x.R = Rf; fresh = true; ++jf; if (jf < nlf) af = Unpack::get(lf, jf); }
-            else if (Rb >= Ra) { x.t = tc; x.rho0 = ab.rho; x.R = Rb; fresh = true; ++jb; if (jb < nlb) ab = Unpack::get(lb, jb); }
-            else { x = ea; fresh = false; ++i; if (i < n) ea = st.load(src, i); }
-            const int s = fresh ? (int)x.rho0 : slack_at(tc, x.t, x.rho0);
+            const bool f_first = Store::R(ef) >= Store::R(eb);
+            const E ev = f_first ? ef : eb;                                // head of the arrivals
+            const uint32_t Ra = Store::R(ea), Rv = Store::R(ev);
+            if (!(Ra | Rv)) break;
+            E x;
+            if (Rv >= Ra) {
+                x = ev;
+                if (f_first) {
+                    ef = none;
+                    if (++jf < nlf) { const SepItem a = Unpack::get(lf, jf); ef = Store::make(a.R, a.rho, tc); }
+                } else {
+                    eb = none;
+                    if (++jb < nlb) { const SepItem a = Unpack::get(lb, jb); eb = Store::make(a.R, a.rho, tc); }
+                }
+            } else {
+                x = ea;
+                ea = none;
+                if (++i < n) ea = st.load(src, i);
+            }
+            const int xt = Store::t(x);
+            const uint32_t xr0 = Store::rho0(x);
+            const int dt = tc - xt;
+            const int s = (int)xr0 - dt * dt;                              // |values| < 2^27 for extents <= 8192
             BJT_SEP_COUNT(0);
             BJT_SEP_TRACE(i + jf + jb == 1 ? 0 : 1, x, tc, dir);
             if (s < 0) { BJT_SEP_COUNT(1); continue; }                     // expired
             if (s > best) {
                 BJT_SEP_COUNT(2);
-                const bool same_tag = best >= 0 && best_R == x.R && last_emitted;
-                best = s; best_t = x.t; best_R = x.R; best_rho0 = x.rho0;
-                const bool may_emit = !(skip_own && x.t == tc);
+                const bool same_tag = best >= 0 && Store::R(bx) == Store::R(x) && last_emitted;
+                best = s; bx = x;
+                const bool may_emit = !(skip_own && xt == tc);
                 if (!REACH) {
                     if (same_tag) --nf;                                    // same tag, more slack: replace
                     last_emitted = may_emit;
                     if (may_emit) {
-                        if (nf < fmax) { out[nf].rho = (uint32_t)s; out[nf].R = x.R; }
+                        if (nf < fmax) { out[nf].rho = (uint32_t)s; out[nf].R = Store::R(x); }
                         ++nf;
                     }
                 } else {
@@ -162,7 +181,7 @@ struct SepActive {
                         last_e = e;                                        // an own arrival counts: the other sweep emits it
                         last_emitted = may_emit;
                         if (may_emit) {
-                            if (nf < fmax) { out[nf].rho = (uint32_t)e; out[nf].R = x.R; }
+                            if (nf < fmax) { out[nf].rho = (uint32_t)e; out[nf].R = Store::R(x); }
                             ++nf;
                         }
                     } else {
@@ -170,9 +189,12 @@ struct SepActive {
                     }
                 }
             } else {
-                if (dir > 0 ? best_t >= x.t : best_t <= x.t) { BJT_SEP_COUNT(3); continue; }   // dominated by an item that is not older
-                const int ex = x.t + dir * sep_sqrt_upper(x.rho0);         // at or beyond x's last position
-                if (slack_at(ex, best_t, best_rho0) >= slack_at(ex, x.t, x.rho0)) { BJT_SEP_COUNT(4); continue; }   // dominated for life
+                const int bt = Store::t(bx);
+                if (dir > 0 ? bt >= xt : bt <= xt) { BJT_SEP_COUNT(3); continue; }   // dominated by an item that is not older
+                // dominated for life?  slack_b(u) - slack_x(u) is linear in u; it is >= 0 here, so test it at (or
+                // beyond) x's last position ex:  (rho_b - rho_x) - (ex - bt)^2 + (ex - xt)^2 >= 0
+                const int ex = xt + dir * sep_sqrt_upper(xr0);
+                if ((int)Store::rho0(bx) - (int)xr0 + (bt - xt) * (2 * ex - bt - xt) >= 0) { BJT_SEP_COUNT(4); continue; }
                 BJT_SEP_COUNT(5);
                 BJT_SEP_TRACE(2, x, tc, dir);
             }
