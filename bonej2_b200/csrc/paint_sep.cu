@@ -158,7 +158,7 @@ struct SepArgs {
 
 // one line of stage 1 (STAGE == 1: line = row (y,z), position = x) or stage 2 (line = (lx, z), position = y).
 // All 32 lanes of the warp must call this together (warp-aggregated allocation); `valid` masks lanes.
-template <bool PACKED, int STAGE, class Active>
+template <bool PACKED, int STAGE, int DIR, class Active>
 __device__ __forceinline__ bool dyn_line(const SepArgs &a, long long line, bool valid, Active &A, SepItem *fr, int fmax) {
     typedef ItemIO<PACKED> IO;
     const int L = STAGE == 1 ? a.w : a.h;
@@ -179,8 +179,8 @@ __device__ __forceinline__ bool dyn_line(const SepArgs &a, long long line, bool 
     unsigned long long chunk_base = 0ull;
     int chunk_left = 0;
     // the inputs of the next position are requested before this position is processed
-    const long long step_in = a.dir > 0 ? in_stride : -in_stride;
-    long long vi = in_base + (long long)(a.dir > 0 ? 0 : L - 1) * in_stride;
+    const long long step_in = DIR > 0 ? in_stride : -in_stride;
+    long long vi = in_base + (long long)(DIR > 0 ? 0 : L - 1) * in_stride;
     uint32_t r_next = 0;
     unsigned long long eF_next = 0ull, eB_next = 0ull;
     if (valid) {
@@ -188,7 +188,7 @@ __device__ __forceinline__ bool dyn_line(const SepArgs &a, long long line, bool 
         else { eF_next = __ldg(a.inF + vi); eB_next = __ldg(a.inB + vi); }
     }
     for (int step = 0; step < L; ++step) {
-        const int t = a.dir > 0 ? step : L - 1 - step;
+        const int t = DIR > 0 ? step : L - 1 - step;
         int nf = 0;
         if (valid) {
             const uint32_t r = r_next;
@@ -201,11 +201,11 @@ __device__ __forceinline__ bool dyn_line(const SepArgs &a, long long line, bool 
             if (STAGE == 1) {
                 if (r | (uint32_t)A.n) {
                     SepItem one; one.rho = r; one.R = r;
-                    nf = A.template step<SepItem, PlainIO, false>(t, a.dir, a.dir < 0, &one, r ? 1 : 0, (const SepItem *)nullptr, 0, fr, fmax, ok);
+                    nf = A.template step<SepItem, PlainIO, false, DIR>(t, &one, r ? 1 : 0, (const SepItem *)nullptr, 0, fr, fmax, ok);
                 }
             } else {
                 if (eF | eB | (unsigned long long)A.n)
-                    nf = A.template step<typename IO::T, IO, true>(t, a.dir, a.dir < 0, ipool + (eF & OFF_MASK), (int)(eF >> 40),
+                    nf = A.template step<typename IO::T, IO, true, DIR>(t, ipool + (eF & OFF_MASK), (int)(eF >> 40),
                                                              ipool + (eB & OFF_MASK), (int)(eB >> 40), fr, fmax, ok);
             }
             if (nf > fmax) { ok = false; nf = fmax; }
@@ -275,7 +275,7 @@ struct StairStore : SepStairLocal<CAP_STAIR> {
 };
 template <> struct FastActive<false> { typedef SepActive<WideStore> T; };
 
-template <bool PACKED, int STAGE>
+template <bool PACKED, int STAGE, int DIR>
 __global__ void __launch_bounds__(TPB) sep_dyn_kernel(SepArgs a) {
     __shared__ unsigned long long sm[PACKED ? 2 * S_SM * TPB : 1];
     const long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(TPB) sep_dyn_kernel(SepArgs a) {
     typename FastActive<PACKED>::T A;
     if constexpr (PACKED) A.st.sm = (uint32_t)__cvta_generic_to_shared(sm + threadIdx.x);
     SepItem fr[FMAX_FAST];
-    const bool ok = dyn_line<PACKED, STAGE>(a, line, valid, A, fr, min(FMAX_FAST, c_fmax_limit));
+    const bool ok = dyn_line<PACKED, STAGE, DIR>(a, line, valid, A, fr, min(FMAX_FAST, c_fmax_limit));
     if (valid && !ok) record_redo(a, line);
 }
 
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(TPB) sep_dyn_kernel(SepArgs a) {
 constexpr size_t SLOT_BYTES = (size_t)2 * CAP_BIG * sizeof(SepEntry) + (size_t)FMAX_BIG * sizeof(SepItem);
 
 // redo: NSLOTS threads, each takes failed lines slot, slot + NSLOTS, ...
-template <bool PACKED, int STAGE>
+template <bool PACKED, int STAGE, int DIR>
 __global__ void __launch_bounds__(32) sep_dyn_redo_kernel(SepArgs a) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const int count = *a.redo_count;
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(32) sep_dyn_redo_kernel(SepArgs a) {
         const int idx = base + slot;
         const bool valid = idx < count;
         const long long line = valid ? a.redo_list[idx] : 0;
-        const bool ok = dyn_line<PACKED, STAGE>(a, line, valid, A, fr, FMAX_BIG);
+        const bool ok = dyn_line<PACKED, STAGE, DIR>(a, line, valid, A, fr, FMAX_BIG);
         if (valid && !ok) atomicOr(a.flags, (uint32_t)F_ACTIVE);
     }
 }
@@ -386,8 +386,14 @@ int run_sep(const uint32_t *ridge, int w, int h, int d, const Plan &p, char *ws,
         a.poolflag = F_POOL1;
         const long long nlines = (long long)h * d;
         cudaMemsetAsync(redo_count, 0, 4, s);
-        sep_dyn_kernel<PACKED, 1><<<(unsigned)((nlines + TPB - 1) / TPB), TPB, 0, s>>>(a);
-        sep_dyn_redo_kernel<PACKED, 1><<<NSLOTS / 32, 32, 0, s>>>(a);
+        const unsigned grid = (unsigned)((nlines + TPB - 1) / TPB);
+        if (dir > 0) {
+            sep_dyn_kernel<PACKED, 1, +1><<<grid, TPB, 0, s>>>(a);
+            sep_dyn_redo_kernel<PACKED, 1, +1><<<NSLOTS / 32, 32, 0, s>>>(a);
+        } else {
+            sep_dyn_kernel<PACKED, 1, -1><<<grid, TPB, 0, s>>>(a);
+            sep_dyn_redo_kernel<PACKED, 1, -1><<<NSLOTS / 32, 32, 0, s>>>(a);
+        }
         launches += 2;
     }
     for (int xc0 = 0; xc0 < w; xc0 += XC) {
@@ -400,8 +406,14 @@ int run_sep(const uint32_t *ridge, int w, int h, int d, const Plan &p, char *ws,
             a.poolflag = F_POOL2;
             const long long nlines = (long long)xw * d;
             cudaMemsetAsync(redo_count, 0, 4, s);
-            sep_dyn_kernel<PACKED, 2><<<(unsigned)((nlines + TPB - 1) / TPB), TPB, 0, s>>>(a);
-            sep_dyn_redo_kernel<PACKED, 2><<<NSLOTS / 32, 32, 0, s>>>(a);
+            const unsigned grid = (unsigned)((nlines + TPB - 1) / TPB);
+            if (dir > 0) {
+                sep_dyn_kernel<PACKED, 2, +1><<<grid, TPB, 0, s>>>(a);
+                sep_dyn_redo_kernel<PACKED, 2, +1><<<NSLOTS / 32, 32, 0, s>>>(a);
+            } else {
+                sep_dyn_kernel<PACKED, 2, -1><<<grid, TPB, 0, s>>>(a);
+                sep_dyn_redo_kernel<PACKED, 2, -1><<<NSLOTS / 32, 32, 0, s>>>(a);
+            }
             launches += 2;
         }
         for (int dir = +1; dir >= -1; dir -= 2) {

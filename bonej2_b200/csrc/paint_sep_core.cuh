@@ -119,9 +119,11 @@ struct SepActive {
     //   (floor(sqrt(slack)), R) and an item is emitted only if it reaches strictly further than every
     //   emitted item with a larger tag -- equal reach with a smaller tag can never win there.
     // Visiting order: R descending; on equal R the forward list, then the backward list, then the active set.
-    template <class RawT, class Unpack, bool REACH>
-    BJT_HD int step(int tc, int dir, bool skip_own, const RawT *lf, int nlf, const RawT *lb, int nlb, SepItem *out,
-                    int fmax, bool &ok) {
+    // DIR: sweep direction (+1 / -1); the backward sweep does not emit its own arrivals (the forward one did).
+    template <class RawT, class Unpack, bool REACH, int DIR>
+    BJT_HD int step(int tc, const RawT *lf, int nlf, const RawT *lb, int nlb, SepItem *out, int fmax, bool &ok) {
+        constexpr int dir = DIR;
+        constexpr bool skip_own = DIR < 0;
         const int src = cur, dst = cur ^ 1;
         const int cap = st.cap();
         int i = 0, jf = 0, jb = 0, w = 0, nf = 0;

@@ -49,10 +49,13 @@ void dyn_line(const uint32_t *src, const Lists *inF, const Lists *inB, size_t ba
         int nf;
         if (src) {
             SepItem one; one.rho = src[v]; one.R = src[v];
-            nf = A.step<SepItem, SepUnpackPlain, false>(t, dir, dir < 0, &one, src[v] ? 1 : 0, nullptr, 0, fr, FMAX, ok);
+            nf = dir > 0 ? A.step<SepItem, SepUnpackPlain, false, +1>(t, &one, src[v] ? 1 : 0, nullptr, 0, fr, FMAX, ok)
+                         : A.step<SepItem, SepUnpackPlain, false, -1>(t, &one, src[v] ? 1 : 0, nullptr, 0, fr, FMAX, ok);
         } else {
-            nf = A.step<SepItem, SepUnpackPlain, true>(t, dir, dir < 0, inF->pool.data() + inF->off[v], (int)inF->cnt[v],
-                                                  inB->pool.data() + inB->off[v], (int)inB->cnt[v], fr, FMAX, ok);
+            const SepItem *pf = inF->pool.data() + inF->off[v], *pb = inB->pool.data() + inB->off[v];
+            const int cf = (int)inF->cnt[v], cb = (int)inB->cnt[v];
+            nf = dir > 0 ? A.step<SepItem, SepUnpackPlain, true, +1>(t, pf, cf, pb, cb, fr, FMAX, ok)
+                         : A.step<SepItem, SepUnpackPlain, true, -1>(t, pf, cf, pb, cb, fr, FMAX, ok);
         }
         if (!ok) st->overflow_act++;
         if (A.n > st->max_active) st->max_active = A.n;
