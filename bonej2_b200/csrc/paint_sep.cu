@@ -247,9 +247,10 @@ __device__ __forceinline__ bool stair_line(const SepArgs &a, long long line, Sta
             const unsigned long long e = which ? eB : eF;
             const typename IO::T *p = ipool + (e & OFF_MASK);
             const int cnt = (int)(e >> 40);
+            int hint = 0;                                   // tags descend within a list: each search resumes at the last
             for (int k = 0; k < cnt; ++k) {
                 const SepItem it = IO::get(p, k);
-                ok &= S.arrive(u, it.rho, it.R);
+                ok &= S.arrive(u, it.rho, it.R, hint);
             }
         }
         const uint32_t r = S.query(u);

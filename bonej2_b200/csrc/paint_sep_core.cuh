@@ -240,13 +240,16 @@ struct SepStair {
     BJT_HD void clear() { n = 0; }
 
     // u = coordinate in sweep direction (z forward, -z backward); e = how far the item reaches.
+    // hint: search start.  Every entry in front of it must have a tag > Rn; arrive() leaves the position it
+    // found, so the items of one list (tags descending) can pass the same variable along, starting from 0.
     // Returns false on overflow.
-    BJT_HD bool arrive(int u, uint32_t e, uint32_t Rn) {
+    BJT_HD bool arrive(int u, uint32_t e, uint32_t Rn, int &hint) {
         const int En = u + (int)e;
         // cheap reject against the head: R_n <= R_head and reach_n <= reach_head
         if (n > 0 && Rn <= st.getR(0) && En <= st.getE(0)) return true;
-        int pos = 0;
+        int pos = hint;
         while (pos < n && st.getR(pos) > Rn) ++pos;
+        hint = pos;
         if (pos > 0 && st.getE(pos - 1) >= En) return true;            // a larger tag reaches at least as far
         if (pos < n && st.getR(pos) == Rn && st.getE(pos) >= En) return true;
         int k = pos;
@@ -264,6 +267,7 @@ struct SepStair {
         st.put(pos, Rn, En);
         return true;
     }
+    BJT_HD bool arrive(int u, uint32_t e, uint32_t Rn) { int hint = 0; return arrive(u, e, Rn, hint); }
 
     // value at coordinate u (after this position's arrivals): largest tag still reaching u
     BJT_HD uint32_t query(int u) {

@@ -78,9 +78,10 @@ void stair_line(const Lists &inF, const Lists &inB, size_t base, int L, int dir,
         const size_t v = base + (size_t)x;
         for (int which = 0; which < 2; ++which) {
             const Lists &in = which ? inB : inF;
+            int hint = 0;
             for (uint32_t k = 0; k < in.cnt[v]; ++k) {
                 const SepItem it = in.pool[in.off[v] + k];
-                if (!S.arrive(u, it.rho, it.R)) st->overflow_act++;
+                if (!S.arrive(u, it.rho, it.R, hint)) st->overflow_act++;
             }
         }
         if (S.n > st->max_stair) st->max_stair = S.n;
