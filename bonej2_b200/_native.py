@@ -77,6 +77,13 @@ _SIGS = {
     "bjt_device_info": ([_VP, C.c_char_p, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)], _I),
     "bjt_set_paint_path": ([_VP, _I], _I),
     "bjt_launch_count": ([_VP], C.c_int64),
+    "bjt_dev_paint_open": ([_VP, _VP, _I, _I, _I, C.c_int64], _I),
+    "bjt_dev_paint_nxslabs": ([_VP], _I),
+    "bjt_dev_paint_xslab_width": ([_VP, _I], _I),
+    "bjt_dev_paint_lists": ([_VP, _I], _I),
+    "bjt_dev_paint_export": ([_VP, _I, _I, _I, _I, _VP, _VP, _I], _I),
+    "bjt_dev_paint_sweep": ([_VP, _I, _I, _VP, _VP, _I, _VP, _VP, _I, _VP], _I),
+    "bjt_dev_paint_close": ([_VP, _VP], _I),
     "bjt_debug_set_paint_limits": ([_VP, _I, _I], _I),
     "bjt_debug_paint_redo_lines": ([_VP], C.c_int64),
     "bjt_host_alloc": ([C.c_size_t], _VP),
@@ -168,6 +175,35 @@ class Context:
 
     def set_paint_path(self, path: int):
         self._ck(lib().bjt_set_paint_path(self._h, int(path)))
+
+    # ---- stepwise painter of a z-slab (see include/bonej_thickness.h) ----
+    def dev_paint_open(self, d_ridge, w, h, d, max_rsq):
+        self._ck(lib().bjt_dev_paint_open(self._h, d_ridge, w, h, d, int(max_rsq)))
+        return lib().bjt_dev_paint_nxslabs(self._h)
+
+    def dev_paint_xslab_width(self, xs):
+        return lib().bjt_dev_paint_xslab_width(self._h, xs)
+
+    def dev_paint_lists(self, xs):
+        self._ck(lib().bjt_dev_paint_lists(self._h, xs))
+
+    def dev_paint_export(self, xs, side, gap, nplanes, d_count, d_items, kcap):
+        self._ck(lib().bjt_dev_paint_export(self._h, xs, side, gap, nplanes, d_count, d_items, kcap))
+
+    def dev_paint_sweep(self, xs, lo, hi, kcap, d_rsq):
+        """lo / hi: lists of (count_ptr, items_ptr) device pointers of the staircases imported from below / above"""
+        def arr(pairs, k):
+            a = (C.c_void_p * max(1, len(pairs)))()
+            for i, pr in enumerate(pairs):
+                a[i] = pr[k]
+            return a
+        self._ck(lib().bjt_dev_paint_sweep(self._h, xs, len(lo), arr(lo, 0), arr(lo, 1), len(hi), arr(hi, 0), arr(hi, 1),
+                                           kcap, d_rsq))
+
+    def dev_paint_close(self) -> int:
+        f = C.c_uint32(0)
+        self._ck(lib().bjt_dev_paint_close(self._h, C.byref(f)))
+        return int(f.value)
 
     def debug_set_paint_limits(self, active_cap=0, front_cap=0):
         self._ck(lib().bjt_debug_set_paint_limits(self._h, int(active_cap), int(front_cap)))

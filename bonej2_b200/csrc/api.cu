@@ -33,6 +33,8 @@ struct bjt_ctx {
     cudaEvent_t ev[16];
     int paint_path = -1;
     int64_t launches = 0;
+    // stepwise painter of a z-slab (bjt_dev_paint_open .. _close)
+    struct { bool open = false; int w = 0, h = 0, d = 0, variant = 0; void *ws = nullptr; uint32_t *flags = nullptr; } ps;
 };
 
 static char g_err[512] = "no error";
@@ -672,6 +674,67 @@ int bjt_dev_paint(bjt_ctx *c, const uint32_t *d_ridge, int w, int h, int d, int 
     rc = dev_paint(c, d_ridge, w, h, d, path, -1, -1, d_rsq, nullptr);
     c->paint_path = saved;
     return rc;
+}
+
+// ---- stepwise painter of one z-slab -------------------------------------------------------------------
+int bjt_dev_paint_open(bjt_ctx *c, const uint32_t *d_ridge, int w, int h, int d, int64_t max_rsq) {
+    ENTER(c);
+    int rc = check_dims(c, w, h, d);
+    if (rc) return rc;
+    if (!d_ridge || max_rsq < 0) return fail(c, BJT_E_ARG, "paint_open: null ridge or negative tag bound");
+    uint32_t *scal;
+    WS("scalars", 256, scal);
+    const int variant = max_rsq >= 65536 ? 1 : 0;
+    void *wsp;
+    WS("paint_sep", paint_sep_workspace_bytes(w, h, d, variant), wsp);
+    CK(cudaMemsetAsync(scal + 8, 0, 4, c->stream));
+    c->ps.open = true; c->ps.w = w; c->ps.h = h; c->ps.d = d; c->ps.variant = variant; c->ps.ws = wsp; c->ps.flags = scal + 8;
+    c->launches += paint_sep_stage1(d_ridge, w, h, d, variant, wsp, scal + 8, c->stream); CKL();
+    return BJT_OK;
+}
+
+int bjt_dev_paint_nxslabs(bjt_ctx *c) { return c && c->ps.open ? paint_sep_nxslabs(c->ps.w) : 0; }
+int bjt_dev_paint_xslab_width(bjt_ctx *c, int xs) { return c && c->ps.open ? paint_sep_xslab_width(c->ps.w, xs) : 0; }
+
+int bjt_dev_paint_lists(bjt_ctx *c, int xs) {
+    ENTER(c);
+    if (!c->ps.open || xs < 0 || xs >= paint_sep_nxslabs(c->ps.w)) return fail(c, BJT_E_ARG, "paint_lists: no open painter or bad x-slab");
+    c->launches += paint_sep_stage2(c->ps.w, c->ps.h, c->ps.d, c->ps.variant, c->ps.ws, xs, c->ps.flags, c->stream); CKL();
+    return BJT_OK;
+}
+
+int bjt_dev_paint_export(bjt_ctx *c, int xs, int side, int gap, int nplanes, uint32_t *d_count, void *d_items, int kcap) {
+    ENTER(c);
+    if (!c->ps.open || xs < 0 || xs >= paint_sep_nxslabs(c->ps.w)) return fail(c, BJT_E_ARG, "paint_export: no open painter or bad x-slab");
+    if ((side != 1 && side != -1) || gap < 1 || nplanes < 1 || kcap < 1 || !d_count || !d_items)
+        return fail(c, BJT_E_ARG, "paint_export: bad side / gap / planes / capacity");
+    c->launches += paint_sep_export(c->ps.w, c->ps.h, c->ps.d, c->ps.variant, c->ps.ws, xs, side, gap, nplanes, d_count,
+                                    reinterpret_cast<uint2 *>(d_items), kcap, c->ps.flags, c->stream); CKL();
+    return BJT_OK;
+}
+
+int bjt_dev_paint_sweep(bjt_ctx *c, int xs, int n_lo, const uint32_t *const *lo_count, const void *const *lo_items, int n_hi,
+                        const uint32_t *const *hi_count, const void *const *hi_items, int kcap, uint32_t *d_rsq) {
+    ENTER(c);
+    if (!c->ps.open || xs < 0 || xs >= paint_sep_nxslabs(c->ps.w)) return fail(c, BJT_E_ARG, "paint_sweep: no open painter or bad x-slab");
+    if (n_lo < 0 || n_hi < 0 || n_lo > SEP_MAX_SOURCES || n_hi > SEP_MAX_SOURCES || !d_rsq)
+        return fail(c, BJT_E_ARG, "paint_sweep: at most %d sources per side", SEP_MAX_SOURCES);
+    SepImports imp{};
+    imp.n_lo = n_lo; imp.n_hi = n_hi; imp.kcap = kcap;
+    for (int i = 0; i < n_lo; ++i) { imp.lo_cnt[i] = lo_count[i]; imp.lo_items[i] = reinterpret_cast<const uint2 *>(lo_items[i]); }
+    for (int i = 0; i < n_hi; ++i) { imp.hi_cnt[i] = hi_count[i]; imp.hi_items[i] = reinterpret_cast<const uint2 *>(hi_items[i]); }
+    c->launches += paint_sep_stage3(c->ps.w, c->ps.h, c->ps.d, c->ps.variant, c->ps.ws, xs, &imp, d_rsq, c->ps.flags, c->stream); CKL();
+    return BJT_OK;
+}
+
+int bjt_dev_paint_close(bjt_ctx *c, uint32_t *overflow_flags) {
+    ENTER(c);
+    if (!c->ps.open) return fail(c, BJT_E_ARG, "paint_close: no open painter");
+    c->ps.open = false;
+    CK(cudaMemcpyAsync(c->h_scal + 8, c->ps.flags, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (overflow_flags) *overflow_flags = c->h_scal[8];
+    return BJT_OK;
 }
 
 int bjt_dev_finish(bjt_ctx *c, const uint32_t *d_rsq, const uint8_t *d_original, int w, int h, int d, int inverse,

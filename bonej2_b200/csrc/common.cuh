@@ -65,6 +65,27 @@ void paint_sep_set_limits(int cap, int fmax);          // test hook: 0 = default
 unsigned long long paint_sep_redo_lines(const void *workspace);
 int launch_paint_sep(const uint32_t *ridge, int w, int h, int d, int wide, void *workspace, uint32_t *rsq,
                      uint32_t *overflow_flag, cudaStream_t s);
+// the same painter in steps, for z-slab sharded runs (stages 1 and 2 are plane-local; only the z sweeps of
+// stage 3 cross slab boundaries).  For every x-slab xs < paint_sep_nxslabs(w): stage2, export towards the
+// neighbours, [exchange], stage3 with what the neighbours exported.
+// Boundary staircases: per column (y * xw + lx) up to kcap items (x = reach beyond the receiver's first /
+// last plane, y = tag), tags descending, and a count.
+constexpr int SEP_MAX_SOURCES = 4;
+struct SepImports {
+    int n_lo, n_hi, kcap;                                   // sources below plane 0 / above plane d-1
+    const uint32_t *lo_cnt[SEP_MAX_SOURCES]; const uint2 *lo_items[SEP_MAX_SOURCES];
+    const uint32_t *hi_cnt[SEP_MAX_SOURCES]; const uint2 *hi_items[SEP_MAX_SOURCES];
+};
+int paint_sep_nxslabs(int w);
+int paint_sep_xslab_width(int w, int xs);
+int paint_sep_stage1(const uint32_t *ridge, int w, int h, int d, int variant, void *workspace, uint32_t *flags, cudaStream_t s);
+int paint_sep_stage2(int w, int h, int d, int variant, void *workspace, int xs, uint32_t *flags, cudaStream_t s);
+// side +1: items of the last `hh` planes that reach plane d - 1 + gap or beyond; side -1: items of the first
+// `hh` planes that reach plane -gap or beyond (gap >= 1)
+int paint_sep_export(int w, int h, int d, int variant, void *workspace, int xs, int side, int gap, int hh,
+                     uint32_t *cnt, uint2 *items, int kcap, uint32_t *flags, cudaStream_t s);
+int paint_sep_stage3(int w, int h, int d, int variant, void *workspace, int xs, const SepImports *imp, uint32_t *rsq,
+                     uint32_t *flags, cudaStream_t s);
 
 // 2*sqrt + cleanup + mask + NaN/calibrate + stats
 // output / statistics restricted to planes [z_lo, z_hi) of the local volume; `out` starts at plane z_lo

@@ -154,6 +154,8 @@ struct SepArgs {
     int *redo_count;
     unsigned long long *redo_total;     // lines sent to the redo kernels in this run (diagnostics, tests)
     char *scratch;           // stores of the redo kernels
+    // stage 3 of a z-slab: staircases the neighbouring slabs exported (arrive at plane 0 / plane d-1)
+    SepImports imp;
 };
 
 // one line of stage 1 (STAGE == 1: line = row (y,z), position = x) or stage 2 (line = (lx, z), position = y).
@@ -253,6 +255,22 @@ __device__ __forceinline__ bool stair_line(const SepArgs &a, long long line, Sta
                 ok &= S.arrive(u, it.rho, it.R, hint);
             }
         }
+        if (z == 0) {
+            for (int src = 0; src < a.imp.n_lo; ++src) {
+                const int cnt = (int)a.imp.lo_cnt[src][in_base];
+                const uint2 *p = a.imp.lo_items[src] + in_base * a.imp.kcap;
+                int hint = 0;
+                for (int k = 0; k < cnt; ++k) { const uint2 it = p[k]; ok &= S.arrive(u, it.x, it.y, hint); }
+            }
+        }
+        if (z == a.d - 1) {
+            for (int src = 0; src < a.imp.n_hi; ++src) {
+                const int cnt = (int)a.imp.hi_cnt[src][in_base];
+                const uint2 *p = a.imp.hi_items[src] + in_base * a.imp.kcap;
+                int hint = 0;
+                for (int k = 0; k < cnt; ++k) { const uint2 it = p[k]; ok &= S.arrive(u, it.x, it.y, hint); }
+            }
+        }
         const uint32_t r = S.query(u);
         uint32_t *o = a.out + out_base + (long long)z * out_stride;
         if (a.dir > 0) *o = r;
@@ -333,6 +351,52 @@ __global__ void __launch_bounds__(32) sep_stair_redo_kernel(SepArgs a) {
         if (!stair_line<PACKED>(a, a.redo_list[idx], S)) atomicOr(a.flags, (uint32_t)F_ACTIVE);
 }
 
+// boundary staircase of a z-slab: what the items of the planes next to a slab face still cover beyond it.
+// One thread per column; sweep towards the face over the last hh planes, then write the steps that reach the
+// receiver's first plane (coordinate `target` in sweep direction) as (reach beyond it, tag), tags descending.
+template <bool PACKED>
+__global__ void __launch_bounds__(TPB) sep_export_kernel(SepArgs a, int side, int gap, int hh, uint32_t *cnt, uint2 *items,
+                                                          int kcap) {
+    typedef ItemIO<PACKED> IO;
+    const long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= (long long)a.xw * a.h) return;
+    const long long in_stride = (long long)a.h * a.xw;
+    const typename IO::T *ipool = reinterpret_cast<const typename IO::T *>(a.in_pool);
+    SepStair<StairStore> S;
+    S.clear();
+    bool ok = true;
+    const int nplanes = hh < a.d ? hh : a.d;
+    for (int step = 0; step < nplanes; ++step) {
+        const int z = side > 0 ? a.d - nplanes + step : nplanes - 1 - step;
+        const int u = side > 0 ? z : -z;
+        const long long vi = line + (long long)z * in_stride;
+        const unsigned long long eF = __ldg(a.inF + vi), eB = __ldg(a.inB + vi);
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const unsigned long long e = which ? eB : eF;
+            const typename IO::T *p = ipool + (e & OFF_MASK);
+            const int c = (int)(e >> 40);
+            int hint = 0;
+            for (int k = 0; k < c; ++k) {
+                const SepItem it = IO::get(p, k);
+                ok &= S.arrive(u, it.rho, it.R, hint);
+            }
+        }
+        S.query(u);
+    }
+    const int target = (side > 0 ? a.d - 1 : 0) + gap;
+    int nout = 0;
+    for (int i = 0; i < S.n; ++i) {
+        const int E = S.st.getE(i);
+        if (E < target) continue;
+        if (nout < kcap) items[line * kcap + nout] = make_uint2((uint32_t)(E - target), S.st.getR(i));
+        ++nout;
+    }
+    if (nout > kcap) { ok = false; nout = kcap; }
+    cnt[line] = (uint32_t)nout;
+    if (!ok) atomicOr(a.flags, (uint32_t)F_FRONT);
+}
+
 struct Plan {
     size_t n, nslab, maxlines;
     size_t off_idx1f, off_idx1b, off_idx2f, off_idx2b, off_pool1, off_pool2, off_counters, off_redo, off_scratch, total;
@@ -362,31 +426,43 @@ Plan make_plan(int w, int h, int d, int wide, int scale) {
     return p;
 }
 
+struct Bufs {
+    unsigned long long *counters, *idx1f, *idx1b, *idx2f, *idx2b;
+    int *redo_count;
+    void *pool1, *pool2;
+    SepArgs base;
+};
+
+Bufs make_bufs(int w, int h, int d, const Plan &p, char *ws, uint32_t *flags) {
+    Bufs b;
+    b.counters = reinterpret_cast<unsigned long long *>(ws + p.off_counters);
+    b.redo_count = reinterpret_cast<int *>(b.counters + 4);
+    b.idx1f = reinterpret_cast<unsigned long long *>(ws + p.off_idx1f);
+    b.idx1b = reinterpret_cast<unsigned long long *>(ws + p.off_idx1b);
+    b.idx2f = reinterpret_cast<unsigned long long *>(ws + p.off_idx2f);
+    b.idx2b = reinterpret_cast<unsigned long long *>(ws + p.off_idx2b);
+    b.pool1 = ws + p.off_pool1; b.pool2 = ws + p.off_pool2;
+    b.base = SepArgs{};
+    b.base.w = w; b.base.h = h; b.base.d = d; b.base.flags = flags;
+    b.base.redo_list = reinterpret_cast<int *>(ws + p.off_redo); b.base.redo_count = b.redo_count;
+    b.base.redo_total = b.counters + 5;
+    b.base.scratch = ws + p.off_scratch;
+    return b;
+}
+
+// stage 1: both directions share pool 1
 template <bool PACKED>
-int run_sep(const uint32_t *ridge, int w, int h, int d, const Plan &p, char *ws, uint32_t *rsq, uint32_t *flags,
-            cudaStream_t s) {
+int run_stage1(const uint32_t *ridge, int w, int h, int d, const Plan &p, char *ws, uint32_t *flags, cudaStream_t s) {
+    Bufs b = make_bufs(w, h, d, p, ws, flags);
     int launches = 0;
-    unsigned long long *counters = reinterpret_cast<unsigned long long *>(ws + p.off_counters);
-    int *redo_count = reinterpret_cast<int *>(counters + 4);
-    SepArgs base{};
-    base.w = w; base.h = h; base.d = d; base.flags = flags;
-    base.redo_list = reinterpret_cast<int *>(ws + p.off_redo); base.redo_count = redo_count;
-    base.redo_total = counters + 5;
-    base.scratch = ws + p.off_scratch;
-    unsigned long long *idx1f = reinterpret_cast<unsigned long long *>(ws + p.off_idx1f);
-    unsigned long long *idx1b = reinterpret_cast<unsigned long long *>(ws + p.off_idx1b);
-    unsigned long long *idx2f = reinterpret_cast<unsigned long long *>(ws + p.off_idx2f);
-    unsigned long long *idx2b = reinterpret_cast<unsigned long long *>(ws + p.off_idx2b);
-    void *pool1 = ws + p.off_pool1, *pool2 = ws + p.off_pool2;
-    cudaMemsetAsync(counters, 0, 256, s);
-    // stage 1: both directions share pool 1
+    cudaMemsetAsync(b.counters, 0, 256, s);
     for (int dir = +1; dir >= -1; dir -= 2) {
-        SepArgs a = base;
+        SepArgs a = b.base;
         a.ridge = ridge; a.xc0 = 0; a.xw = w; a.dir = dir;
-        a.out_idx = dir > 0 ? idx1f : idx1b; a.out_pool = pool1; a.out_cap = p.cap1; a.out_counter = counters;
+        a.out_idx = dir > 0 ? b.idx1f : b.idx1b; a.out_pool = b.pool1; a.out_cap = p.cap1; a.out_counter = b.counters;
         a.poolflag = F_POOL1;
         const long long nlines = (long long)h * d;
-        cudaMemsetAsync(redo_count, 0, 4, s);
+        cudaMemsetAsync(b.redo_count, 0, 4, s);
         const unsigned grid = (unsigned)((nlines + TPB - 1) / TPB);
         if (dir > 0) {
             sep_dyn_kernel<PACKED, 1, +1><<<grid, TPB, 0, s>>>(a);
@@ -397,36 +473,76 @@ int run_sep(const uint32_t *ridge, int w, int h, int d, const Plan &p, char *ws,
         }
         launches += 2;
     }
+    return launches;
+}
+
+// stage 2 of one x-slab: lists along y into pool 2 (reused by every slab)
+template <bool PACKED>
+int run_stage2(int w, int h, int d, const Plan &p, char *ws, int xc0, uint32_t *flags, cudaStream_t s) {
+    Bufs b = make_bufs(w, h, d, p, ws, flags);
+    int launches = 0;
+    const int xw = (w - xc0) < XC ? (w - xc0) : XC;
+    cudaMemsetAsync(b.counters + 1, 0, 8, s);
+    for (int dir = +1; dir >= -1; dir -= 2) {
+        SepArgs a = b.base;
+        a.inF = b.idx1f; a.inB = b.idx1b; a.in_pool = b.pool1; a.xc0 = xc0; a.xw = xw; a.dir = dir;
+        a.out_idx = dir > 0 ? b.idx2f : b.idx2b; a.out_pool = b.pool2; a.out_cap = p.cap2; a.out_counter = b.counters + 1;
+        a.poolflag = F_POOL2;
+        const long long nlines = (long long)xw * d;
+        cudaMemsetAsync(b.redo_count, 0, 4, s);
+        const unsigned grid = (unsigned)((nlines + TPB - 1) / TPB);
+        if (dir > 0) {
+            sep_dyn_kernel<PACKED, 2, +1><<<grid, TPB, 0, s>>>(a);
+            sep_dyn_redo_kernel<PACKED, 2, +1><<<NSLOTS / 32, 32, 0, s>>>(a);
+        } else {
+            sep_dyn_kernel<PACKED, 2, -1><<<grid, TPB, 0, s>>>(a);
+            sep_dyn_redo_kernel<PACKED, 2, -1><<<NSLOTS / 32, 32, 0, s>>>(a);
+        }
+        launches += 2;
+    }
+    return launches;
+}
+
+// stage 3 of one x-slab: z sweeps, painted r^2 out
+template <bool PACKED>
+int run_stage3(int w, int h, int d, const Plan &p, char *ws, int xc0, const SepImports *imp, uint32_t *rsq, uint32_t *flags,
+               cudaStream_t s) {
+    Bufs b = make_bufs(w, h, d, p, ws, flags);
+    int launches = 0;
+    const int xw = (w - xc0) < XC ? (w - xc0) : XC;
+    for (int dir = +1; dir >= -1; dir -= 2) {
+        SepArgs a = b.base;
+        a.inF = b.idx2f; a.inB = b.idx2b; a.in_pool = b.pool2; a.xc0 = xc0; a.xw = xw; a.dir = dir;
+        a.out = rsq;
+        if (imp) a.imp = *imp;
+        const long long nlines = (long long)xw * h;
+        cudaMemsetAsync(b.redo_count, 0, 4, s);
+        sep_stair_kernel<PACKED><<<(unsigned)((nlines + TPB - 1) / TPB), TPB, 0, s>>>(a);
+        sep_stair_redo_kernel<PACKED><<<NSLOTS / 32, 32, 0, s>>>(a);
+        launches += 2;
+    }
+    return launches;
+}
+
+template <bool PACKED>
+int run_export(int w, int h, int d, const Plan &p, char *ws, int xc0, int side, int gap, int hh, uint32_t *cnt, uint2 *items,
+               int kcap, uint32_t *flags, cudaStream_t s) {
+    Bufs b = make_bufs(w, h, d, p, ws, flags);
+    const int xw = (w - xc0) < XC ? (w - xc0) : XC;
+    SepArgs a = b.base;
+    a.inF = b.idx2f; a.inB = b.idx2b; a.in_pool = b.pool2; a.xc0 = xc0; a.xw = xw; a.dir = side;
+    const long long nlines = (long long)xw * h;
+    sep_export_kernel<PACKED><<<(unsigned)((nlines + TPB - 1) / TPB), TPB, 0, s>>>(a, side, gap, hh, cnt, items, kcap);
+    return 1;
+}
+
+template <bool PACKED>
+int run_sep(const uint32_t *ridge, int w, int h, int d, const Plan &p, char *ws, uint32_t *rsq, uint32_t *flags,
+            cudaStream_t s) {
+    int launches = run_stage1<PACKED>(ridge, w, h, d, p, ws, flags, s);
     for (int xc0 = 0; xc0 < w; xc0 += XC) {
-        const int xw = (w - xc0) < XC ? (w - xc0) : XC;
-        cudaMemsetAsync(counters + 1, 0, 8, s);
-        for (int dir = +1; dir >= -1; dir -= 2) {
-            SepArgs a = base;
-            a.inF = idx1f; a.inB = idx1b; a.in_pool = pool1; a.xc0 = xc0; a.xw = xw; a.dir = dir;
-            a.out_idx = dir > 0 ? idx2f : idx2b; a.out_pool = pool2; a.out_cap = p.cap2; a.out_counter = counters + 1;
-            a.poolflag = F_POOL2;
-            const long long nlines = (long long)xw * d;
-            cudaMemsetAsync(redo_count, 0, 4, s);
-            const unsigned grid = (unsigned)((nlines + TPB - 1) / TPB);
-            if (dir > 0) {
-                sep_dyn_kernel<PACKED, 2, +1><<<grid, TPB, 0, s>>>(a);
-                sep_dyn_redo_kernel<PACKED, 2, +1><<<NSLOTS / 32, 32, 0, s>>>(a);
-            } else {
-                sep_dyn_kernel<PACKED, 2, -1><<<grid, TPB, 0, s>>>(a);
-                sep_dyn_redo_kernel<PACKED, 2, -1><<<NSLOTS / 32, 32, 0, s>>>(a);
-            }
-            launches += 2;
-        }
-        for (int dir = +1; dir >= -1; dir -= 2) {
-            SepArgs a = base;
-            a.inF = idx2f; a.inB = idx2b; a.in_pool = pool2; a.xc0 = xc0; a.xw = xw; a.dir = dir;
-            a.out = rsq;
-            const long long nlines = (long long)xw * h;
-            cudaMemsetAsync(redo_count, 0, 4, s);
-            sep_stair_kernel<PACKED><<<(unsigned)((nlines + TPB - 1) / TPB), TPB, 0, s>>>(a);
-            sep_stair_redo_kernel<PACKED><<<NSLOTS / 32, 32, 0, s>>>(a);
-            launches += 2;
-        }
+        launches += run_stage2<PACKED>(w, h, d, p, ws, xc0, flags, s);
+        launches += run_stage3<PACKED>(w, h, d, p, ws, xc0, nullptr, rsq, flags, s);
     }
     return launches;
 }
@@ -449,6 +565,34 @@ unsigned long long paint_sep_redo_lines(const void *workspace) {
 // variant: bit 0 = wide (u64) items, bit 1 = doubled pools
 size_t paint_sep_workspace_bytes(int w, int h, int d, int variant) {
     return make_plan(w, h, d, variant & 1, (variant & 2) ? 2 : 1).total;
+}
+
+int paint_sep_nxslabs(int w) { return (w + XC - 1) / XC; }
+int paint_sep_xslab_width(int w, int xs) { const int xc0 = xs * XC; return (w - xc0) < XC ? (w - xc0) : XC; }
+
+int paint_sep_stage1(const uint32_t *ridge, int w, int h, int d, int variant, void *workspace, uint32_t *flags, cudaStream_t s) {
+    const Plan p = make_plan(w, h, d, variant & 1, (variant & 2) ? 2 : 1);
+    char *ws = reinterpret_cast<char *>(workspace);
+    return (variant & 1) ? run_stage1<false>(ridge, w, h, d, p, ws, flags, s) : run_stage1<true>(ridge, w, h, d, p, ws, flags, s);
+}
+int paint_sep_stage2(int w, int h, int d, int variant, void *workspace, int xs, uint32_t *flags, cudaStream_t s) {
+    const Plan p = make_plan(w, h, d, variant & 1, (variant & 2) ? 2 : 1);
+    char *ws = reinterpret_cast<char *>(workspace);
+    return (variant & 1) ? run_stage2<false>(w, h, d, p, ws, xs * XC, flags, s) : run_stage2<true>(w, h, d, p, ws, xs * XC, flags, s);
+}
+int paint_sep_export(int w, int h, int d, int variant, void *workspace, int xs, int side, int gap, int hh, uint32_t *cnt,
+                     uint2 *items, int kcap, uint32_t *flags, cudaStream_t s) {
+    const Plan p = make_plan(w, h, d, variant & 1, (variant & 2) ? 2 : 1);
+    char *ws = reinterpret_cast<char *>(workspace);
+    return (variant & 1) ? run_export<false>(w, h, d, p, ws, xs * XC, side, gap, hh, cnt, items, kcap, flags, s)
+                         : run_export<true>(w, h, d, p, ws, xs * XC, side, gap, hh, cnt, items, kcap, flags, s);
+}
+int paint_sep_stage3(int w, int h, int d, int variant, void *workspace, int xs, const SepImports *imp, uint32_t *rsq,
+                     uint32_t *flags, cudaStream_t s) {
+    const Plan p = make_plan(w, h, d, variant & 1, (variant & 2) ? 2 : 1);
+    char *ws = reinterpret_cast<char *>(workspace);
+    return (variant & 1) ? run_stage3<false>(w, h, d, p, ws, xs * XC, imp, rsq, flags, s)
+                         : run_stage3<true>(w, h, d, p, ws, xs * XC, imp, rsq, flags, s);
 }
 
 int launch_paint_sep(const uint32_t *ridge, int w, int h, int d, int variant, void *workspace, uint32_t *rsq,

@@ -4,11 +4,16 @@ The volume [d][h][w] is cut into contiguous z-slabs, one per rank
 
   EDT x, y          slab-local kernels
   EDT z             all-to-all transpose z-slabs -> y-slabs, z pass on whole z lines, transpose back
-  ridge + paint     every rank fetches the squared-EDT planes within H = r_max + 2 of its slab (r_max from
-                    an all-reduce of the largest squared distance), computes the ridge and paints slab +
-                    halo locally: any ball that touches the slab +- 2 has its centre inside that range
-                    (the "max-radius halo exchange" of BASELINE.json's north_star)
-  cleanup .. stats  on slab +- 2 painted planes, output and statistics restricted to the slab
+  ridge             on the slab's own planes (one fetched plane of squared EDT either side)
+  paint             the painter's x and y stages are plane-local; its z sweeps cross slab faces.  What crosses
+                    is, per (x, y) column, the staircase (tag, reach beyond the face) of the balls centred
+                    within r_max planes of the face (r_max from an all-reduce of the largest squared
+                    distance): every rank exports that to the slabs within reach, imports theirs and sweeps
+                    its own planes (the "max-radius halo exchange" of BASELINE.json's north_star, with the
+                    halo reduced to what actually reaches across).  Fallback, and the only path of backends
+                    without the stepwise painter: fetch the squared-EDT planes within r_max + 2 and paint
+                    slab + halo locally.
+  cleanup .. stats  on slab +- 2 painted planes (fetched), output and statistics restricted to the slab
                     (bjt_dev_finish_range); (n, sum, sum^2, min, max) are combined across ranks before
                     mean and sd are formed, as ij.process.StackStatistics does on the whole stack
 
@@ -213,6 +218,40 @@ class CudaStages:
         self.ctx.dev_paint(ridge_ext.data_ptr(), w, h, de, out.data_ptr())
         return out
 
+    # stepwise painter (bjt_dev_paint_open .. _close); boundary buffers are int32 tensors [ncol * (2 kcap + 1)]:
+    # items first (8-byte aligned), counts behind
+    def paint_open(self, ridge_own, max_rsq):
+        dz, h, w = ridge_own.shape
+        self._ps = (ridge_own, self._i32((dz, h, w)))
+        return self.ctx.dev_paint_open(ridge_own.data_ptr(), w, h, dz, max_rsq)
+
+    def paint_xslab_cols(self, xs):
+        return self.ctx.dev_paint_xslab_width(xs) * self._ps[0].shape[1]
+
+    def paint_lists(self, xs):
+        self.ctx.dev_paint_lists(xs)
+
+    def boundary_buffer(self, ncol, kcap):
+        return torch.empty(ncol * (2 * kcap + 1), dtype=torch.int32, device=self.device)
+
+    @staticmethod
+    def _split(buf, ncol, kcap):
+        return buf.data_ptr() + 8 * ncol * kcap, buf.data_ptr()              # (count pointer, items pointer)
+
+    def paint_export(self, xs, side, gap, nplanes, buf, ncol, kcap):
+        cnt, items = self._split(buf, ncol, kcap)
+        self.ctx.dev_paint_export(xs, side, gap, nplanes, cnt, items, kcap)
+
+    def paint_sweep(self, xs, lo, hi, ncol, kcap):
+        self.ctx.dev_paint_sweep(xs, [self._split(b, ncol, kcap) for b in lo], [self._split(b, ncol, kcap) for b in hi],
+                                 kcap, self._ps[1].data_ptr())
+
+    def paint_close(self):
+        flags = self.ctx.dev_paint_close()
+        out = self._ps[1]
+        self._ps = None
+        return out, flags
+
     def full(self, shape, value):
         return torch.full(shape, value, dtype=torch.int32, device=self.device)
 
@@ -232,7 +271,62 @@ def no_result(n: int) -> int:
     return 3 * (n + 1) * (n + 1)
 
 
-def thickness_slab(stages, comm: Comm, slab_u8, dims, inverse, mask=True, pixel_width=1.0, timings=None):
+BOUNDARY_KCAP = 32          # staircase steps per column a slab face can carry (more: fall back to the halo repaint)
+MAX_SOURCES = 4             # slabs per side a sweep can import from (bjt_dev_paint_sweep)
+
+
+def paint_exchange(stages, comm: Comm, ridge_own, zs, gmax, kcap=BOUNDARY_KCAP):
+    """Painted r^2 of this rank's own planes: plane-local x / y stages, boundary staircases exchanged with the
+    slabs within reach, z sweeps.  Returns None (on every rank alike) when the stepwise painter cannot take
+    the case -- too many slabs within reach or a capacity exceeded -- and the caller repaints slab + halo."""
+    G, r = comm.size, comm.rank
+    z0, z1 = zs[r]
+    rmax = math.isqrt(gmax)                                               # no ball reaches further than this
+    nplanes = rmax + 1
+
+    def within(p, q):
+        """gap from slab p's face plane to slab q's first plane, or 0 when out of reach / empty"""
+        (a0, a1), (b0, b1) = zs[p], zs[q]
+        if a1 == a0 or b1 == b0:
+            return 0
+        gap = b0 - (a1 - 1) if q > p else a0 - (b1 - 1)
+        return gap if gap <= rmax else 0
+
+    too_many = any(sum(1 for p in range(q) if within(p, q)) > MAX_SOURCES or
+                   sum(1 for p in range(q + 1, G) if within(p, q)) > MAX_SOURCES for q in range(G))
+    if too_many:
+        return None
+    flags = 0
+    out = None
+    if z1 > z0:
+        nxs = stages.paint_open(ridge_own, gmax)
+        for xs in range(nxs):
+            ncol = stages.paint_xslab_cols(xs)
+            stages.paint_lists(xs)
+            sends, recvs, lo, hi = {}, {}, [], []
+            for p in range(G):
+                if p == r:
+                    continue
+                gap = within(r, p)
+                if gap:                                                   # what I carry across to slab p
+                    buf = stages.boundary_buffer(ncol, kcap)
+                    stages.paint_export(xs, +1 if p > r else -1, gap, nplanes, buf, ncol, kcap)
+                    sends[p] = buf
+                if within(p, r):                                          # what slab p carries across to me
+                    recvs[p] = stages.boundary_buffer(ncol, kcap)
+                    (lo if p < r else hi).append(recvs[p])
+            comm.exchange(sends, recvs)
+            stages.paint_sweep(xs, lo, hi, ncol, kcap)
+            del sends, recvs, lo, hi
+        out, flags = stages.paint_close()
+    flags = comm.allreduce_max_int(int(flags != 0), ridge_own.device)
+    if flags:
+        return None
+    return out if out is not None else ridge_own.new_empty((0,) + tuple(ridge_own.shape[1:]))
+
+
+def thickness_slab(stages, comm: Comm, slab_u8, dims, inverse, mask=True, pixel_width=1.0, timings=None,
+                   paint_mode="auto"):
     """One pipeline run (LocalThicknessWrapper.processImage + StackStatistics) on this rank's z-slab.
     slab_u8: [dz][h][w] planes zs[rank] of the volume dims = (w, h, d).  Returns (map slab f32, stats dict)."""
     w, h, d = dims
@@ -272,6 +366,26 @@ def thickness_slab(stages, comm: Comm, slab_u8, dims, inverse, mask=True, pixel_
     elif gmax >= n0:
         rsq_sub = stages.full((s_hi - s_lo, h, w), n0)                 # no background anywhere (sentinel)
     else:
+        rsq_sub = None
+        if paint_mode != "halo" and hasattr(stages, "paint_open"):
+            # ridge of the slab's own planes: the squared EDT one plane further out on either side
+            needs = [(max(0, a - 1), min(d, b + 1)) if b > a else (a, a) for (a, b) in zs]
+            sq_ext = gather_planes(comm, sq, zs, needs)
+            mark("halo", t0); t0 = t_()
+            ridge_own = stages.ridge(sq_ext)[z0 - needs[r][0]:z1 - needs[r][0]] if z1 > z0 else sq_ext
+            del sq_ext
+            mark("ridge", t0); t0 = t_()
+            rsq_own = paint_exchange(stages, comm, ridge_own, zs, gmax)
+            del ridge_own
+            mark("paint", t0); t0 = t_()
+            if rsq_own is not None:
+                needs2 = [(max(0, a - 2), min(d, b + 2)) if b > a else (a, a) for (a, b) in zs]
+                rsq_sub = gather_planes(comm, rsq_own, zs, needs2)
+                del rsq_own
+                mark("halo", t0); t0 = t_()
+            elif paint_mode == "exchange":
+                raise RuntimeError("stepwise painter refused the case (capacity or reach) and paint_mode='exchange' forbids the fallback")
+    if gmax != 0 and gmax < n0 and rsq_sub is None:
         H = math.isqrt(gmax - 1) + 1 + 2                               # ceil(sqrt(r^2 max)) + 2
         # ridge of planes [z0-H, z1+H) needs the squared EDT one plane further out
         needs = []

@@ -122,6 +122,30 @@ int bjt_dev_edt_y(bjt_ctx *ctx, const uint16_t *d_gx, int w, int h, int d, int n
 int bjt_dev_edt_z(bjt_ctx *ctx, const uint32_t *d_gy, int w, int h, int d, int n_sentinel, uint32_t *d_sq);
 int bjt_dev_ridge(bjt_ctx *ctx, const uint32_t *d_sq, int w, int h, int d, uint32_t *d_ridge);
 int bjt_dev_paint(bjt_ctx *ctx, const uint32_t *d_ridge, int w, int h, int d, int path, uint32_t *d_rsq);
+
+/* The painter of one z-slab in steps (Local_Thickness_Parallel over a volume cut along z).  Its x and y
+ * stages are plane-local; only the z sweeps cross slab faces, and what crosses is small: per (x, y) column
+ * the staircase of (tag, reach beyond the face) of the balls centred next to the face.
+ *   open(ridge of the slab's own planes, max_rsq = largest tag anywhere)      x stage
+ *   for xs in 0 .. nxslabs-1  (column blocks of xslab_width(xs) columns):
+ *       lists(xs)                                                             y stage of the block
+ *       export(xs, side, gap, nplanes, count, items, kcap)   for every slab that lies within reach:
+ *           side +1 / -1: the receiver lies above / below; gap = planes between my face plane and the
+ *           receiver's first plane, counted from 1 for the adjacent slab; nplanes >= reach of the largest
+ *           ball; count[ncol] and items[ncol * kcap] (8 bytes each: reach beyond, tag), ncol =
+ *           xslab_width(xs) * h, column index y * xslab_width + x
+ *       -- exchange the exported buffers between ranks --
+ *       sweep(xs, imports from below, imports from above, kcap, rsq of the slab's own planes)   z stage
+ *   close(&flags): flags != 0 means a list or staircase capacity was exceeded and rsq is NOT valid; run the
+ *   slab through bjt_dev_paint on slab + halo instead (it is never silent).                              */
+int bjt_dev_paint_open(bjt_ctx *ctx, const uint32_t *d_ridge, int w, int h, int d, int64_t max_rsq);
+int bjt_dev_paint_nxslabs(bjt_ctx *ctx);
+int bjt_dev_paint_xslab_width(bjt_ctx *ctx, int xs);
+int bjt_dev_paint_lists(bjt_ctx *ctx, int xs);
+int bjt_dev_paint_export(bjt_ctx *ctx, int xs, int side, int gap, int nplanes, uint32_t *d_count, void *d_items, int kcap);
+int bjt_dev_paint_sweep(bjt_ctx *ctx, int xs, int n_lo, const uint32_t *const *lo_count, const void *const *lo_items,
+                        int n_hi, const uint32_t *const *hi_count, const void *const *hi_items, int kcap, uint32_t *d_rsq);
+int bjt_dev_paint_close(bjt_ctx *ctx, uint32_t *overflow_flags);
 int bjt_dev_finish(bjt_ctx *ctx, const uint32_t *d_rsq, const uint8_t *d_original, int w, int h, int d,
                    int inverse, int calibrate, double pixel_width, float *d_out, bjt_stats *stats);
 /* same on a slab with halo planes: the map and the statistics cover planes [z_lo, z_hi) of the local

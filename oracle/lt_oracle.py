@@ -182,3 +182,42 @@ def sep_paint_model(ridge_u32):
                 items_per_voxel=[[st.items[s][k] / r.size for k in range(2)] for s in range(2)],
                 mean_active=[st.sum_active[s] / max(1, st.steps[s]) for s in range(3)])
     return out, info
+
+
+class SepPaintSession:
+    """The CPU model's painter in steps (oracle/sep_paint_model.cpp spm_open .. spm_close): same calls and
+    buffer layout as bjt_dev_paint_open .. _close, on numpy arrays.  TEST ONLY."""
+
+    def __init__(self, ridge_u32):
+        r = _vol(ridge_u32, np.uint32)
+        self.d, self.h, self.w = r.shape
+        L = lib()
+        L.spm_open.restype = C.c_void_p
+        L.spm_close.restype = C.c_long
+        self._h = C.c_void_p(L.spm_open(_p(r, C.c_uint32), self.w, self.h, self.d))
+
+    def export(self, side, gap, nplanes, kcap):
+        ncol = self.w * self.h
+        cnt = np.zeros(ncol, np.uint32)
+        items = np.zeros((ncol, kcap, 2), np.uint32)
+        lib().spm_export(self._h, int(side), int(gap), int(nplanes), _p(cnt, C.c_uint32), _p(items, C.c_uint32), int(kcap))
+        return cnt, items
+
+    def sweep(self, lo, hi, kcap):
+        """lo / hi: lists of (cnt, items) imported from below / above"""
+        def arrs(pairs):
+            PT = C.POINTER(C.c_uint32)
+            a = (PT * max(1, len(pairs)))()
+            b = (PT * max(1, len(pairs)))()
+            for i, (c, it) in enumerate(pairs):
+                a[i] = _p(c, C.c_uint32)
+                b[i] = _p(it, C.c_uint32)
+            return a, b
+        out = np.zeros((self.d, self.h, self.w), np.uint32)
+        lc, li = arrs(lo)
+        hc, hi_ = arrs(hi)
+        lib().spm_sweep(self._h, len(lo), lc, li, len(hi), hc, hi_, int(kcap), _p(out, C.c_uint32))
+        return out
+
+    def close(self) -> int:
+        return int(lib().spm_close(self._h))

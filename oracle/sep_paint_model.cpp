@@ -116,3 +116,115 @@ extern "C" int spm_paint(const uint32_t *ridge, int w, int h, int d, uint32_t *o
     }
     return (st->overflow_act || st->overflow_front) ? 1 : 0;
 }
+
+/* ---- the painter in steps, as the CUDA library offers it to z-slab sharded runs (bjt_dev_paint_open ..
+ * _close in include/bonej_thickness.h), so the exchange logic of bonej2_b200/sharded.py can be tested on
+ * CPU over gloo.  One x-slab (the whole width).  Boundary staircases use the kernels' layout: per column
+ * y * w + x up to kcap items {reach beyond, tag}, tags descending, and a count. ---- */
+namespace {
+struct SpmSession {
+    int w, h, d;
+    Lists *l2f, *l2b;
+    long overflow;
+};
+}
+
+extern "C" void *spm_open(const uint32_t *ridge, int w, int h, int d) {
+    const size_t N = (size_t)w * h * d, wh = (size_t)w * h;
+    spm_stats_t st;
+    memset(&st, 0, sizeof st);
+    SpmSession *S = new SpmSession{w, h, d, nullptr, nullptr, 0};
+    /* NB: spm_paint sweeps z first and x last, the kernels x first and z last; for a z-slab the plane-local
+     * stages must be x and y, so here: stage 1 along x, stage 2 along y, stage 3 along z */
+    Lists m1f(N), m1b(N);
+    for (size_t row = 0; row < (size_t)h * d; ++row) {
+        dyn_line(ridge, nullptr, nullptr, row * w, 1, w, +1, m1f, &st, 0);
+        dyn_line(ridge, nullptr, nullptr, row * w, 1, w, -1, m1b, &st, 0);
+    }
+    S->l2f = new Lists(N); S->l2b = new Lists(N);
+    for (int z = 0; z < d; ++z) for (int x = 0; x < w; ++x) {
+        const size_t base = (size_t)z * wh + x;
+        dyn_line(nullptr, &m1f, &m1b, base, (size_t)w, h, +1, *S->l2f, &st, 1);
+        dyn_line(nullptr, &m1f, &m1b, base, (size_t)w, h, -1, *S->l2b, &st, 1);
+    }
+    S->overflow = st.overflow_act + st.overflow_front;
+    return S;
+}
+
+static void spm_arrivals(const SpmSession *S, SepStair<SepStairLocal<CAP> > &T, size_t v, int u, long *ovf) {
+    for (int which = 0; which < 2; ++which) {
+        const Lists &in = which ? *S->l2b : *S->l2f;
+        int hint = 0;
+        for (uint32_t k = 0; k < in.cnt[v]; ++k) {
+            const SepItem it = in.pool[in.off[v] + k];
+            if (!T.arrive(u, it.rho, it.R, hint)) ++*ovf;
+        }
+    }
+}
+
+extern "C" int spm_export(void *handle, int side, int gap, int nplanes, uint32_t *cnt, uint32_t *items, int kcap) {
+    SpmSession *S = (SpmSession *)handle;
+    const size_t wh = (size_t)S->w * S->h;
+    static SepStair<SepStairLocal<CAP> > T;
+    const int np = nplanes < S->d ? nplanes : S->d;
+    for (size_t col = 0; col < wh; ++col) {
+        T.clear();
+        for (int step = 0; step < np; ++step) {
+            const int z = side > 0 ? S->d - np + step : np - 1 - step;
+            const int u = side > 0 ? z : -z;
+            spm_arrivals(S, T, (size_t)z * wh + col, u, &S->overflow);
+            T.query(u);
+        }
+        const int target = (side > 0 ? S->d - 1 : 0) + gap;
+        int nout = 0;
+        for (int i = 0; i < T.n; ++i) {
+            const int E = T.st.getE(i);
+            if (E < target) continue;
+            if (nout < kcap) { items[(col * kcap + nout) * 2] = (uint32_t)(E - target); items[(col * kcap + nout) * 2 + 1] = T.st.getR(i); }
+            ++nout;
+        }
+        if (nout > kcap) { S->overflow++; nout = kcap; }
+        cnt[col] = (uint32_t)nout;
+    }
+    return 0;
+}
+
+extern "C" int spm_sweep(void *handle, int n_lo, const uint32_t *const *lo_cnt, const uint32_t *const *lo_items, int n_hi,
+                         const uint32_t *const *hi_cnt, const uint32_t *const *hi_items, int kcap, uint32_t *out_rsq) {
+    SpmSession *S = (SpmSession *)handle;
+    const size_t wh = (size_t)S->w * S->h;
+    static SepStair<SepStairLocal<CAP> > T;
+    for (size_t col = 0; col < wh; ++col) {
+        for (int dir = +1; dir >= -1; dir -= 2) {
+            T.clear();
+            for (int step = 0; step < S->d; ++step) {
+                const int z = dir > 0 ? step : S->d - 1 - step;
+                const int u = dir > 0 ? z : -z;
+                const size_t v = (size_t)z * wh + col;
+                spm_arrivals(S, T, v, u, &S->overflow);
+                for (int side = 0; side < 2; ++side) {
+                    if (z != (side ? S->d - 1 : 0)) continue;
+                    const int ns = side ? n_hi : n_lo;
+                    for (int src = 0; src < ns; ++src) {
+                        const uint32_t c = (side ? hi_cnt : lo_cnt)[src][col];
+                        const uint32_t *p = (side ? hi_items : lo_items)[src] + col * kcap * 2;
+                        int hint = 0;
+                        for (uint32_t k = 0; k < c; ++k)
+                            if (!T.arrive(u, p[2 * k], p[2 * k + 1], hint)) S->overflow++;
+                    }
+                }
+                const uint32_t r = T.query(u);
+                if (dir > 0) out_rsq[v] = r;
+                else if (r > out_rsq[v]) out_rsq[v] = r;
+            }
+        }
+    }
+    return 0;
+}
+
+extern "C" long spm_close(void *handle) {
+    SpmSession *S = (SpmSession *)handle;
+    const long ovf = S->overflow;
+    delete S->l2f; delete S->l2b; delete S;
+    return ovf;
+}

@@ -61,6 +61,41 @@ class OracleStages:
         _, rsq = lt_oracle.paint(np.sqrt(rg.astype(np.float64)).astype(np.float32), nthreads=2)
         return torch.from_numpy(rsq.astype(np.int32))
 
+    # the painter in steps, on the CPU model of the separable painter (same calls and buffer layout as the
+    # CUDA library's bjt_dev_paint_open .. _close)
+    def paint_open(self, ridge_own, max_rsq):
+        self._ses = lt_oracle.SepPaintSession(_np(ridge_own).astype(np.uint32))
+        self._out = None
+        return 1
+
+    def paint_xslab_cols(self, xs):
+        return self._ses.w * self._ses.h
+
+    def paint_lists(self, xs):
+        pass
+
+    def boundary_buffer(self, ncol, kcap):
+        return torch.zeros(ncol * (2 * kcap + 1), dtype=torch.int32)
+
+    @staticmethod
+    def _split(buf, ncol, kcap):
+        a = _np(buf).view(np.uint32)
+        return a[2 * ncol * kcap:], a[:2 * ncol * kcap]
+
+    def paint_export(self, xs, side, gap, nplanes, buf, ncol, kcap):
+        cnt, items = self._ses.export(side, gap, nplanes, kcap)
+        c, it = self._split(buf, ncol, kcap)
+        c[:] = cnt
+        it[:] = items.reshape(-1)
+
+    def paint_sweep(self, xs, lo, hi, ncol, kcap):
+        conv = lambda bufs: [tuple(np.ascontiguousarray(x) for x in self._split(b, ncol, kcap)) for b in bufs]
+        self._out = self._ses.sweep(conv(lo), conv(hi), kcap)
+
+    def paint_close(self):
+        flags = self._ses.close()
+        return torch.from_numpy(self._out.astype(np.int32)), int(flags != 0)
+
     def full(self, shape, value):
         return torch.full(shape, value, dtype=torch.int32)
 

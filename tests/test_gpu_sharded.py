@@ -75,3 +75,64 @@ def test_two_ranks_nccl_bitwise(oracle, tmp_path, inverse):
     assert np.array_equal(np.nan_to_num(got, nan=-1.0), np.nan_to_num(one, nan=-1.0)), "2-GPU map != 1-GPU map"
     st = np.load(os.path.join(tmp_path, "stats.npy"))
     assert int(st[0]) == st1.count and abs(st[1] - st1.mean) <= 1e-9 * abs(st1.mean)
+
+
+@pytest.mark.parametrize("shape,cuts,seed", [((48, 40, 44), [0, 13, 30, 48], 4),          # three slabs
+                                              ((20, 24, 600), [0, 4, 9, 14, 20], 6)])     # two x-slabs, thin z-slabs
+@pytest.mark.parametrize("inverse", [False, True])
+def test_stepwise_painter_slabs_one_gpu(oracle, shape, cuts, seed, inverse):
+    """The painter in steps (bjt_dev_paint_open .. _close) on z-slabs of one volume, all on this GPU, one
+    context per slab, boundary staircases handed over in device memory: the slabs' painted r^2 must equal
+    the oracle's on the whole volume, bitwise.  Covers export / import kernels without NCCL."""
+    import math
+    from bonej2_b200 import _native, sharded
+    vol = shapes.random_blobs(shape, seed)
+    dist_, sq = oracle.edt(vol, inverse=inverse)
+    rg = oracle.ridge(dist_)
+    _, want = oracle.paint(rg)
+    ridge = np.where(rg > 0, sq, 0).astype(np.int32)
+    gmax = int(ridge.max())
+    rmax = math.isqrt(gmax)
+    d, h, w = shape
+    dev = torch.device("cuda", 0)
+    zs = list(zip(cuts[:-1], cuts[1:]))
+    K = sharded.BOUNDARY_KCAP
+    ctxs = [_native.Context(0) for _ in zs]
+    try:
+        st = []
+        for c, (a, b) in zip(ctxs, zs):
+            c.set_stream(torch.cuda.current_stream().cuda_stream)
+            s = sharded.CudaStages(c, dev)
+            s.nxs = s.paint_open(torch.from_numpy(ridge[a:b].copy()).to(dev), gmax)
+            st.append(s)
+        nxs = st[0].nxs
+        assert nxs == (w + 511) // 512
+
+        def gap(p, q):
+            g = zs[q][0] - (zs[p][1] - 1) if q > p else zs[p][0] - (zs[q][1] - 1)
+            return g if g <= rmax else 0
+
+        for xs in range(nxs):
+            ncol = st[0].paint_xslab_cols(xs)
+            for s in st:
+                s.paint_lists(xs)
+            box = {}
+            for p, s in enumerate(st):
+                for q in range(len(st)):
+                    if q != p and gap(p, q):
+                        box[(p, q)] = s.boundary_buffer(ncol, K)
+                        s.paint_export(xs, +1 if q > p else -1, gap(p, q), rmax + 1, box[(p, q)], ncol, K)
+            for q, s in enumerate(st):
+                lo = [box[(p, q)] for p in range(q) if (p, q) in box]
+                hi = [box[(p, q)] for p in range(q + 1, len(st)) if (p, q) in box]
+                assert len(lo) <= sharded.MAX_SOURCES and len(hi) <= sharded.MAX_SOURCES
+                s.paint_sweep(xs, lo, hi, ncol, K)
+        got = []
+        for s in st:
+            out, flags = s.paint_close()
+            assert flags == 0
+            got.append(out.cpu().numpy())
+        assert np.array_equal(np.concatenate(got).astype(np.uint32), want)
+    finally:
+        for c in ctxs:
+            c.close()

@@ -26,7 +26,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, vol_path, out_dir, inverse, mask):
+def _worker(rank, world, port, vol_path, out_dir, inverse, mask, paint_mode):
     sys.path.insert(0, ROOT)
     from bonej2_b200 import sharded
     from tests.sharded_cpu_backend import OracleStages
@@ -36,25 +36,25 @@ def _worker(rank, world, port, vol_path, out_dir, inverse, mask):
     zs = sharded.split_ranges(d, world)
     slab = torch.from_numpy(vol[zs[rank][0]:zs[rank][1]].copy())
     comm = sharded.Comm()
-    out, stats = sharded.thickness_slab(OracleStages(), comm, slab, (w, h, d), inverse, mask, 0.5)
+    out, stats = sharded.thickness_slab(OracleStages(), comm, slab, (w, h, d), inverse, mask, 0.5, paint_mode=paint_mode)
     np.save(os.path.join(out_dir, f"map_{rank}.npy"), out.numpy())
     if rank == 0:
         np.save(os.path.join(out_dir, "stats.npy"), np.array([stats["count"], stats["mean"], stats["sd"], stats["min"], stats["max"]]))
     dist.destroy_process_group()
 
 
-def _run(vol, inverse, mask, tmp_path, world=2):
+def _run(vol, inverse, mask, tmp_path, world=2, paint_mode="exchange"):
     vol_path = os.path.join(tmp_path, "vol.npy")
     np.save(vol_path, vol)
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, vol_path, str(tmp_path), inverse, mask), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, vol_path, str(tmp_path), inverse, mask, paint_mode), nprocs=world, join=True)
     maps = [np.load(os.path.join(tmp_path, f"map_{r}.npy")) for r in range(world)]
     return np.concatenate(maps, axis=0), np.load(os.path.join(tmp_path, "stats.npy"))
 
 
-def _check(vol, inverse, mask, tmp_path, world=2):
+def _check(vol, inverse, mask, tmp_path, world=2, paint_mode="exchange"):
     from oracle import lt_oracle
-    got, st = _run(vol, inverse, mask, tmp_path, world)
+    got, st = _run(vol, inverse, mask, tmp_path, world, paint_mode)
     ref = lt_oracle.process_image(vol, inverse=inverse, mask=mask, pixel_width=0.5)
     assert np.array_equal(np.isnan(got), np.isnan(ref["map"]))
     ok = ~np.isnan(got)
@@ -66,10 +66,25 @@ def _check(vol, inverse, mask, tmp_path, world=2):
         assert st[4] == ref["stats"].max
 
 
+@pytest.mark.parametrize("paint_mode", ["exchange", "halo"])
 @pytest.mark.parametrize("inverse", [False, True])
-def test_two_ranks_blobs(tmp_path, inverse):
+def test_two_ranks_blobs(tmp_path, inverse, paint_mode):
     from tests import shapes
-    _check(shapes.random_blobs((17, 14, 19), 3), inverse, True, str(tmp_path))
+    _check(shapes.random_blobs((17, 14, 19), 3), inverse, True, str(tmp_path), paint_mode=paint_mode)
+
+
+def test_four_ranks_thin_slabs_exchange(tmp_path):
+    """slabs thinner than the largest ball: staircases cross more than one slab face (several sources per side)"""
+    vol = np.zeros((16, 14, 14), np.uint8)
+    vol[1:15, 1:13, 1:13] = 255                                         # r_max = 6 > slab thickness 4
+    vol[7, 6, 6] = 0
+    _check(vol, False, True, str(tmp_path), world=4, paint_mode="exchange")
+
+
+def test_empty_slabs_exchange(tmp_path):
+    """more ranks than planes: ranks with no plane take part in the collectives only"""
+    from tests import shapes
+    _check(shapes.random_blobs((3, 9, 8), 2), True, False, str(tmp_path), world=4, paint_mode="exchange")
 
 
 def test_two_ranks_big_radius_halo_clipped(tmp_path):
@@ -77,7 +92,8 @@ def test_two_ranks_big_radius_halo_clipped(tmp_path):
     vol = np.zeros((12, 10, 10), np.uint8)
     vol[:, 1:9, 1:9] = 255
     vol[0] = 0
-    _check(vol, False, False, str(tmp_path))
+    _check(vol, False, False, str(tmp_path), paint_mode="halo")
+    _check(vol, False, False, str(tmp_path), paint_mode="exchange")
 
 
 def test_two_ranks_no_background(tmp_path):
