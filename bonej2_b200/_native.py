@@ -86,6 +86,7 @@ _SIGS = {
     "bjt_dev_paint_close": ([_VP, _VP], _I),
     "bjt_debug_set_paint_limits": ([_VP, _I, _I], _I),
     "bjt_debug_paint_redo_lines": ([_VP], C.c_int64),
+    "bjt_debug_set_xslab_cols": ([_I], _I),
     "bjt_host_alloc": ([C.c_size_t], _VP),
     "bjt_host_free": ([_VP], None),
     "bjt_thickness_u8": ([_VP, _VP, _I, _I, _I, _I, _I, _I, _D, _VP, C.POINTER(Stats), C.POINTER(Timing)], _I),
@@ -207,6 +208,11 @@ class Context:
 
     def debug_set_paint_limits(self, active_cap=0, front_cap=0):
         self._ck(lib().bjt_debug_set_paint_limits(self._h, int(active_cap), int(front_cap)))
+
+    @staticmethod
+    def debug_set_xslab_cols(cols=0):
+        if lib().bjt_debug_set_xslab_cols(int(cols)) != 0:
+            raise ValueError("x-slab width must be a non-negative multiple of 32")
 
     def debug_paint_redo_lines(self) -> int:
         return int(lib().bjt_debug_paint_redo_lines(self._h))

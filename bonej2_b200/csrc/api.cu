@@ -174,6 +174,12 @@ int bjt_debug_set_paint_limits(bjt_ctx *c, int active_cap, int front_cap) {
     return BJT_OK;
 }
 
+int bjt_debug_set_xslab_cols(int cols) {
+    if (cols < 0 || (cols % 32) != 0) return BJT_E_ARG;
+    paint_sep_set_xslab_cols(cols);
+    return BJT_OK;
+}
+
 int64_t bjt_debug_paint_redo_lines(bjt_ctx *c) {
     if (!c) return -1;
     std::lock_guard<std::mutex> lk(c->mu);
@@ -693,19 +699,19 @@ int bjt_dev_paint_open(bjt_ctx *c, const uint32_t *d_ridge, int w, int h, int d,
     return BJT_OK;
 }
 
-int bjt_dev_paint_nxslabs(bjt_ctx *c) { return c && c->ps.open ? paint_sep_nxslabs(c->ps.w) : 0; }
-int bjt_dev_paint_xslab_width(bjt_ctx *c, int xs) { return c && c->ps.open ? paint_sep_xslab_width(c->ps.w, xs) : 0; }
+int bjt_dev_paint_nxslabs(bjt_ctx *c) { return c && c->ps.open ? paint_sep_nxslabs(c->ps.w, c->ps.h, c->ps.d) : 0; }
+int bjt_dev_paint_xslab_width(bjt_ctx *c, int xs) { return c && c->ps.open ? paint_sep_xslab_width(c->ps.w, c->ps.h, c->ps.d, xs) : 0; }
 
 int bjt_dev_paint_lists(bjt_ctx *c, int xs) {
     ENTER(c);
-    if (!c->ps.open || xs < 0 || xs >= paint_sep_nxslabs(c->ps.w)) return fail(c, BJT_E_ARG, "paint_lists: no open painter or bad x-slab");
+    if (!c->ps.open || xs < 0 || xs >= paint_sep_nxslabs(c->ps.w, c->ps.h, c->ps.d)) return fail(c, BJT_E_ARG, "paint_lists: no open painter or bad x-slab");
     c->launches += paint_sep_stage2(c->ps.w, c->ps.h, c->ps.d, c->ps.variant, c->ps.ws, xs, c->ps.flags, c->stream); CKL();
     return BJT_OK;
 }
 
 int bjt_dev_paint_export(bjt_ctx *c, int xs, int side, int gap, int nplanes, uint32_t *d_count, void *d_items, int kcap) {
     ENTER(c);
-    if (!c->ps.open || xs < 0 || xs >= paint_sep_nxslabs(c->ps.w)) return fail(c, BJT_E_ARG, "paint_export: no open painter or bad x-slab");
+    if (!c->ps.open || xs < 0 || xs >= paint_sep_nxslabs(c->ps.w, c->ps.h, c->ps.d)) return fail(c, BJT_E_ARG, "paint_export: no open painter or bad x-slab");
     if ((side != 1 && side != -1) || gap < 1 || nplanes < 1 || kcap < 1 || !d_count || !d_items)
         return fail(c, BJT_E_ARG, "paint_export: bad side / gap / planes / capacity");
     c->launches += paint_sep_export(c->ps.w, c->ps.h, c->ps.d, c->ps.variant, c->ps.ws, xs, side, gap, nplanes, d_count,
@@ -716,7 +722,7 @@ int bjt_dev_paint_export(bjt_ctx *c, int xs, int side, int gap, int nplanes, uin
 int bjt_dev_paint_sweep(bjt_ctx *c, int xs, int n_lo, const uint32_t *const *lo_count, const void *const *lo_items, int n_hi,
                         const uint32_t *const *hi_count, const void *const *hi_items, int kcap, uint32_t *d_rsq) {
     ENTER(c);
-    if (!c->ps.open || xs < 0 || xs >= paint_sep_nxslabs(c->ps.w)) return fail(c, BJT_E_ARG, "paint_sweep: no open painter or bad x-slab");
+    if (!c->ps.open || xs < 0 || xs >= paint_sep_nxslabs(c->ps.w, c->ps.h, c->ps.d)) return fail(c, BJT_E_ARG, "paint_sweep: no open painter or bad x-slab");
     if (n_lo < 0 || n_hi < 0 || n_lo > SEP_MAX_SOURCES || n_hi > SEP_MAX_SOURCES || !d_rsq)
         return fail(c, BJT_E_ARG, "paint_sweep: at most %d sources per side", SEP_MAX_SOURCES);
     SepImports imp{};

@@ -62,6 +62,7 @@ int launch_fill_u32(uint32_t *p, size_t n, uint32_t v, cudaStream_t s);
 // separable paint (paths 0/1), see paint_sep.cu
 size_t paint_sep_workspace_bytes(int w, int h, int d, int wide);
 void paint_sep_set_limits(int cap, int fmax);          // test hook: 0 = default
+void paint_sep_set_xslab_cols(int cols);               // test hook: 0 = default (process-wide)
 unsigned long long paint_sep_redo_lines(const void *workspace);
 int launch_paint_sep(const uint32_t *ridge, int w, int h, int d, int wide, void *workspace, uint32_t *rsq,
                      uint32_t *overflow_flag, cudaStream_t s);
@@ -76,8 +77,8 @@ struct SepImports {
     const uint32_t *lo_cnt[SEP_MAX_SOURCES]; const uint2 *lo_items[SEP_MAX_SOURCES];
     const uint32_t *hi_cnt[SEP_MAX_SOURCES]; const uint2 *hi_items[SEP_MAX_SOURCES];
 };
-int paint_sep_nxslabs(int w);
-int paint_sep_xslab_width(int w, int xs);
+int paint_sep_nxslabs(int w, int h, int d);
+int paint_sep_xslab_width(int w, int h, int d, int xs);
 int paint_sep_stage1(const uint32_t *ridge, int w, int h, int d, int variant, void *workspace, uint32_t *flags, cudaStream_t s);
 int paint_sep_stage2(int w, int h, int d, int variant, void *workspace, int xs, uint32_t *flags, cudaStream_t s);
 // side +1: items of the last `hh` planes that reach plane d - 1 + gap or beyond; side -1: items of the first

@@ -13,7 +13,7 @@
 // are neighbours in the pool.  Forward and backward fronts are kept as two lists; the next stage
 // reads both.
 //   stage 1  lines along x (thread per row), whole volume            ridge -> L1F, L1B
-//   stage 2  lines along y, lanes along x, per x-slab of XC columns   L1  -> L2F, L2B (slab-local)
+//   stage 2  lines along y, lanes along x, per x-slab of columns     L1  -> L2F, L2B (slab-local)
 //   stage 3  lines along z, lanes along x, same slab                  L2  -> painted r^2 (coalesced)
 // Items are (slack, R).  PACKED: u32 = R << 16 | slack when the largest r^2 is below 65536;
 // otherwise u64.
@@ -32,7 +32,18 @@ namespace bjt {
 
 namespace {
 
-constexpr int XC = 512;                 // x-slab width of stages 2 and 3
+// x-slab width of stages 2 and 3: as many columns as keep a slab at or below 2^29 voxels (the item pool of
+// stage 2 is sized per slab voxel), at least 512 -- thin z-slabs of a sharded run get the whole width, which
+// keeps the y-stage grid (columns x planes lines) large enough to fill the GPU
+int g_xslab_override = 0;               // test hook (paint_sep_set_xslab_cols)
+inline int xslab_cols(int w, int h, int d) {
+    if (g_xslab_override > 0) return g_xslab_override < w ? g_xslab_override : w;
+    const long long per_col = (long long)h * d;
+    long long xc = (1ll << 29) / (per_col > 0 ? per_col : 1);
+    xc = xc / 128 * 128;
+    if (xc < 512) xc = 512;
+    return xc < w ? (int)xc : w;
+}
 constexpr unsigned long long OFF_MASK = (1ull << 40) - 1ull;
 constexpr int TPB = 128;                // threads per block of the line kernels
 constexpr int S_SM = 12;                // entries per buffer kept in shared memory (PACKED kernels)
@@ -366,6 +377,7 @@ __global__ void __launch_bounds__(TPB) sep_export_kernel(SepArgs a, int side, in
     S.clear();
     bool ok = true;
     const int nplanes = hh < a.d ? hh : a.d;
+    const int target = (side > 0 ? a.d - 1 : 0) + gap;
     for (int step = 0; step < nplanes; ++step) {
         const int z = side > 0 ? a.d - nplanes + step : nplanes - 1 - step;
         const int u = side > 0 ? z : -z;
@@ -379,12 +391,11 @@ __global__ void __launch_bounds__(TPB) sep_export_kernel(SepArgs a, int side, in
             int hint = 0;
             for (int k = 0; k < c; ++k) {
                 const SepItem it = IO::get(p, k);
+                if (u + (int)it.rho < target) continue;                     // does not reach the receiver
                 ok &= S.arrive(u, it.rho, it.R, hint);
             }
         }
-        S.query(u);
     }
-    const int target = (side > 0 ? a.d - 1 : 0) + gap;
     int nout = 0;
     for (int i = 0; i < S.n; ++i) {
         const int E = S.st.getE(i);
@@ -406,7 +417,7 @@ struct Plan {
 Plan make_plan(int w, int h, int d, int wide, int scale) {
     Plan p;
     p.n = (size_t)w * h * d;
-    const int xw = w < XC ? w : XC;
+    const int xw = xslab_cols(w, h, d);
     p.nslab = (size_t)xw * h * d;
     const size_t l1 = (size_t)h * d, l2 = (size_t)xw * d, l3 = (size_t)xw * h;
     p.maxlines = l1 > l2 ? (l1 > l3 ? l1 : l3) : (l2 > l3 ? l2 : l3);
@@ -481,6 +492,7 @@ template <bool PACKED>
 int run_stage2(int w, int h, int d, const Plan &p, char *ws, int xc0, uint32_t *flags, cudaStream_t s) {
     Bufs b = make_bufs(w, h, d, p, ws, flags);
     int launches = 0;
+    const int XC = xslab_cols(w, h, d);
     const int xw = (w - xc0) < XC ? (w - xc0) : XC;
     cudaMemsetAsync(b.counters + 1, 0, 8, s);
     for (int dir = +1; dir >= -1; dir -= 2) {
@@ -509,6 +521,7 @@ int run_stage3(int w, int h, int d, const Plan &p, char *ws, int xc0, const SepI
                cudaStream_t s) {
     Bufs b = make_bufs(w, h, d, p, ws, flags);
     int launches = 0;
+    const int XC = xslab_cols(w, h, d);
     const int xw = (w - xc0) < XC ? (w - xc0) : XC;
     for (int dir = +1; dir >= -1; dir -= 2) {
         SepArgs a = b.base;
@@ -528,6 +541,7 @@ template <bool PACKED>
 int run_export(int w, int h, int d, const Plan &p, char *ws, int xc0, int side, int gap, int hh, uint32_t *cnt, uint2 *items,
                int kcap, uint32_t *flags, cudaStream_t s) {
     Bufs b = make_bufs(w, h, d, p, ws, flags);
+    const int XC = xslab_cols(w, h, d);
     const int xw = (w - xc0) < XC ? (w - xc0) : XC;
     SepArgs a = b.base;
     a.inF = b.idx2f; a.inB = b.idx2b; a.in_pool = b.pool2; a.xc0 = xc0; a.xw = xw; a.dir = side;
@@ -540,6 +554,7 @@ template <bool PACKED>
 int run_sep(const uint32_t *ridge, int w, int h, int d, const Plan &p, char *ws, uint32_t *rsq, uint32_t *flags,
             cudaStream_t s) {
     int launches = run_stage1<PACKED>(ridge, w, h, d, p, ws, flags, s);
+    const int XC = xslab_cols(w, h, d);
     for (int xc0 = 0; xc0 < w; xc0 += XC) {
         launches += run_stage2<PACKED>(w, h, d, p, ws, xc0, flags, s);
         launches += run_stage3<PACKED>(w, h, d, p, ws, xc0, nullptr, rsq, flags, s);
@@ -548,6 +563,8 @@ int run_sep(const uint32_t *ridge, int w, int h, int d, const Plan &p, char *ws,
 }
 
 }  // namespace
+
+void paint_sep_set_xslab_cols(int cols) { g_xslab_override = cols; }
 
 void paint_sep_set_limits(int cap, int fmax) {
     const int c = cap > 0 ? cap : 1 << 30, f = fmax > 0 ? fmax : 1 << 30;
@@ -567,8 +584,11 @@ size_t paint_sep_workspace_bytes(int w, int h, int d, int variant) {
     return make_plan(w, h, d, variant & 1, (variant & 2) ? 2 : 1).total;
 }
 
-int paint_sep_nxslabs(int w) { return (w + XC - 1) / XC; }
-int paint_sep_xslab_width(int w, int xs) { const int xc0 = xs * XC; return (w - xc0) < XC ? (w - xc0) : XC; }
+int paint_sep_nxslabs(int w, int h, int d) { const int XC = xslab_cols(w, h, d); return (w + XC - 1) / XC; }
+int paint_sep_xslab_width(int w, int h, int d, int xs) {
+    const int XC = xslab_cols(w, h, d), xc0 = xs * XC;
+    return (w - xc0) < XC ? (w - xc0) : XC;
+}
 
 int paint_sep_stage1(const uint32_t *ridge, int w, int h, int d, int variant, void *workspace, uint32_t *flags, cudaStream_t s) {
     const Plan p = make_plan(w, h, d, variant & 1, (variant & 2) ? 2 : 1);
@@ -578,21 +598,21 @@ int paint_sep_stage1(const uint32_t *ridge, int w, int h, int d, int variant, vo
 int paint_sep_stage2(int w, int h, int d, int variant, void *workspace, int xs, uint32_t *flags, cudaStream_t s) {
     const Plan p = make_plan(w, h, d, variant & 1, (variant & 2) ? 2 : 1);
     char *ws = reinterpret_cast<char *>(workspace);
-    return (variant & 1) ? run_stage2<false>(w, h, d, p, ws, xs * XC, flags, s) : run_stage2<true>(w, h, d, p, ws, xs * XC, flags, s);
+    return (variant & 1) ? run_stage2<false>(w, h, d, p, ws, xs * xslab_cols(w, h, d), flags, s) : run_stage2<true>(w, h, d, p, ws, xs * xslab_cols(w, h, d), flags, s);
 }
 int paint_sep_export(int w, int h, int d, int variant, void *workspace, int xs, int side, int gap, int hh, uint32_t *cnt,
                      uint2 *items, int kcap, uint32_t *flags, cudaStream_t s) {
     const Plan p = make_plan(w, h, d, variant & 1, (variant & 2) ? 2 : 1);
     char *ws = reinterpret_cast<char *>(workspace);
-    return (variant & 1) ? run_export<false>(w, h, d, p, ws, xs * XC, side, gap, hh, cnt, items, kcap, flags, s)
-                         : run_export<true>(w, h, d, p, ws, xs * XC, side, gap, hh, cnt, items, kcap, flags, s);
+    return (variant & 1) ? run_export<false>(w, h, d, p, ws, xs * xslab_cols(w, h, d), side, gap, hh, cnt, items, kcap, flags, s)
+                         : run_export<true>(w, h, d, p, ws, xs * xslab_cols(w, h, d), side, gap, hh, cnt, items, kcap, flags, s);
 }
 int paint_sep_stage3(int w, int h, int d, int variant, void *workspace, int xs, const SepImports *imp, uint32_t *rsq,
                      uint32_t *flags, cudaStream_t s) {
     const Plan p = make_plan(w, h, d, variant & 1, (variant & 2) ? 2 : 1);
     char *ws = reinterpret_cast<char *>(workspace);
-    return (variant & 1) ? run_stage3<false>(w, h, d, p, ws, xs * XC, imp, rsq, flags, s)
-                         : run_stage3<true>(w, h, d, p, ws, xs * XC, imp, rsq, flags, s);
+    return (variant & 1) ? run_stage3<false>(w, h, d, p, ws, xs * xslab_cols(w, h, d), imp, rsq, flags, s)
+                         : run_stage3<true>(w, h, d, p, ws, xs * xslab_cols(w, h, d), imp, rsq, flags, s);
 }
 
 int launch_paint_sep(const uint32_t *ridge, int w, int h, int d, int variant, void *workspace, uint32_t *rsq,

@@ -66,6 +66,8 @@ int64_t bjt_launch_count(const bjt_ctx *ctx);
 /* test hook: cap the fast painter kernels' per-line capacities (0 = default) so that small volumes exercise
  * the redo kernels; results must not change */
 int  bjt_debug_set_paint_limits(bjt_ctx *ctx, int active_cap, int front_cap);
+/* test hook, process-wide: width of the painter's column blocks (multiple of 32; 0 = default) */
+int  bjt_debug_set_xslab_cols(int cols);
 /* lines the last separable paint of this context sent to its redo kernels */
 int64_t bjt_debug_paint_redo_lines(bjt_ctx *ctx);
 /* page-locked host memory (what a JNI direct ByteBuffer / the bench wraps so copies are DMA) */

@@ -77,10 +77,10 @@ def test_two_ranks_nccl_bitwise(oracle, tmp_path, inverse):
     assert int(st[0]) == st1.count and abs(st[1] - st1.mean) <= 1e-9 * abs(st1.mean)
 
 
-@pytest.mark.parametrize("shape,cuts,seed", [((48, 40, 44), [0, 13, 30, 48], 4),          # three slabs
-                                              ((20, 24, 600), [0, 4, 9, 14, 20], 6)])     # two x-slabs, thin z-slabs
+@pytest.mark.parametrize("shape,cuts,seed,xcols", [((48, 40, 44), [0, 13, 30, 48], 4, 0),       # three slabs
+                                                    ((20, 24, 200), [0, 4, 9, 14, 20], 6, 64)])  # four column blocks, thin z-slabs
 @pytest.mark.parametrize("inverse", [False, True])
-def test_stepwise_painter_slabs_one_gpu(oracle, shape, cuts, seed, inverse):
+def test_stepwise_painter_slabs_one_gpu(oracle, shape, cuts, seed, xcols, inverse):
     """The painter in steps (bjt_dev_paint_open .. _close) on z-slabs of one volume, all on this GPU, one
     context per slab, boundary staircases handed over in device memory: the slabs' painted r^2 must equal
     the oracle's on the whole volume, bitwise.  Covers export / import kernels without NCCL."""
@@ -98,6 +98,7 @@ def test_stepwise_painter_slabs_one_gpu(oracle, shape, cuts, seed, inverse):
     zs = list(zip(cuts[:-1], cuts[1:]))
     K = sharded.BOUNDARY_KCAP
     ctxs = [_native.Context(0) for _ in zs]
+    _native.Context.debug_set_xslab_cols(xcols)
     try:
         st = []
         for c, (a, b) in zip(ctxs, zs):
@@ -106,7 +107,7 @@ def test_stepwise_painter_slabs_one_gpu(oracle, shape, cuts, seed, inverse):
             s.nxs = s.paint_open(torch.from_numpy(ridge[a:b].copy()).to(dev), gmax)
             st.append(s)
         nxs = st[0].nxs
-        assert nxs == (w + 511) // 512
+        assert nxs == ((w + xcols - 1) // xcols if xcols else 1)
 
         def gap(p, q):
             g = zs[q][0] - (zs[p][1] - 1) if q > p else zs[p][0] - (zs[q][1] - 1)
@@ -134,5 +135,6 @@ def test_stepwise_painter_slabs_one_gpu(oracle, shape, cuts, seed, inverse):
             got.append(out.cpu().numpy())
         assert np.array_equal(np.concatenate(got).astype(np.uint32), want)
     finally:
+        _native.Context.debug_set_xslab_cols(0)
         for c in ctxs:
             c.close()
