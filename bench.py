@@ -111,7 +111,7 @@ def run_reference(args, rank, world):
     sample = f"{n_sample}^3 phantom (same recipe, seed {SEED}), Both, mask on; whole pipeline incl. brute-force paint"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u32/f32", "data": "synthetic",
         "config": {"workload": f"BoneJ Thickness Tb.Th+Tb.Sp, mask on, {args.size}^3 synthetic trabecular phantom",
                    "timed_sample": sample},
@@ -119,10 +119,28 @@ def run_reference(args, rank, world):
                          "note": "CPU restatement of sc.fiji LocalThickness_ (no JVM in image)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the one JSON line, on the process's original stdout"""
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    # libraries print to stdout as they please (NCCL announces its version there); the contract is ONE JSON
+    # line, so everything else that reaches fd 1 is sent to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -161,12 +179,16 @@ def main():
 
     if world > 1:
         from bonej2_b200 import sharded
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         result = sharded.bench(args, rank, world, local_rank, dist)
+        clocks = sampler.stop()
         if rank == 0:
+            result["clocks"] = clocks
             result["roofline"]["peak"] = hbm_peak
             result["roofline"]["frac"] = result["roofline"]["achieved"] / hbm_peak
             result["roofline"]["peak_kind"] = peak_kind
-            print(json.dumps(result), flush=True)
+            emit(result)
         dist.destroy_process_group()
         return
 
@@ -275,7 +297,7 @@ def main():
 
     line = {
         "metric": METRIC, "value": N / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32/f32", "data": "synthetic",
         "config": {"workload": f"BoneJ Thickness Tb.Th+Tb.Sp (mapChoice Both), mask on, {n}^3 synthetic trabecular phantom "
                                f"(BASELINE.json configs[2] at 1 GPU)", "volume": [n, n, n], "bv_tv": round(bvtv, 4),
@@ -288,7 +310,7 @@ def main():
         "results": {"tb_th": {k: stats_dev[0][k] for k in ("count", "mean", "sd", "max")},
                     "tb_sp": {k: stats_dev[1][k] for k in ("count", "mean", "sd", "max")}},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == "__main__":
