@@ -161,3 +161,12 @@ def test_painter_redo_kernels(ctx, oracle, caps):
                 assert ctx.debug_paint_redo_lines() > 50
     finally:
         ctx.debug_set_paint_limits(0, 0)
+
+
+@pytest.mark.parametrize("shape", [(40, 36, 48), (33, 47, 64), (70, 35, 32), (128, 96, 64), (16, 200, 16)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_edt_odd_line_lengths(ctx, oracle, shape, inverse):
+    """squared EDT, bit for bit, on line lengths that are not multiples of the kernels' tile sizes"""
+    vol = shapes.random_blobs(shape, 11)
+    _, want = oracle.edt(vol, inverse=inverse)
+    assert np.array_equal(ctx.edt_sq(vol, inverse=inverse), want)
