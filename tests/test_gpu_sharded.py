@@ -79,8 +79,8 @@ def test_two_ranks_nccl_bitwise(oracle, tmp_path, inverse):
 
 @pytest.mark.parametrize("shape,cuts,seed,xcols", [((48, 40, 44), [0, 13, 30, 48], 4, 0),       # three slabs
                                                     ((20, 24, 200), [0, 4, 9, 14, 20], 6, 64)])  # four column blocks, thin z-slabs
-@pytest.mark.parametrize("inverse", [False, True])
-def test_stepwise_painter_slabs_one_gpu(oracle, shape, cuts, seed, xcols, inverse):
+@pytest.mark.parametrize("inverse,wide", [(False, False), (True, False), (True, True)])
+def test_stepwise_painter_slabs_one_gpu(oracle, shape, cuts, seed, xcols, inverse, wide):
     """The painter in steps (bjt_dev_paint_open .. _close) on z-slabs of one volume, all on this GPU, one
     context per slab, boundary staircases handed over in device memory: the slabs' painted r^2 must equal
     the oracle's on the whole volume, bitwise.  Covers export / import kernels without NCCL."""
@@ -93,6 +93,7 @@ def test_stepwise_painter_slabs_one_gpu(oracle, shape, cuts, seed, xcols, invers
     ridge = np.where(rg > 0, sq, 0).astype(np.int32)
     gmax = int(ridge.max())
     rmax = math.isqrt(gmax)
+    tag_bound = max(gmax, 70000) if wide else gmax              # a looser bound is legal and selects the u64-item kernels
     d, h, w = shape
     dev = torch.device("cuda", 0)
     zs = list(zip(cuts[:-1], cuts[1:]))
@@ -104,7 +105,7 @@ def test_stepwise_painter_slabs_one_gpu(oracle, shape, cuts, seed, xcols, invers
         for c, (a, b) in zip(ctxs, zs):
             c.set_stream(torch.cuda.current_stream().cuda_stream)
             s = sharded.CudaStages(c, dev)
-            s.nxs = s.paint_open(torch.from_numpy(ridge[a:b].copy()).to(dev), gmax)
+            s.nxs = s.paint_open(torch.from_numpy(ridge[a:b].copy()).to(dev), tag_bound)
             st.append(s)
         nxs = st[0].nxs
         assert nxs == ((w + xcols - 1) // xcols if xcols else 1)
