@@ -275,7 +275,7 @@ BOUNDARY_KCAP = 32          # staircase steps per column a slab face can carry (
 MAX_SOURCES = 4             # slabs per side a sweep can import from (bjt_dev_paint_sweep)
 
 
-def paint_exchange(stages, comm: Comm, ridge_own, zs, gmax, kcap=BOUNDARY_KCAP):
+def paint_exchange(stages, comm: Comm, ridge_own, zs, gmax, kcap=BOUNDARY_KCAP, timings=None):
     """Painted r^2 of this rank's own planes: plane-local x / y stages, boundary staircases exchanged with the
     slabs within reach, z sweeps.  Returns None (on every rank alike) when the stepwise painter cannot take
     the case -- too many slabs within reach or a capacity exceeded -- and the caller repaints slab + halo."""
@@ -298,11 +298,23 @@ def paint_exchange(stages, comm: Comm, ridge_own, zs, gmax, kcap=BOUNDARY_KCAP):
         return None
     flags = 0
     out = None
+    t_ = time.perf_counter
+
+    def mark(name, t0):
+        if timings is not None:
+            if str(getattr(stages, "device", "cpu")).startswith("cuda"):
+                torch.cuda.synchronize()
+            timings[name] = timings.get(name, 0.0) + (t_() - t0)
+        return t_()
+
     if z1 > z0:
+        t0 = t_()
         nxs = stages.paint_open(ridge_own, gmax)
+        t0 = mark("paint.x_stage", t0)
         for xs in range(nxs):
             ncol = stages.paint_xslab_cols(xs)
             stages.paint_lists(xs)
+            t0 = mark("paint.y_stage", t0)
             sends, recvs, lo, hi = {}, {}, [], []
             for p in range(G):
                 if p == r:
@@ -315,8 +327,11 @@ def paint_exchange(stages, comm: Comm, ridge_own, zs, gmax, kcap=BOUNDARY_KCAP):
                 if within(p, r):                                          # what slab p carries across to me
                     recvs[p] = stages.boundary_buffer(ncol, kcap)
                     (lo if p < r else hi).append(recvs[p])
+            t0 = mark("paint.export", t0)
             comm.exchange(sends, recvs)
+            t0 = mark("paint.exchange", t0)
             stages.paint_sweep(xs, lo, hi, ncol, kcap)
+            t0 = mark("paint.z_stage", t0)
             del sends, recvs, lo, hi
         out, flags = stages.paint_close()
     flags = comm.allreduce_max_int(int(flags != 0), ridge_own.device)
@@ -375,7 +390,7 @@ def thickness_slab(stages, comm: Comm, slab_u8, dims, inverse, mask=True, pixel_
             ridge_own = stages.ridge(sq_ext)[z0 - needs[r][0]:z1 - needs[r][0]] if z1 > z0 else sq_ext
             del sq_ext
             mark("ridge", t0); t0 = t_()
-            rsq_own = paint_exchange(stages, comm, ridge_own, zs, gmax)
+            rsq_own = paint_exchange(stages, comm, ridge_own, zs, gmax, timings=timings)
             del ridge_own
             mark("paint", t0); t0 = t_()
             if rsq_own is not None:
