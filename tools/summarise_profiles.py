@@ -1,6 +1,6 @@
 """Turn the ncu outputs of tools/profile_round.sh into tracked summaries under profiles/.
 usage: python tools/summarise_profiles.py rNN"""
-import csv, json, os, shutil, subprocess, sys
+import csv, re, json, os, shutil, subprocess, sys
 R = sys.argv[1] if len(sys.argv) > 1 else "r01"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
@@ -18,6 +18,7 @@ for r in rows[hdr + 1:]:
     if len(r) <= iV or r[iM] != "gpu__time_duration.sum":
         continue
     k = r[iK].replace("bjt::", "").replace("<unnamed>::", "")
+    k = re.sub(r"\((bool|int)\)", "", k)                        # template arguments print as (int)-1
     k = k.split("(")[0]
     if k not in agg:
         agg[k] = [0, 0.0]; order.append(k)
