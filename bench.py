@@ -221,6 +221,7 @@ def main():
     stage_ms = {}
     launches = 0
     n_ridge = [0, 0]
+    y_sweeps = 0
     torch.cuda.synchronize()
     ev0.record(stream)
     for _ in range(args.steps):
@@ -229,8 +230,10 @@ def main():
             d = tm.as_dict()
             launches += d["n_launches"]
             n_ridge[k] = d["n_ridge"]
-            for key in ("ms_edt_x", "ms_edt_y", "ms_edt_z", "ms_ridge", "ms_paint", "ms_finish"):
+            for key in ("ms_edt_x", "ms_edt_y", "ms_edt_z", "ms_ridge", "ms_paint", "ms_finish",
+                        "ms_paint_x", "ms_paint_y", "ms_paint_z"):
                 stage_ms[key] = stage_ms.get(key, 0.0) + d[key]
+            y_sweeps += d["n_paint_y_sweeps"]
     ev1.record(stream)
     torch.cuda.synchronize()
     dev_ms = ev0.elapsed_time(ev1) / args.steps
@@ -272,19 +275,45 @@ def main():
     alg = {"ms_edt_x": 5.0 * N * 2, "ms_edt_y": 8.0 * N * 2, "ms_edt_z": 8.0 * N * 2, "ms_ridge": 8.0 * N * 2,
            "ms_finish": 25.0 * N * 2, "ms_paint": 4.0 * N * 2 + 16.0 * (n_ridge[0] + n_ridge[1])}
     stages = {}
-    for k, ms in per_step.items():
-        gbs = alg[k] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        stages[k[3:]] = {"ms_per_step": round(ms, 3), "alg_GB": round(alg[k] / 1e9, 3), "GBps": round(gbs, 1),
+    for k, a in alg.items():
+        ms = per_step[k]
+        gbs = a / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        stages[k[3:]] = {"ms_per_step": round(ms, 3), "alg_GB": round(a / 1e9, 3), "GBps": round(gbs, 1),
                          "frac_of_hbm_peak": round(gbs / hbm_peak, 4)}
+    for k in ("ms_paint_x", "ms_paint_y", "ms_paint_z"):
+        stages[k[3:]] = {"ms_per_step": round(per_step[k], 3)}
     edt_ms = per_step["ms_edt_x"] + per_step["ms_edt_y"] + per_step["ms_edt_z"]
     edt_gbs = 21.0 * N * 2 / (edt_ms * 1e-3) / 1e9
     stages["edt_total"] = {"ms_per_step": round(edt_ms, 3), "alg_GB": round(42.0 * N / 1e9, 3), "GBps": round(edt_gbs, 1),
                            "frac_of_hbm_peak": round(edt_gbs / hbm_peak, 4)}
-    dom = max(per_step, key=per_step.get)
-    dom_gbs = alg[dom] / (per_step[dom] * 1e-3) / 1e9
-    roofline = {"kernel": dom[3:], "bound": "hbm", "achieved": dom_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": dom_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind,
-                "note": "dominant stage by device time; algorithmic bytes per SURVEY.md 8(d); see stages for the EDT passes"}
+    # The dominant kernel is the painter's y-stage sweep, sep_dyn_kernel<., 2, +-1> (one launch = one direction over one
+    # block of columns; each is followed by its redo kernel, microseconds).  Algorithmic bytes of a launch (DESIGN.md
+    # 4.3): the list index words it cannot avoid -- two 8-byte words read and one written per voxel of the block
+    # (the items themselves, about 4 B x 5 per voxel, are not counted).  Launch time: events around the y stage of
+    # every block inside the library (bjt_timing.ms_paint_y), on the stream the kernels run on.
+    sweeps_per_step = y_sweeps / args.steps
+    if sweeps_per_step > 0 and per_step["ms_paint_y"] > 0:
+        launch_ms = per_step["ms_paint_y"] / sweeps_per_step
+        launch_bytes = 24.0 * N * 4.0 / sweeps_per_step    # 24 B x voxels of one block: blocks per run = sweeps / (2 runs x 2 directions)
+        y_gbs = launch_bytes / (launch_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            rec = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ystage_traffic.json")))
+            if rec.get("volume") == [n, n, n]:
+                traffic = rec["dram_bytes_per_launch"]
+        except (OSError, ValueError, KeyError):
+            pass
+        roofline = {"kernel": "sep_dyn_kernel<PACKED,2,+-1> (painter y-stage sweep)", "bound": "hbm", "achieved": y_gbs,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": y_gbs / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
+                    "launch_ms": round(launch_ms, 3), "launches_per_step": sweeps_per_step,
+                    "algorithmic_bytes_per_launch": launch_bytes,
+                    "share_of_step": round(per_step["ms_paint_y"] / dev_ms, 4),
+                    "note": "instruction-issue bound, not HBM bound (profiles/README.md); `stages` holds the streaming kernels"}
+    else:   # the separable painter did not run (constant fast path / scatter fallback): report the slowest stage
+        dom = max(alg, key=lambda k: per_step[k])
+        dom_gbs = alg[dom] / (per_step[dom] * 1e-3) / 1e9
+        roofline = {"kernel": dom[3:], "bound": "hbm", "achieved": dom_gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": dom_gbs / hbm_peak, "traffic": None, "peak_kind": peak_kind}
 
     # ---- CPU baseline (bounded sample) -----------------------------------------------------------------
     cpu = None

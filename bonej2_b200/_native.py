@@ -59,7 +59,8 @@ class Timing(C.Structure):
                 ("ms_ridge", C.c_float), ("ms_paint", C.c_float), ("ms_cleanup", C.c_float),
                 ("ms_finish", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
                 ("n_ridge", C.c_int64), ("n_launches", C.c_int64), ("rsq_max", C.c_uint32),
-                ("paint_path", C.c_int32)]
+                ("paint_path", C.c_int32), ("ms_paint_x", C.c_float), ("ms_paint_y", C.c_float),
+                ("ms_paint_z", C.c_float), ("n_paint_y_sweeps", C.c_int32)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

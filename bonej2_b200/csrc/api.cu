@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <map>
+#include <vector>
 #include <mutex>
 #include <string>
 
@@ -33,6 +34,10 @@ struct bjt_ctx {
     cudaEvent_t ev[16];
     int paint_path = -1;
     int64_t launches = 0;
+    // per-stage device time of the last separable paint (events around the x stage and every column block's y / z stage)
+    std::vector<cudaEvent_t> pev;
+    float paint_ms[3] = {0, 0, 0};
+    int paint_launches[3] = {0, 0, 0};
     // stepwise painter of a z-slab (bjt_dev_paint_open .. _close)
     struct { bool open = false; int w = 0, h = 0, d = 0, variant = 0; void *ws = nullptr; uint32_t *flags = nullptr; } ps;
 };
@@ -129,6 +134,7 @@ void bjt_destroy(bjt_ctx *c) {
     if (!c) return;
     bjt_release_workspace(c);
     for (auto &ev : c->ev) cudaEventDestroy(ev);
+    for (auto &ev : c->pev) cudaEventDestroy(ev);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -311,9 +317,31 @@ static int dev_paint(bjt_ctx *c, const uint32_t *ridge, int w, int h, int d, int
             void *wsp;
             WS("paint_sep", wb, wsp);
             CK(cudaMemsetAsync(scal + 8, 0, 4, c->stream));
-            c->launches += launch_paint_sep(ridge, w, h, d, variant, wsp, rsq, scal + 8, c->stream); CKL();
+            // x stage, then per column block the y and z stages, with an event at every boundary
+            const int nxs = paint_sep_nxslabs(w, h, d);
+            const size_t nev = 1 + (size_t)nxs * 2 + 1;
+            while (c->pev.size() < nev) { cudaEvent_t e; CK(cudaEventCreate(&e)); c->pev.push_back(e); }
+            size_t ne = 0;
+            CK(cudaEventRecord(c->pev[ne++], c->stream));
+            c->launches += paint_sep_stage1(ridge, w, h, d, variant, wsp, scal + 8, c->stream); CKL();
+            CK(cudaEventRecord(c->pev[ne++], c->stream));
+            for (int xs = 0; xs < nxs; ++xs) {
+                c->launches += paint_sep_stage2(w, h, d, variant, wsp, xs, scal + 8, c->stream); CKL();
+                CK(cudaEventRecord(c->pev[ne++], c->stream));
+                c->launches += paint_sep_stage3(w, h, d, variant, wsp, xs, nullptr, rsq, scal + 8, c->stream); CKL();
+                CK(cudaEventRecord(c->pev[ne++], c->stream));
+            }
             CK(cudaMemcpyAsync(c->h_scal + 8, scal + 8, 4, cudaMemcpyDeviceToHost, c->stream));
             CK(cudaStreamSynchronize(c->stream));
+            c->paint_ms[0] = c->paint_ms[1] = c->paint_ms[2] = 0.f;
+            cudaEventElapsedTime(&c->paint_ms[0], c->pev[0], c->pev[1]);
+            for (int xs = 0; xs < nxs; ++xs) {
+                float a = 0.f, b = 0.f;
+                cudaEventElapsedTime(&a, c->pev[1 + 2 * xs], c->pev[2 + 2 * xs]);
+                cudaEventElapsedTime(&b, c->pev[2 + 2 * xs], c->pev[3 + 2 * xs]);
+                c->paint_ms[1] += a; c->paint_ms[2] += b;
+            }
+            c->paint_launches[0] = 2; c->paint_launches[1] = 2 * nxs; c->paint_launches[2] = 2 * nxs;   // sweeps (each followed by its redo kernel)
             if (c->h_scal[8] == 0) { if (path_used) *path_used = wide; return BJT_OK; }
         }
         if (forced)
@@ -426,6 +454,11 @@ static int dev_pipeline(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, in
         tm->rsq_max = maxval;
         tm->paint_path = path_used;
         tm->n_launches = c->launches - launches0;
+        const bool sep = path_used == 0 || path_used == 1;
+        tm->ms_paint_x = sep ? c->paint_ms[0] : 0.f;
+        tm->ms_paint_y = sep ? c->paint_ms[1] : 0.f;
+        tm->ms_paint_z = sep ? c->paint_ms[2] : 0.f;
+        tm->n_paint_y_sweeps = sep ? c->paint_launches[1] : 0;
     }
     return BJT_OK;
 }

@@ -50,6 +50,9 @@ typedef struct bjt_timing {
     uint32_t rsq_max;       /* largest squared EDT value                                    */
     int32_t paint_path;     /* 0 = separable (16-bit items), 1 = separable (32-bit items),
                                2 = brute-force scatter, 3 = constant fast path (no background) */
+    float   ms_paint_x, ms_paint_y, ms_paint_z;   /* separable painter by stage (0 on the other paths)  */
+    int32_t n_paint_y_sweeps;                     /* launches of the y-stage sweep kernel (the dominant
+                                                     kernel): 2 directions x column blocks               */
 } bjt_timing;
 
 /* ---- context ------------------------------------------------------------------------------- */
