@@ -8,8 +8,9 @@ trabecular phantom -- what ThicknessWrapper.run() does for one dataset (Thicknes
              maps and their statistics are left in HBM; CUDA events on the stream the kernels use.
   e2e        the same work through the C-ABI call a JNI shim binds (bjt_thickness_both_u8) with
              page-locked HOST buffers: upload and both map downloads are inside the timed region.
-  roofline   the dominant stage of the step (by device time) against the measured HBM peak, plus
-             the EDT passes (the part of the metric quoted as "EDT HBM GB/s") under `stages`.
+  roofline   the dominant kernel (the painter's y-stage sweep): algorithmic bytes of one launch over its
+             launch time from events inside the library, against the measured HBM peak; every stage,
+             the EDT passes included (the "EDT HBM GB/s" of the metric), is under `stages`.
   cpu_baseline  the CPU oracle (a restatement of sc.fiji LocalThickness_, no JVM in the image) on
              a bounded sample of the same workload, on the box's host cores.
 
