@@ -80,6 +80,59 @@ def split_3d_subspaces(data: np.ndarray, axes, axis_names=None):
         yield Subspace(np.ascontiguousarray(arr), pos, tuple(axes[i] for i in split), ", ".join(parts))
 
 
+def _runs(map_choice):
+    if map_choice not in ("Trabecular thickness", "Trabecular separation", "Both"):
+        raise ValueError("Unexpected map choice")
+    return [("Tb.Th", False)] if map_choice == "Trabecular thickness" else \
+           [("Tb.Sp", True)] if map_choice == "Trabecular separation" else [("Tb.Th", False), ("Tb.Sp", True)]
+
+
+def thickness_hyperstack_ranks(data, axes, name="image", map_choice="Both", mask=True, pixel_width=1.0, unit="",
+                               device=None, run=None, group=None):
+    """The same batch over the ranks of a torch.distributed job (one process per GPU): subspace k is handled
+    by rank k mod world, every rank returns all rows in subspace order.  Subspaces are independent, so there
+    is no data-path collective -- only the result rows are gathered.
+
+    run(vol_u8, inverse) -> (mean, sd, max) may be injected (tests on CPU over gloo); by default it is the
+    CUDA path on `device` (default: the rank's local device) and fails without it."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    runs = _runs(map_choice)
+    unit_header = f"({unit or 'pixel'})"
+    ctx = None
+    if run is None:
+        import os
+        ctx = _native.Context(int(os.environ.get("LOCAL_RANK", rank)) if device is None else device)
+
+        def run(vol, inverse):
+            _, st, _ = ctx.thickness(vol, inverse=inverse, mask=mask, pixel_width=pixel_width, want_map=False)
+            return (st.mean, st.sd, st.max) if st.count else (float("nan"),) * 3
+    mine = []
+    try:
+        for k, sub in enumerate(split_3d_subspaces(np.asarray(data), axes)):
+            if k % world != rank:
+                continue
+            if sub.data.dtype != np.uint8:
+                raise ValueError("Need a binary image")
+            vals = {}
+            for prefix, inverse in runs:
+                mean, sd, mx = run(sub.data, inverse)
+                vals[f"{prefix} Mean {unit_header}"] = mean
+                vals[f"{prefix} Std Dev {unit_header}"] = sd
+                vals[f"{prefix} Max {unit_header}"] = mx
+            mine.append((k, f"{name} {sub.label}".strip(), vals))
+    finally:
+        if ctx is not None:
+            ctx.close()
+    parts = [mine]
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine, group=group)
+    rows = sorted((row for part in parts for row in part), key=lambda r: r[0])
+    return [(label, vals) for _, label, vals in rows]
+
+
 def thickness_hyperstack(data, axes, name="image", map_choice="Both", mask=True, pixel_width=1.0, unit="",
                          devices=(0,), want_maps=False):
     """Thickness on every {X, Y, Z} subspace.  Returns rows [(label, {header: value})] in subspace order

@@ -59,3 +59,59 @@ def test_batched_thickness_matches_oracle(oracle):
             else:
                 assert math.isclose(got, st.mean, rel_tol=1e-5)
                 assert math.isclose(vals[f"{prefix} Max (mm)"], st.max, rel_tol=1e-5)
+
+
+def _ranks_worker(rank, world, port, path, out_dir):
+    import os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import torch.distributed as dist
+    from bonej2_b200 import hyperstack as H
+    from oracle import lt_oracle
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    data = np.load(path)
+    seen = []
+
+    def run(vol, inverse):                                      # oracle stands in for the CUDA call: the test is about
+        seen.append(int(vol.sum()))                             # who runs which subspace and the order of the rows
+        st = lt_oracle.process_image(vol, inverse=inverse, mask=True)["stats"]
+        return (st.mean, st.sd, st.max) if st.count else (float("nan"),) * 3
+
+    rows = H.thickness_hyperstack_ranks(data, [X, Y, Z, CHANNEL, TIME], name="s", map_choice="Trabecular thickness", run=run)
+    np.save(os.path.join(out_dir, f"rows_{rank}.npy"), np.array([[r[1]["Tb.Th Mean (pixel)"] for r in rows]]))
+    with open(os.path.join(out_dir, f"labels_{rank}.txt"), "w") as f:
+        f.write("\n".join(r[0] for r in rows) + f"\n#{len(seen)}")
+    dist.destroy_process_group()
+
+
+def test_ranks_split_subspaces_and_agree(tmp_path, oracle):
+    """world_size 2 over gloo: each rank runs every other subspace, both end with all rows in subspace order"""
+    import socket
+    import torch.multiprocessing as mp
+    vols = [shapes.random_blobs((8, 9, 10), s) for s in (1, 2, 3, 4, 5)] + [np.zeros((8, 9, 10), np.uint8)]
+    data = np.stack(vols).reshape(2, 3, 8, 9, 10)               # T, C, Z, Y, X -> 6 subspaces
+    path = str(tmp_path / "hs.npy")
+    np.save(path, data)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_ranks_worker, args=(2, port, path, str(tmp_path)), nprocs=2, join=True)
+    want = []
+    for v in vols:
+        st = oracle.process_image(v, inverse=False, mask=True)["stats"]
+        want.append(st.mean if st.count else float("nan"))
+    for rank in (0, 1):
+        got = np.load(str(tmp_path / f"rows_{rank}.npy"))[0]
+        assert np.allclose(got, want, rtol=0, atol=0, equal_nan=True)
+        lines = open(str(tmp_path / f"labels_{rank}.txt")).read().split("\n")
+        assert lines[:3] == ["s Channel: 1, Time: 1", "s Channel: 2, Time: 1", "s Channel: 3, Time: 1"]
+        assert lines[-1] == "#3"                                 # three of the six subspaces ran here
+
+
+@pytest.mark.gpu
+def test_ranks_single_process_cuda(oracle):
+    """without a process group the rank form is the plain batch on this GPU"""
+    vols = [shapes.random_blobs((12, 14, 16), s) for s in (4, 5)]
+    rows = hs.thickness_hyperstack_ranks(np.stack(vols), [X, Y, Z, TIME], name="t", map_choice="Both")
+    assert [r[0] for r in rows] == ["t Time: 1", "t Time: 2"]
+    for (label, vals), vol in zip(rows, vols):
+        st = oracle.process_image(vol, inverse=True, mask=True)["stats"]
+        assert math.isclose(vals["Tb.Sp Mean (pixel)"], st.mean, rel_tol=1e-5)
