@@ -78,6 +78,10 @@ _SIGS = {
     "bjt_device_info": ([_VP, C.c_char_p, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)], _I),
     "bjt_set_paint_path": ([_VP, _I], _I),
     "bjt_launch_count": ([_VP], C.c_int64),
+    "bjt_label_stats_f32": ([_VP, _VP, _VP, C.c_size_t, _I, _VP, _VP], _I),
+    "bjt_dev_label_stats_f32": ([_VP, _VP, _VP, C.c_size_t, _I, _VP, _VP], _I),
+    "bjt_slice_stats_f32": ([_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP], _I),
+    "bjt_dev_slice_stats_f32": ([_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP], _I),
     "bjt_dev_paint_open": ([_VP, _VP, _I, _I, _I, C.c_int64], _I),
     "bjt_dev_paint_nxslabs": ([_VP], _I),
     "bjt_dev_paint_xslab_width": ([_VP, _I], _I),
@@ -177,6 +181,26 @@ class Context:
 
     def set_paint_path(self, path: int):
         self._ck(lib().bjt_set_paint_path(self._h, int(path)))
+
+    # ---- consumers of the map ----
+    def label_stats(self, map_f32, labels_i32, sizes_i64):
+        """ParticleAnalysis.getMeanStdDev: [n_labels][3] = mean, sd, max per particle label"""
+        m = np.ascontiguousarray(map_f32, np.float32)
+        lab = np.ascontiguousarray(labels_i32, np.int32)
+        sz = np.ascontiguousarray(sizes_i64, np.int64)
+        out = np.zeros((sz.size, 3), np.float64)
+        self._ck(lib().bjt_label_stats_f32(self._h, _ptr(m), _ptr(lab), m.size, sz.size, _ptr(sz), _ptr(out)))
+        return out
+
+    def slice_stats(self, map_f32, roi=None):
+        """SliceGeometry: ([d][3] = mean, max, sd per slice inside roi = (x, y, w, h), counts)"""
+        m = self._vol(map_f32, np.float32)
+        d, h, w = m.shape
+        rx, ry, rw, rh = roi if roi is not None else (0, 0, w, h)
+        out = np.zeros((d, 3), np.float64)
+        cnt = np.zeros(d, np.int64)
+        self._ck(lib().bjt_slice_stats_f32(self._h, _ptr(m), w, h, d, rx, ry, rw, rh, _ptr(out), _ptr(cnt)))
+        return out, cnt
 
     # ---- stepwise painter of a z-slab (see include/bonej_thickness.h) ----
     def dev_paint_open(self, d_ridge, w, h, d, max_rsq):

@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <cmath>
 #include <map>
 #include <vector>
 #include <mutex>
@@ -713,6 +714,94 @@ int bjt_dev_paint(bjt_ctx *c, const uint32_t *d_ridge, int w, int h, int d, int 
     rc = dev_paint(c, d_ridge, w, h, d, path, -1, -1, d_rsq, nullptr);
     c->paint_path = saved;
     return rc;
+}
+
+// ---- consumers of the map: segmented statistics ---------------------------------------------------------
+static int dev_label_stats(bjt_ctx *c, const float *d_map, const int32_t *d_labels, size_t n, int n_labels,
+                           const int64_t *sizes, double *out) {
+    if (!d_map || !d_labels || !sizes || !out || n_labels < 1) return fail(c, BJT_E_ARG, "label_stats: null pointer or no labels");
+    double *work, *d_sizes;
+    uint32_t *scal;
+    WS("scalars", 256, scal);
+    WS("seg_work", (size_t)5 * n_labels * sizeof(double), work);
+    WS("seg_sizes", (size_t)n_labels * sizeof(double), d_sizes);
+    std::vector<double> hs(n_labels);
+    for (int i = 0; i < n_labels; ++i) hs[i] = (double)sizes[i];
+    CK(cudaMemcpyAsync(d_sizes, hs.data(), hs.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(scal + 9, 0, 4, c->stream));
+    c->launches += launch_label_stats(d_map, d_labels, n, n_labels, d_sizes, work, scal + 9, c->stream); CKL();
+    std::vector<double> hw((size_t)5 * n_labels);
+    CK(cudaMemcpyAsync(hw.data(), work, hw.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_scal + 9, scal + 9, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->h_scal[9]) return fail(c, BJT_E_ARG, "label_stats: a label outside [0, %d) on a voxel with a value", n_labels);
+    for (int p = 0; p < n_labels; ++p) {
+        const double mean = hw[(size_t)3 * n_labels + p], ssq = hw[(size_t)4 * n_labels + p];
+        out[3 * p + 0] = p ? mean : 0.0;                       // the reference never fills mean / sd of label 0
+        out[3 * p + 1] = p ? std::sqrt(ssq / (double)sizes[p]) : 0.0;
+        out[3 * p + 2] = hw[(size_t)n_labels + p];
+    }
+    return BJT_OK;
+}
+
+int bjt_dev_label_stats_f32(bjt_ctx *c, const float *d_map, const int32_t *d_labels, size_t n, int n_labels,
+                            const int64_t *sizes, double *out) {
+    ENTER(c);
+    return dev_label_stats(c, d_map, d_labels, n, n_labels, sizes, out);
+}
+
+int bjt_label_stats_f32(bjt_ctx *c, const float *map, const int32_t *labels, size_t n, int n_labels, const int64_t *sizes,
+                        double *out) {
+    ENTER(c);
+    if (!map || !labels || n == 0) return fail(c, BJT_E_ARG, "label_stats: null pointer or empty map");
+    float *d_map; int32_t *d_lab;
+    WS("out", n * sizeof(float), d_map);
+    WS("bufA", n * sizeof(uint32_t), d_lab);
+    CK(cudaMemcpyAsync(d_map, map, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_lab, labels, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    return dev_label_stats(c, d_map, d_lab, n, n_labels, sizes, out);
+}
+
+static int dev_slice_stats(bjt_ctx *c, const float *d_map, int w, int h, int d, int rx, int ry, int rw, int rh, double *out,
+                           int64_t *counts) {
+    if (!d_map || !out) return fail(c, BJT_E_ARG, "slice_stats: null pointer");
+    if (rx < 0 || ry < 0 || rw < 1 || rh < 1 || rx + rw > w || ry + rh > h)
+        return fail(c, BJT_E_ARG, "slice_stats: ROI %d,%d %dx%d outside the %dx%d slice", rx, ry, rw, rh, w, h);
+    double *work;
+    WS("seg_work", (size_t)5 * d * sizeof(double), work);
+    c->launches += launch_slice_stats(d_map, w, h, d, rx, ry, rw, rh, work, c->stream); CKL();
+    std::vector<double> hw((size_t)5 * d);
+    CK(cudaMemcpyAsync(hw.data(), work, hw.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int z = 0; z < d; ++z) {
+        const double cnt = hw[(size_t)2 * d + z];
+        out[3 * z + 0] = hw[(size_t)3 * d + z];                // sum / count: NaN for an empty slice, as 0.0 / 0.0 in Java
+        out[3 * z + 1] = hw[(size_t)d + z];
+        out[3 * z + 2] = std::sqrt(hw[(size_t)4 * d + z] / cnt);
+        if (counts) counts[z] = (int64_t)cnt;
+    }
+    return BJT_OK;
+}
+
+int bjt_dev_slice_stats_f32(bjt_ctx *c, const float *d_map, int w, int h, int d, int rx, int ry, int rw, int rh, double *out,
+                            int64_t *counts) {
+    ENTER(c);
+    int rc = check_dims(c, w, h, d);
+    if (rc) return rc;
+    return dev_slice_stats(c, d_map, w, h, d, rx, ry, rw, rh, out, counts);
+}
+
+int bjt_slice_stats_f32(bjt_ctx *c, const float *map, int w, int h, int d, int rx, int ry, int rw, int rh, double *out,
+                        int64_t *counts) {
+    ENTER(c);
+    int rc = check_dims(c, w, h, d);
+    if (rc) return rc;
+    if (!map) return fail(c, BJT_E_ARG, "slice_stats: null pointer");
+    const size_t n = (size_t)w * h * d;
+    float *d_map;
+    WS("out", n * sizeof(float), d_map);
+    CK(cudaMemcpyAsync(d_map, map, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    return dev_slice_stats(c, d_map, w, h, d, rx, ry, rw, rh, out, counts);
 }
 
 // ---- stepwise painter of one z-slab -------------------------------------------------------------------

@@ -96,6 +96,10 @@ int launch_finish(const uint32_t *rsq, const uint8_t *original, int w, int h, in
 int finish_partials(int w, int h, int nz);
 int launch_stats(const float *map, size_t n, StatsPartial *partials, int npartials, StatsPartial *result,
                  cudaStream_t s);
+// segmented statistics of a map on the device (segstats.cu); work = 5 * segments doubles: sum, max, count, mean, ssq
+int launch_label_stats(const float *map, const int32_t *labels, size_t n, int nseg, const double *sizes, double *work,
+                       uint32_t *bad, cudaStream_t s);
+int launch_slice_stats(const float *map, int w, int h, int d, int rx, int ry, int rw, int rh, double *work, cudaStream_t s);
 int launch_check_binary(const uint8_t *in, size_t n, uint32_t *bad, cudaStream_t s);
 
 int launch_phantom(const int32_t *shapes, int nshapes, int w, int h, int d, int z0, int dz, uint8_t *out,

@@ -119,6 +119,23 @@ int bjt_cleanup_f32(bjt_ctx *ctx, const uint32_t *rsq, const uint8_t *original, 
                     int inverse, int calibrate, double pixel_width, float *out_map, bjt_stats *stats);
 int bjt_stats_f32(bjt_ctx *ctx, const float *map, size_t n, bjt_stats *stats);
 
+/* ---- consumers of the map: the reductions Legacy plugins run over a thickness map ------------- *
+ * Per particle label, ParticleAnalysis.getMeanStdDev (Legacy/bonej/.../ParticleAnalysis.java:325-364): over the
+ * voxels of label p with value > 0, out[3p] = sum / sizes[p], out[3p+1] = sqrt(sum (v - mean)^2 / sizes[p]),
+ * out[3p+2] = max; label 0: mean and sd stay 0.  sizes = the particles' voxel counts (the caller has them).
+ * A label outside [0, n_labels) on a voxel with a value is BJT_E_ARG.                                       */
+int bjt_label_stats_f32(bjt_ctx *ctx, const float *map, const int32_t *labels, size_t n, int n_labels,
+                        const int64_t *sizes, double *out);
+int bjt_dev_label_stats_f32(bjt_ctx *ctx, const float *d_map, const int32_t *d_labels, size_t n, int n_labels,
+                            const int64_t *sizes, double *out);
+/* Per slice inside an ROI rectangle, SliceGeometry (Legacy/bonej/.../SliceGeometry.java:876-900, 1172-1200): over the
+ * pixels with value > 0, out[3z] = mean, out[3z+1] = max (0 if none), out[3z+2] = sqrt(sum (mean - v)^2 / count);
+ * an empty slice gives NaN for mean and sd like the Java arithmetic; counts (may be NULL) = pixels counted.    */
+int bjt_slice_stats_f32(bjt_ctx *ctx, const float *map, int w, int h, int d, int rx, int ry, int rw, int rh,
+                        double *out, int64_t *counts);
+int bjt_dev_slice_stats_f32(bjt_ctx *ctx, const float *d_map, int w, int h, int d, int rx, int ry, int rw, int rh,
+                            double *out, int64_t *counts);
+
 /* ---- stage-level entry points, DEVICE buffers (z-slab sharded orchestration, profiling) ------- *
  * n_sentinel is max(w,h,d) of the WHOLE volume (a slab passes the global value).               */
 int bjt_dev_edt_x(bjt_ctx *ctx, const uint8_t *d_in, int w, int h, int d, int inverse, int threshold,
