@@ -8,11 +8,13 @@
 //           (lane l owns 32 consecutive voxels of every 1024-voxel segment), nearest flags left
 //           and right come from clz/ffs plus a warp prefix-max / suffix-min over the lanes, and
 //           the in-row distance (not squared) goes out as u16: 1 B read + 2 B written per voxel.
-//   y, z    one thread per line, adjacent threads on adjacent x, so every access of a warp is
-//           one contiguous row segment.  Each thread walks its line once; the minimiser of
-//           f(y') + (y-y')^2 is monotone in y, so the scan for y starts at the previous
-//           minimiser and stops as soon as (y'-y)^2 reaches the running minimum.  Candidate
-//           reads hit L1; HBM sees one read and one write per voxel.
+//   y, z    a block stages TX adjacent lines completely in shared memory and every warp computes, for its
+//           columns at once, h(t) = min_d f(t+d) + d^2 by walking d outwards on both sides until d^2 has
+//           reached the running minimum of every lane (edt_tile_kernel): no candidate read leaves the SM,
+//           HBM sees one read and one write per voxel.  Shapes that do not fit a tile fall back to one
+//           thread per line (edt_line4_kernel / edt_line_kernel): the minimiser of f(y') + (y-y')^2 is
+//           monotone in y, so the scan for y starts at the previous minimiser and stops as soon as
+//           (y'-y)^2 reaches the running minimum; candidate reads hit L1.
 #include "common.cuh"
 
 namespace bjt {

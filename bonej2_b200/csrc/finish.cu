@@ -6,9 +6,10 @@
 //   ij.process.StackStatistics              count / sum / sum^2 / min / max in double    (A.7)
 // as driven by ThicknessWrapper.createMap / addMapResults (ThicknessWrapper.java:158-196).
 //
-// One fused kernel.  A block owns 32 x 8 x 8 output voxels and stages the painted r^2 of the
-// (36 x 12 x 12) tile with its 2-voxel halo in shared memory (out-of-image cells hold a marker that
-// counts as "not zero", as the reference's look() returns -1 there).  From the tile it derives the
+// One fused kernel.  A block owns 32 x 8 x 8 output voxels and stages 2*sqrt(R) of the (36 x 12 x 12)
+// tile with its 2-voxel halo in shared memory as float (out-of-image cells hold a marker that counts
+// as "not zero", as the reference's look() returns -1 there); "not zero" / "interior" are kept as one
+// 64-bit word per tile row, built with ballots.  From the tile it derives the
 // "interior" flag (non-zero, no zero 26-neighbour) on the 1-voxel halo, then the value of each output
 // voxel: interior voxels keep 2*sqrt(R); surface voxels take the float32 mean of their interior
 // neighbours visited in the order faces, edges, corners (the order fixes the last ulp); then mask,
