@@ -341,7 +341,7 @@ def paint_exchange(stages, comm: Comm, ridge_own, zs, gmax, kcap=BOUNDARY_KCAP, 
 
 
 def thickness_slab(stages, comm: Comm, slab_u8, dims, inverse, mask=True, pixel_width=1.0, timings=None,
-                   paint_mode="auto"):
+                   paint_mode="auto", boundary_kcap=BOUNDARY_KCAP):
     """One pipeline run (LocalThicknessWrapper.processImage + StackStatistics) on this rank's z-slab.
     slab_u8: [dz][h][w] planes zs[rank] of the volume dims = (w, h, d).  Returns (map slab f32, stats dict)."""
     w, h, d = dims
@@ -390,7 +390,7 @@ def thickness_slab(stages, comm: Comm, slab_u8, dims, inverse, mask=True, pixel_
             ridge_own = stages.ridge(sq_ext)[z0 - needs[r][0]:z1 - needs[r][0]] if z1 > z0 else sq_ext
             del sq_ext
             mark("ridge", t0); t0 = t_()
-            rsq_own = paint_exchange(stages, comm, ridge_own, zs, gmax, timings=timings)
+            rsq_own = paint_exchange(stages, comm, ridge_own, zs, gmax, kcap=boundary_kcap, timings=timings)
             del ridge_own
             mark("paint", t0); t0 = t_()
             if rsq_own is not None:

@@ -26,7 +26,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, vol_path, out_dir, inverse, mask, paint_mode):
+def _worker(rank, world, port, vol_path, out_dir, inverse, mask, paint_mode, kcap=None):
     sys.path.insert(0, ROOT)
     from bonej2_b200 import sharded
     from tests.sharded_cpu_backend import OracleStages
@@ -36,25 +36,26 @@ def _worker(rank, world, port, vol_path, out_dir, inverse, mask, paint_mode):
     zs = sharded.split_ranges(d, world)
     slab = torch.from_numpy(vol[zs[rank][0]:zs[rank][1]].copy())
     comm = sharded.Comm()
-    out, stats = sharded.thickness_slab(OracleStages(), comm, slab, (w, h, d), inverse, mask, 0.5, paint_mode=paint_mode)
+    kw = {} if kcap is None else {"boundary_kcap": kcap}
+    out, stats = sharded.thickness_slab(OracleStages(), comm, slab, (w, h, d), inverse, mask, 0.5, paint_mode=paint_mode, **kw)
     np.save(os.path.join(out_dir, f"map_{rank}.npy"), out.numpy())
     if rank == 0:
         np.save(os.path.join(out_dir, "stats.npy"), np.array([stats["count"], stats["mean"], stats["sd"], stats["min"], stats["max"]]))
     dist.destroy_process_group()
 
 
-def _run(vol, inverse, mask, tmp_path, world=2, paint_mode="exchange"):
+def _run(vol, inverse, mask, tmp_path, world=2, paint_mode="exchange", kcap=None):
     vol_path = os.path.join(tmp_path, "vol.npy")
     np.save(vol_path, vol)
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, vol_path, str(tmp_path), inverse, mask, paint_mode), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, vol_path, str(tmp_path), inverse, mask, paint_mode, kcap), nprocs=world, join=True)
     maps = [np.load(os.path.join(tmp_path, f"map_{r}.npy")) for r in range(world)]
     return np.concatenate(maps, axis=0), np.load(os.path.join(tmp_path, "stats.npy"))
 
 
-def _check(vol, inverse, mask, tmp_path, world=2, paint_mode="exchange"):
+def _check(vol, inverse, mask, tmp_path, world=2, paint_mode="exchange", kcap=None):
     from oracle import lt_oracle
-    got, st = _run(vol, inverse, mask, tmp_path, world, paint_mode)
+    got, st = _run(vol, inverse, mask, tmp_path, world, paint_mode, kcap)
     ref = lt_oracle.process_image(vol, inverse=inverse, mask=mask, pixel_width=0.5)
     assert np.array_equal(np.isnan(got), np.isnan(ref["map"]))
     ok = ~np.isnan(got)
@@ -79,6 +80,15 @@ def test_four_ranks_thin_slabs_exchange(tmp_path):
     vol[1:15, 1:13, 1:13] = 255                                         # r_max = 6 > slab thickness 4
     vol[7, 6, 6] = 0
     _check(vol, False, True, str(tmp_path), world=4, paint_mode="exchange")
+
+
+def test_boundary_overflow_falls_back_to_halo_repaint(tmp_path):
+    """one staircase step per column is not enough here: every rank must notice and repaint slab + halo"""
+    from tests import shapes
+    vol = shapes.random_blobs((17, 14, 19), 3)
+    _check(vol, True, True, str(tmp_path), paint_mode="auto", kcap=1)
+    with pytest.raises(Exception):
+        _check(vol, True, True, str(tmp_path), paint_mode="exchange", kcap=1)       # no fallback allowed: an error, not a wrong map
 
 
 def test_empty_slabs_exchange(tmp_path):
