@@ -84,3 +84,34 @@ def test_512_line_kernel_equals_tile_kernel(ctx, vol512):
             # padding is at least 2, so any value <= 4 is decided by voxels both shapes share)
             sel = sa[:, :, :500] <= 4
             assert np.array_equal(sa[:, :, :500][sel], sb[:, :, :500][sel])
+
+
+def test_config2_1024_device_resident_properties(ctx):
+    """BASELINE.json configs[2] at one GPU (the bench's workload), device-resident like the bench: properties that
+    need no oracle -- every voxel of the run's foreground gets a value (mask on), the two runs partition the
+    volume, the largest thickness is the diameter of the largest inscribed ball (2 sqrt(max r^2), kept by the
+    cleanup because that voxel is interior), every value is at least 2, and the run is repeatable bit for bit."""
+    import torch
+    from bonej2_b200.phantom import phantom_shapes
+    n = 1024
+    free, _ = torch.cuda.mem_get_info()
+    if free < 120 * (1 << 30):
+        pytest.skip("needs about 120 GB of free device memory")
+    d_in = torch.empty(n ** 3, dtype=torch.uint8, device="cuda")
+    ctx.dev_phantom(phantom_shapes(n, n, n, 1), n, n, n, 0, n, d_in.data_ptr())
+    n_fg = int((d_in == 255).sum().item())
+    assert int((d_in == 0).sum().item()) + n_fg == n ** 3
+    d_out = torch.empty(n ** 3, dtype=torch.float32, device="cuda")
+    counts = []
+    for inverse in (False, True):
+        st, tm = ctx.dev_thickness(d_in.data_ptr(), n, n, n, inverse=inverse, mask=True, d_out=d_out.data_ptr())
+        counts.append(st.count)
+        assert tm.paint_path == 0
+        assert st.max == pytest.approx(2.0 * math.sqrt(tm.rsq_max), rel=1e-6)
+        assert st.min >= 2.0
+        assert int(torch.isnan(d_out).sum().item()) == n ** 3 - st.count
+        first = d_out[::4099].clone()
+        st2, _ = ctx.dev_thickness(d_in.data_ptr(), n, n, n, inverse=inverse, mask=True, d_out=d_out.data_ptr())
+        assert (st2.count, st2.mean, st2.sd, st2.max) == (st.count, st.mean, st.sd, st.max)
+        assert torch.equal(torch.nan_to_num(first, nan=-1.0), torch.nan_to_num(d_out[::4099], nan=-1.0))
+    assert counts == [n_fg, n ** 3 - n_fg]
