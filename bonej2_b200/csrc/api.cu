@@ -68,6 +68,19 @@ static int fail(bjt_ctx *c, int code, const char *fmt, ...) {
             return fail(c, BJT_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// A few words from device memory into the page-locked readback area, written by a kernel through the mapped
+// pointer instead of a device-to-host memcpy: a memcpy would queue behind whatever the copy engine is doing,
+// and in a "Both" call that is the 4 N-byte download of the first map -- the second run would wait for it at its
+// first readback.
+__global__ void peek_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int nwords) {
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+}
+static cudaError_t peek(bjt_ctx *c, void *host_dst, const void *dev_src, size_t bytes) {
+    peek_kernel<<<1, 32, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(dev_src), reinterpret_cast<uint32_t *>(host_dst),
+                                         (int)(bytes / 4));
+    return cudaGetLastError();
+}
+
 static int ws_get(bjt_ctx *c, const char *name, size_t bytes, void **out) {
     bjt_ctx::Buf &b = c->bufs[name];
     if (b.cap < bytes) {
@@ -236,7 +249,7 @@ static int dev_edt(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, int inv
     c->launches += launch_edt_z(gy, w, h, d, n0, sq, nullptr, scal, c->stream); CKL();
     if (evs) CK(cudaEventRecord(evs[3], c->stream));
     if (maxval_host) {
-        CK(cudaMemcpyAsync(c->h_scal, scal, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(peek(c, c->h_scal, scal, sizeof(uint32_t)));
         CK(cudaStreamSynchronize(c->stream));
         *maxval_host = c->h_scal[0];
     }
@@ -263,13 +276,13 @@ static int dev_ridge(bjt_ctx *c, const uint32_t *sq, int w, int h, int d, uint32
         CK(cudaMemsetAsync(present, 0, (size_t)maxval + 1, c->stream));
         c->launches += launch_mark_present(sq, N, present, scal + 6, c->stream); CKL();
         c->launches += launch_collect_values(present, maxval, values, scal + 2, c->stream); CKL();
-        CK(cudaMemcpyAsync(c->h_scal + 2, scal + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(peek(c, c->h_scal + 2, scal + 2, sizeof(uint32_t)));
         CK(cudaStreamSynchronize(c->stream));
         c->launches += launch_ridge_template(values, c->h_scal[2], t1, t2, t3, c->stream); CKL();
     }
     c->launches += launch_ridge(sq, w, h, d, t1, t2, t3, ridge, (unsigned long long *)(scal + 4), c->stream); CKL();
     if (n_ridge) {
-        CK(cudaMemcpyAsync(c->h_scal + 4, scal + 4, 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(peek(c, c->h_scal + 4, scal + 4, 8));
         CK(cudaStreamSynchronize(c->stream));
         *n_ridge = (int64_t)(*(unsigned long long *)(c->h_scal + 4));
     }
@@ -283,7 +296,7 @@ static int dev_ridge_full(bjt_ctx *c, const uint32_t *sq, int w, int h, int d, u
     WS("scalars", 256, scal);
     CK(cudaMemsetAsync(scal, 0, 4, c->stream));
     c->launches += launch_mark_present(sq, N, nullptr, scal, c->stream); CKL();
-    CK(cudaMemcpyAsync(c->h_scal, scal, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(peek(c, c->h_scal, scal, 4));
     CK(cudaStreamSynchronize(c->stream));
     return dev_ridge(c, sq, w, h, d, c->h_scal[0], ridge, n_ridge);
 }
@@ -299,7 +312,7 @@ static int dev_paint(bjt_ctx *c, const uint32_t *ridge, int w, int h, int d, int
         if (max_r < 0) {   // largest tag decides whether items fit 16+16 bits
             CK(cudaMemsetAsync(scal + 14, 0, 4, c->stream));
             c->launches += launch_mark_present(ridge, N, nullptr, scal + 14, c->stream); CKL();
-            CK(cudaMemcpyAsync(c->h_scal + 14, scal + 14, 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(peek(c, c->h_scal + 14, scal + 14, 4));
             CK(cudaStreamSynchronize(c->stream));
             max_r = c->h_scal[14];
         }
@@ -332,7 +345,7 @@ static int dev_paint(bjt_ctx *c, const uint32_t *ridge, int w, int h, int d, int
                 c->launches += paint_sep_stage3(w, h, d, variant, wsp, xs, nullptr, rsq, scal + 8, c->stream); CKL();
                 CK(cudaEventRecord(c->pev[ne++], c->stream));
             }
-            CK(cudaMemcpyAsync(c->h_scal + 8, scal + 8, 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(peek(c, c->h_scal + 8, scal + 8, 4));
             CK(cudaStreamSynchronize(c->stream));
             c->paint_ms[0] = c->paint_ms[1] = c->paint_ms[2] = 0.f;
             cudaEventElapsedTime(&c->paint_ms[0], c->pev[0], c->pev[1]);
@@ -358,7 +371,7 @@ static int dev_paint(bjt_ctx *c, const uint32_t *ridge, int w, int h, int d, int
         } else {   // count first (null sink)
             CK(cudaMemsetAsync(scal + 10, 0, 8, c->stream));
             c->launches += launch_compact_ridge(ridge, w, h, d, nullptr, (unsigned long long *)(scal + 10), c->stream); CKL();
-            CK(cudaMemcpyAsync(c->h_scal + 10, scal + 10, 8, cudaMemcpyDeviceToHost, c->stream));
+            CK(peek(c, c->h_scal + 10, scal + 10, 8));
             CK(cudaStreamSynchronize(c->stream));
             npts = *(unsigned long long *)(c->h_scal + 10);
         }
@@ -382,7 +395,7 @@ static int dev_finish_range(bjt_ctx *c, const uint32_t *rsq, const uint8_t *d_or
     c->launches += launch_finish(rsq, d_original, w, h, d, z_lo, z_hi, inverse, calibrate, (float)pixel_width, d_out,
                                  partials, np, result, c->stream); CKL();
     if (stats) {
-        CK(cudaMemcpyAsync(c->h_stats, result, sizeof(StatsPartial), cudaMemcpyDeviceToHost, c->stream));
+        CK(peek(c, c->h_stats, result, sizeof(StatsPartial)));
         CK(cudaStreamSynchronize(c->stream));
         stats_out(*c->h_stats, stats);
     }
@@ -410,7 +423,7 @@ static int dev_pipeline(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, in
     // input check of LocalThicknessWrapper.processImage: only 0 and 255
     CK(cudaMemsetAsync(scal + 12, 0, 4, c->stream));
     c->launches += launch_check_binary(d_in, N, scal + 12, c->stream); CKL();
-    CK(cudaMemcpyAsync(c->h_scal + 12, scal + 12, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(peek(c, c->h_scal + 12, scal + 12, 4));
 
     uint32_t maxval = 0;
     int rc = dev_edt(c, d_in, w, h, d, inverse, thresh, n, gx, bufA, bufB, &maxval, c->ev);
@@ -662,7 +675,7 @@ int bjt_stats_f32(bjt_ctx *c, const float *map, size_t n, bjt_stats *stats) {
     WS("stats_result", sizeof(StatsPartial), result);
     CK(cudaMemcpyAsync(d_out, map, n * 4, cudaMemcpyHostToDevice, c->stream));
     c->launches += launch_stats(d_out, n, partials, np, result, c->stream); CKL();
-    CK(cudaMemcpyAsync(c->h_stats, result, sizeof(StatsPartial), cudaMemcpyDeviceToHost, c->stream));
+    CK(peek(c, c->h_stats, result, sizeof(StatsPartial)));
     CK(cudaStreamSynchronize(c->stream));
     stats_out(*c->h_stats, stats);
     return BJT_OK;
@@ -732,7 +745,7 @@ static int dev_label_stats(bjt_ctx *c, const float *d_map, const int32_t *d_labe
     c->launches += launch_label_stats(d_map, d_labels, n, n_labels, d_sizes, work, scal + 9, c->stream); CKL();
     std::vector<double> hw((size_t)5 * n_labels);
     CK(cudaMemcpyAsync(hw.data(), work, hw.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(c->h_scal + 9, scal + 9, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(peek(c, c->h_scal + 9, scal + 9, 4));
     CK(cudaStreamSynchronize(c->stream));
     if (c->h_scal[9]) return fail(c, BJT_E_ARG, "label_stats: a label outside [0, %d) on a voxel with a value", n_labels);
     for (int p = 0; p < n_labels; ++p) {
@@ -859,7 +872,7 @@ int bjt_dev_paint_close(bjt_ctx *c, uint32_t *overflow_flags) {
     ENTER(c);
     if (!c->ps.open) return fail(c, BJT_E_ARG, "paint_close: no open painter");
     c->ps.open = false;
-    CK(cudaMemcpyAsync(c->h_scal + 8, c->ps.flags, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(peek(c, c->h_scal + 8, c->ps.flags, 4));
     CK(cudaStreamSynchronize(c->stream));
     if (overflow_flags) *overflow_flags = c->h_scal[8];
     return BJT_OK;
