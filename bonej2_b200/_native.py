@@ -78,6 +78,7 @@ _SIGS = {
     "bjt_device_info": ([_VP, C.c_char_p, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)], _I),
     "bjt_set_paint_path": ([_VP, _I], _I),
     "bjt_launch_count": ([_VP], C.c_int64),
+    "bjt_find_ridge_points_u8": ([_VP, _VP, _I, _I, _I, _D, _VP, C.c_int64, _VP, _VP], _I),
     "bjt_label_stats_f32": ([_VP, _VP, _VP, C.c_size_t, _I, _VP, _VP], _I),
     "bjt_dev_label_stats_f32": ([_VP, _VP, _VP, C.c_size_t, _I, _VP, _VP], _I),
     "bjt_slice_stats_f32": ([_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP], _I),
@@ -181,6 +182,16 @@ class Context:
 
     def set_paint_path(self, path: int):
         self._ck(lib().bjt_set_paint_path(self._h, int(path)))
+
+    def find_ridge_points(self, vol_u8, fraction=0.6, cap=1 << 20):
+        """FindRidgePoints: ([n][3] seed points (x, y, z), number found, largest ridge value)"""
+        v = self._vol(vol_u8, np.uint8)
+        d, h, w = v.shape
+        out = np.zeros((cap, 3), np.float64)
+        n = C.c_int64(0)
+        mx = C.c_float(0)
+        self._ck(lib().bjt_find_ridge_points_u8(self._h, _ptr(v), w, h, d, float(fraction), _ptr(out), cap, C.byref(n), C.byref(mx)))
+        return out[:min(cap, n.value)].copy(), int(n.value), float(mx.value)
 
     # ---- consumers of the map ----
     def label_stats(self, map_f32, labels_i32, sizes_i64):

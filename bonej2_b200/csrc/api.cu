@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <cmath>
 #include <map>
 #include <vector>
@@ -815,6 +816,65 @@ int bjt_slice_stats_f32(bjt_ctx *c, const float *map, int w, int h, int d, int r
     WS("out", n * sizeof(float), d_map);
     CK(cudaMemcpyAsync(d_map, map, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     return dev_slice_stats(c, d_map, w, h, d, rx, ry, rw, rh, out, counts);
+}
+
+// ---- FindRidgePoints: seeds for Ellipsoid Factor ---------------------------------------------------------
+int bjt_find_ridge_points_u8(bjt_ctx *c, const uint8_t *in, int w, int h, int d, double fraction, double *out_xyz,
+                             int64_t cap, int64_t *n_found, float *ridge_max) {
+    ENTER(c);
+    int rc = check_dims(c, w + 2, h + 2, d + 2);
+    if (rc) return rc;
+    if (!in || !n_found || cap < 0 || (cap > 0 && !out_xyz)) return fail(c, BJT_E_ARG, "find_ridge_points: null pointer");
+    const int W = w + 2, H = h + 2, D = d + 2;
+    const size_t n_in = (size_t)w * h * d, n = (size_t)W * H * D;
+    uint8_t *d_raw, *d_pad; uint16_t *gx; uint32_t *bufA, *bufB, *scal; float *fa, *fb; unsigned long long *found;
+    WS("in", n, d_pad);
+    WS("raw_in", n_in, d_raw);
+    WS("gx", n * sizeof(uint16_t), gx);
+    WS("bufA", n * sizeof(uint32_t), bufA);
+    WS("bufB", n * sizeof(uint32_t), bufB);
+    WS("out", n * sizeof(float), fa);
+    WS("out2", n * sizeof(float), fb);
+    WS("scalars", 256, scal);
+    CK(cudaMemcpyAsync(d_raw, in, n_in, cudaMemcpyHostToDevice, c->stream));
+    c->launches += launch_pad_binary(d_raw, w, h, d, d_pad, c->stream); CKL();
+    uint32_t maxval = 0;
+    const int nmax = W > H ? (W > D ? W : D) : (H > D ? H : D);
+    rc = dev_edt(c, d_pad, W, H, D, 0, 128, nmax, gx, bufA, bufB, &maxval, c->ev);     // the border is background: no sentinel
+    if (rc) return rc;
+    *n_found = 0;
+    if (ridge_max) *ridge_max = 0.f;
+    if (maxval == 0) return BJT_OK;                                                    // no foreground
+    float *fc = reinterpret_cast<float *>(bufA);
+    c->launches += launch_ridge_points_map(bufB, W, H, D, fa, fb, fc, scal + 16, c->stream); CKL();
+    CK(peek(c, c->h_scal + 16, scal + 16, 4));
+    CK(cudaStreamSynchronize(c->stream));
+    float mx;
+    memcpy(&mx, c->h_scal + 16, 4);
+    if (ridge_max) *ridge_max = mx;
+    const float threshold = (float)fraction * mx;                                       // float x float, as getRealFloat() * getRealFloat()
+    const unsigned long long ucap = (unsigned long long)(cap > 0 ? cap : 0);
+    WS("points", (size_t)(ucap ? ucap : 1) * sizeof(unsigned long long), found);
+    c->launches += launch_ridge_points_collect(fa, n, threshold, found, ucap, (unsigned long long *)(scal + 18), c->stream); CKL();
+    CK(peek(c, c->h_scal + 18, scal + 18, 8));
+    CK(cudaStreamSynchronize(c->stream));
+    unsigned long long cnt;
+    memcpy(&cnt, c->h_scal + 18, 8);
+    *n_found = (int64_t)cnt;
+    const unsigned long long take = cnt < ucap ? cnt : ucap;
+    if (take) {
+        std::vector<unsigned long long> idx(take);
+        CK(cudaMemcpyAsync(idx.data(), found, take * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        std::sort(idx.begin(), idx.end());                                              // the reference's cursor order: x fastest
+        for (unsigned long long k = 0; k < take; ++k) {
+            const unsigned long long i = idx[k];
+            out_xyz[3 * k + 0] = (double)(i % W) - 0.5;
+            out_xyz[3 * k + 1] = (double)((i / W) % H) - 0.5;
+            out_xyz[3 * k + 2] = (double)(i / ((unsigned long long)W * H)) - 0.5;
+        }
+    }
+    return BJT_OK;
 }
 
 // ---- stepwise painter of one z-slab -------------------------------------------------------------------

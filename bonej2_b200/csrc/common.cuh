@@ -100,6 +100,12 @@ int launch_stats(const float *map, size_t n, StatsPartial *partials, int npartia
 int launch_label_stats(const float *map, const int32_t *labels, size_t n, int nseg, const double *sizes, double *work,
                        uint32_t *bad, cudaStream_t s);
 int launch_slice_stats(const float *map, int w, int h, int d, int rx, int ry, int rw, int rh, double *work, cudaStream_t s);
+// FindRidgePoints (ridgepoints.cu)
+int launch_pad_binary(const uint8_t *in, int w, int h, int d, uint8_t *out, cudaStream_t s);
+int launch_ridge_points_map(const uint32_t *sq, int W, int H, int D, float *a, float *b, float *c, uint32_t *max_bits,
+                            cudaStream_t s);
+int launch_ridge_points_collect(const float *ridge, size_t n, float threshold, unsigned long long *out, unsigned long long cap,
+                                unsigned long long *count, cudaStream_t s);
 int launch_check_binary(const uint8_t *in, size_t n, uint32_t *bad, cudaStream_t s);
 
 int launch_phantom(const int32_t *shapes, int nshapes, int w, int h, int d, int z0, int dz, uint8_t *out,

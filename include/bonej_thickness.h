@@ -136,6 +136,13 @@ int bjt_slice_stats_f32(bjt_ctx *ctx, const float *map, int w, int h, int d, int
 int bjt_dev_slice_stats_f32(bjt_ctx *ctx, const float *d_map, int w, int h, int d, int rx, int ry, int rw, int rh,
                             double *out, int64_t *counts);
 
+/* org.bonej.ops.skeletonize.FindRidgePoints (Modern/ops/.../FindRidgePoints.java:55-116), the seed finder of
+ * Ellipsoid Factor, on the CUDA EDT.  in: w*h*d bytes, non-zero = foreground.  fraction: thresholdForBeingARidgePoint
+ * (reference default 0.6).  Writes up to cap points (x, y, z as doubles, voxel-centre coordinates of the input, in
+ * the reference's iteration order) and the number found (may exceed cap); ridge_max (may be NULL) = largest ridge value. */
+int bjt_find_ridge_points_u8(bjt_ctx *ctx, const uint8_t *in, int w, int h, int d, double fraction, double *out_xyz,
+                             int64_t cap, int64_t *n_found, float *ridge_max);
+
 /* ---- stage-level entry points, DEVICE buffers (z-slab sharded orchestration, profiling) ------- *
  * n_sentinel is max(w,h,d) of the WHOLE volume (a slab passes the global value).               */
 int bjt_dev_edt_x(bjt_ctx *ctx, const uint8_t *d_in, int w, int h, int d, int inverse, int threshold,
