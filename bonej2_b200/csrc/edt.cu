@@ -332,18 +332,20 @@ __global__ void __launch_bounds__(128) edt_line4_kernel(const TIn *__restrict__ 
 // has reached the running minimum of every lane (one vote per step).  No candidate read leaves the SM,
 // nothing depends on a load from global memory inside the loop, and the results go out as contiguous
 // row pieces straight from registers.  HBM traffic is exactly one read and one write per voxel.
+constexpr int EDT_PAD = 64;     // sentinel rows on either side of the staged lines: walks up to this distance need no clamping
+
 template <typename TIn, int TX, bool WANT_MAX>
 __global__ void __launch_bounds__(1024) edt_tile_kernel(const TIn *__restrict__ in, uint32_t *__restrict__ out, int groups,
                                                          long long outer, long long stride, int L, uint32_t n0,
                                                          uint32_t *__restrict__ maxval) {
-    extern __shared__ uint32_t sm_raw[];                 // [L + 2][TX]: rows -1 and L hold BIG (beyond the line)
+    extern __shared__ uint32_t sm_raw[];                 // [EDT_PAD + L + EDT_PAD][TX]: the pad rows hold BIG (beyond the line)
     constexpr int RPW = 32 / TX;                         // line positions per warp step
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int xx = lane % TX, rsub = lane / TX;
     const long long base = (long long)(blockIdx.x / groups) * outer + (long long)(blockIdx.x % groups) * TX;
     const uint32_t BIG = 0x3FFFFFFFu;
-    uint32_t *sm = sm_raw + TX;                          // sm[t * TX + xx], t in [-1, L]
-    if (threadIdx.x < TX) { sm[-TX + (int)threadIdx.x] = BIG; sm[L * TX + threadIdx.x] = BIG; }
+    uint32_t *sm = sm_raw + EDT_PAD * TX;                // sm[t * TX + xx], t in [-EDT_PAD, L + EDT_PAD)
+    for (int i = threadIdx.x; i < EDT_PAD * TX; i += blockDim.x) { sm[-EDT_PAD * TX + i] = BIG; sm[L * TX + i] = BIG; }
     for (int r0 = warp * RPW; r0 < L; r0 += nwarps * RPW) {
         const int t = r0 + rsub;
         if (t < L) sm[t * TX + xx] = f_of(__ldg(in + base + (long long)t * stride + xx), n0);
@@ -354,15 +356,29 @@ __global__ void __launch_bounds__(1024) edt_tile_kernel(const TIn *__restrict__ 
         const int t = r0 + rsub;
         const bool valid = t < L;
         const int tc = valid ? t : 0;
-        uint32_t m = valid ? sm[t * TX + xx] : 0u;
-        // two distances per vote; positions beyond the line ends clamp onto the BIG rows
-        for (int dlt = 1;; dlt += 2) {
+        const uint32_t *pc = sm + tc * TX + xx;
+        uint32_t m = valid ? *pc : 0u;
+        // two distances per vote.  Up to EDT_PAD the pad rows stand in for "beyond the line": no clamping
+        int dlt = 1;
+        const uint32_t *lo = pc - TX, *hi = pc + TX;
+        for (; dlt + 3 <= EDT_PAD; dlt += 4, lo -= 4 * TX, hi += 4 * TX) {
             const uint32_t d2 = (uint32_t)(dlt * dlt);
             if (!__any_sync(0xFFFFFFFFu, d2 < m)) break;
-            const uint32_t d2b = d2 + 2u * (uint32_t)dlt + 1u;
-            const uint32_t lo = sm[max(tc - dlt, -1) * TX + xx], hi = sm[min(tc + dlt, L) * TX + xx];
-            const uint32_t lo2 = sm[max(tc - dlt - 1, -1) * TX + xx], hi2 = sm[min(tc + dlt + 1, L) * TX + xx];
-            m = min(m, min(min(lo, hi) + d2, min(lo2, hi2) + d2b));
+            const uint32_t e = 2u * (uint32_t)dlt;
+            const uint32_t d2b = d2 + e + 1u, d2c = d2 + 2u * e + 4u, d2d = d2 + 3u * e + 9u;
+            const uint32_t m0 = min(min(lo[0], hi[0]) + d2, min(lo[-TX], hi[TX]) + d2b);
+            const uint32_t m1 = min(min(lo[-2 * TX], hi[2 * TX]) + d2c, min(lo[-3 * TX], hi[3 * TX]) + d2d);
+            m = min(m, min(m0, m1));
+        }
+        if (dlt + 3 > EDT_PAD) {                         // long walks: positions beyond the pad clamp onto its outermost rows
+            for (;; dlt += 2) {
+                const uint32_t d2 = (uint32_t)(dlt * dlt);
+                if (!__any_sync(0xFFFFFFFFu, d2 < m)) break;
+                const uint32_t d2b = d2 + 2u * (uint32_t)dlt + 1u;
+                const uint32_t a = sm[max(tc - dlt, -1) * TX + xx], b = sm[min(tc + dlt, L) * TX + xx];
+                const uint32_t a2 = sm[max(tc - dlt - 1, -1) * TX + xx], b2 = sm[min(tc + dlt + 1, L) * TX + xx];
+                m = min(m, min(min(a, b) + d2, min(a2, b2) + d2b));
+            }
         }
         if (valid) {
             const uint32_t res = m < n0 ? m : n0;
@@ -382,9 +398,9 @@ static bool launch_edt_tile(const TIn *in, uint32_t *out, int w, long long noute
                             int L, uint32_t n0, uint32_t *maxval, cudaStream_t s) {
     const size_t budget = 100 * 1024;      // two blocks per SM: one loads its tile while the other computes
     int tx = 32;
-    while (tx > 4 && (size_t)(L + 2) * tx * 4 > budget) tx >>= 1;
-    if ((size_t)(L + 2) * tx * 4 > budget || w % tx != 0) return false;
-    const size_t smem = (size_t)(L + 2) * tx * 4;
+    while (tx > 4 && (size_t)(L + 2 * EDT_PAD) * tx * 4 > budget) tx >>= 1;
+    if ((size_t)(L + 2 * EDT_PAD) * tx * 4 > budget || w % tx != 0) return false;
+    const size_t smem = (size_t)(L + 2 * EDT_PAD) * tx * 4;
     const int groups = w / tx;
     const unsigned grid = (unsigned)(nouter * groups);
     const int threads = 1024;
