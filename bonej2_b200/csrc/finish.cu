@@ -146,7 +146,10 @@ __global__ void __launch_bounds__(FTX *FTY, 4) finish_kernel(const uint32_t *__r
             const int cz = tz + 2;
             const float c = S[cz][cy][cx];
             float v = c;
-            if (c != 0.0f && !((itrow[cz][cy] >> cx) & 1ull)) {
+            // a voxel the mask removes needs no value (the mask is applied after the cleanup, so skipping its average
+            // changes nothing; its painted value still counts as "not zero" for its neighbours' interior flags above)
+            const bool kept = (int)og[tz][threadIdx.y][threadIdx.x] == fgval;
+            if (kept && c != 0.0f && !((itrow[cz][cy] >> cx) & 1ull)) {
                 // surface voxel: float32 mean of the interior neighbours, faces, edges, corners in turn.
                 // The 9 flag rows sit in registers; adding 0.0f for the other neighbours is exact.
                 unsigned long long rows[3][3];
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(FTX *FTY, 4) finish_kernel(const uint32_t *__r
                 v = n > 0 ? s / (float)n : c;
             }
             const size_t p = z * wh + (size_t)y * w + x;
-            if ((int)og[tz][threadIdx.y][threadIdx.x] != fgval) v = 0.0f;
+            if (!kept) v = 0.0f;
             if (calibrate) {
                 if (v == 0.0f) v = __int_as_float(0x7FC00000);
                 v = v * pw;
