@@ -252,6 +252,12 @@ class CudaStages:
         self._ps = None
         return out, flags
 
+    def plane_weights(self, ridge):
+        """cost estimate per plane of a ridge slab (see plane_costs)"""
+        nz, h, w = ridge.shape
+        q = ridge.sum(dim=(1, 2), dtype=torch.float64) / float(h * w)
+        return (float(h * w) * (COST_BASE + q * q)).tolist()
+
     def full(self, shape, value):
         return torch.full(shape, value, dtype=torch.int32, device=self.device)
 
@@ -269,6 +275,42 @@ class CudaStages:
 
 def no_result(n: int) -> int:
     return 3 * (n + 1) * (n + 1)
+
+
+def balanced_ranges(weights, parts: int):
+    """contiguous ranges of range(len(weights)) with near-equal weight sums (ranges may be empty)"""
+    n = len(weights)
+    total = float(sum(weights))
+    if n == 0 or total <= 0.0:
+        return split_ranges(n, parts)
+    cuts, acc, k = [0], 0.0, 1
+    for i, wgt in enumerate(weights):
+        acc += float(wgt)
+        while k < parts and acc >= k * total / parts:
+            cuts.append(i + 1)
+            k += 1
+    while len(cuts) < parts:
+        cuts.append(n)
+    cuts.append(n)
+    return [(cuts[i], max(cuts[i], cuts[i + 1])) for i in range(parts)]
+
+
+# Painter cost of a plane, from its ridge points.  Measured on 128-plane slabs of the 1024^3 phantom (tools/slab_cost.py):
+# Tb.Th 18-19 ms everywhere; Tb.Sp 45-54 ms inside the volume but 72 and 83 ms for the two face slabs, whose balls are
+# larger.  With q = (sum of the ridge r^2 of the plane) / (voxels of the plane), cost ~ voxels x (113 + q^2) reproduces the
+# three levels (q = 1.5, 13.4, 19.5 -> 115 : 293 : 493 against 18.6 : 47 : 83 ms).  Only the ratios matter, and a poor
+# estimate costs balance, never correctness.
+COST_BASE = 113.0
+
+
+def plane_costs(comm: Comm, stages, ridge_own, zs):
+    """estimated painter cost of every plane of the volume (the same list on every rank)"""
+    mine = stages.plane_weights(ridge_own) if ridge_own.shape[0] else []
+    if comm.size == 1:
+        return list(mine)
+    parts = [None] * comm.size
+    dist.all_gather_object(parts, [float(x) for x in mine], group=comm.group)
+    return [x for part in parts for x in part]
 
 
 BOUNDARY_KCAP = 32          # staircase steps per column a slab face can carry (more: fall back to the halo repaint)
@@ -341,7 +383,7 @@ def paint_exchange(stages, comm: Comm, ridge_own, zs, gmax, kcap=BOUNDARY_KCAP, 
 
 
 def thickness_slab(stages, comm: Comm, slab_u8, dims, inverse, mask=True, pixel_width=1.0, timings=None,
-                   paint_mode="auto", boundary_kcap=BOUNDARY_KCAP):
+                   paint_mode="auto", boundary_kcap=BOUNDARY_KCAP, balance=True):
     """One pipeline run (LocalThicknessWrapper.processImage + StackStatistics) on this rank's z-slab.
     slab_u8: [dz][h][w] planes zs[rank] of the volume dims = (w, h, d).  Returns (map slab f32, stats dict)."""
     w, h, d = dims
@@ -390,12 +432,20 @@ def thickness_slab(stages, comm: Comm, slab_u8, dims, inverse, mask=True, pixel_
             ridge_own = stages.ridge(sq_ext)[z0 - needs[r][0]:z1 - needs[r][0]] if z1 > z0 else sq_ext
             del sq_ext
             mark("ridge", t0); t0 = t_()
-            rsq_own = paint_exchange(stages, comm, ridge_own, zs, gmax, kcap=boundary_kcap, timings=timings)
+            # the painter works on its own split of the planes: equal estimated cost instead of equal thickness (balls are
+            # larger near the volume faces and bone is not spread evenly); ridge planes move over, painted planes move back
+            zp = zs
+            if balance and G > 1 and hasattr(stages, "plane_weights"):
+                zp = balanced_ranges(plane_costs(comm, stages, ridge_own, zs), G)
+                if zp != zs:
+                    ridge_own = gather_planes(comm, ridge_own, zs, zp)
+                mark("rebalance", t0); t0 = t_()
+            rsq_own = paint_exchange(stages, comm, ridge_own, zp, gmax, kcap=boundary_kcap, timings=timings)
             del ridge_own
             mark("paint", t0); t0 = t_()
             if rsq_own is not None:
                 needs2 = [(max(0, a - 2), min(d, b + 2)) if b > a else (a, a) for (a, b) in zs]
-                rsq_sub = gather_planes(comm, rsq_own, zs, needs2)
+                rsq_sub = gather_planes(comm, rsq_own, zp, needs2)
                 del rsq_own
                 mark("halo", t0); t0 = t_()
             elif paint_mode == "exchange":

@@ -96,6 +96,11 @@ class OracleStages:
         flags = self._ses.close()
         return torch.from_numpy(self._out.astype(np.int32)), int(flags != 0)
 
+    def plane_weights(self, ridge):
+        """deliberately lopsided, so the painter's split differs from the I/O split in the tests"""
+        r = _np(ridge).astype(np.float64)
+        return (1.0 + 50.0 * np.sqrt(r).sum(axis=(1, 2))).tolist()
+
     def full(self, shape, value):
         return torch.full(shape, value, dtype=torch.int32)
 

@@ -123,3 +123,15 @@ def test_split_ranges():
     from bonej2_b200.sharded import split_ranges
     assert split_ranges(10, 3) == [(0, 4), (4, 7), (7, 10)]
     assert split_ranges(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+
+
+def test_balanced_ranges():
+    from bonej2_b200.sharded import balanced_ranges
+    assert balanced_ranges([1] * 10, 3) == [(0, 4), (4, 7), (7, 10)]
+    assert balanced_ranges([10, 1, 1, 1, 1, 1, 1, 1, 1, 10], 2) == [(0, 5), (5, 10)]
+    assert balanced_ranges([0, 0, 5, 0, 0], 4) == [(0, 3), (3, 3), (3, 3), (3, 5)]          # empty ranges are legal
+    assert balanced_ranges([], 3) == [(0, 0)] * 3
+    for w, g in (([3, 1, 4, 1, 5, 9, 2, 6], 3), ([1, 1], 4), ([7], 2)):
+        r = balanced_ranges(w, g)
+        assert len(r) == g and r[0][0] == 0 and r[-1][1] == len(w)
+        assert all(a <= b for a, b in r) and all(r[i][1] == r[i + 1][0] for i in range(g - 1))
