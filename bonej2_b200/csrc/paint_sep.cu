@@ -6,8 +6,10 @@
 // oracle/sep_paint_model.cpp that tests it without a GPU).  Cost is O(N * front size) instead of
 // the sum of ball volumes.
 //
-// Layout.  One thread per line, 32 adjacent lines per warp, every lane at the same position of its
-// line, so a warp moves through the volume as a plane front.  Fronts are variable-length lists:
+// Layout.  One thread per line, every lane of a warp at the same position of its line, so a warp moves
+// through the volume as a plane front.  A warp's 32 lines are an 8 x 4 patch of the plane of lines
+// (sep_patch_line in paint_sep_core.cuh): neighbours in both directions have similar active sets, which is
+// what a lock-step warp pays for.  Fronts are variable-length lists:
 // per voxel one u64 index entry (offset:40 | count:24) into an item pool; a warp allocates the
 // items of one step with a single atomicAdd (shuffle prefix sum), so items of neighbouring lines
 // are neighbours in the pool.  Forward and backward fronts are kept as two lists; the next stage
@@ -308,9 +310,10 @@ template <> struct FastActive<false> { typedef SepActive<WideStore> T; };
 template <bool PACKED, int STAGE, int DIR>
 __global__ void __launch_bounds__(TPB) sep_dyn_kernel(SepArgs a) {
     __shared__ unsigned long long sm[PACKED ? 2 * S_SM * TPB : 1];
-    const long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nlines = STAGE == 1 ? (long long)a.h * a.d : (long long)a.xw * a.d;
-    const bool valid = line < nlines;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long pl = STAGE == 1 ? sep_patch_line(tid, a.h, a.d) : sep_patch_line(tid, a.xw, a.d);
+    const bool valid = pl >= 0;                      // whole warps stay in: dyn_line allocates as a warp
+    const long long line = valid ? pl : 0;
     typename FastActive<PACKED>::T A;
     if constexpr (PACKED) A.st.sm = (uint32_t)__cvta_generic_to_shared(sm + threadIdx.x);
     SepItem fr[FMAX_FAST];
@@ -343,8 +346,8 @@ __global__ void __launch_bounds__(32) sep_dyn_redo_kernel(SepArgs a) {
 
 template <bool PACKED>
 __global__ void __launch_bounds__(TPB) sep_stair_kernel(SepArgs a) {
-    const long long line = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (line >= (long long)a.xw * a.h) return;
+    const long long line = sep_patch_line((long long)blockIdx.x * blockDim.x + threadIdx.x, a.xw, a.h);
+    if (line < 0) return;
     SepStair<StairStore> S;
     if (!stair_line<PACKED>(a, line, S)) record_redo(a, line);
 }
@@ -423,8 +426,8 @@ Plan make_plan(int w, int h, int d, int wide, int scale) {
     p.maxlines = l1 > l2 ? (l1 > l3 ? l1 : l3) : (l2 > l3 ? l2 : l3);
     const size_t isz = wide ? 8 : 4;
     // items; every warp may leave up to one CHUNK unused per sweep
-    p.cap1 = (unsigned long long)p.n * (unsigned)(4 * scale) + (unsigned long long)(l1 / 32 + 1) * CHUNK * 2 + 65536;
-    p.cap2 = (unsigned long long)p.nslab * (unsigned)(12 * scale) + (unsigned long long)(l2 / 32 + 1) * CHUNK * 2 + 65536;
+    p.cap1 = (unsigned long long)p.n * (unsigned)(4 * scale) + (unsigned long long)sep_patch_warps(h, d) * CHUNK * 2 + 65536;
+    p.cap2 = (unsigned long long)p.nslab * (unsigned)(12 * scale) + (unsigned long long)sep_patch_warps(xw, d) * CHUNK * 2 + 65536;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
     p.off_counters = take(256);
@@ -472,9 +475,8 @@ int run_stage1(const uint32_t *ridge, int w, int h, int d, const Plan &p, char *
         a.ridge = ridge; a.xc0 = 0; a.xw = w; a.dir = dir;
         a.out_idx = dir > 0 ? b.idx1f : b.idx1b; a.out_pool = b.pool1; a.out_cap = p.cap1; a.out_counter = b.counters;
         a.poolflag = F_POOL1;
-        const long long nlines = (long long)h * d;
         cudaMemsetAsync(b.redo_count, 0, 4, s);
-        const unsigned grid = (unsigned)((nlines + TPB - 1) / TPB);
+        const unsigned grid = (unsigned)((sep_patch_threads(h, d) + TPB - 1) / TPB);
         if (dir > 0) {
             sep_dyn_kernel<PACKED, 1, +1><<<grid, TPB, 0, s>>>(a);
             sep_dyn_redo_kernel<PACKED, 1, +1><<<NSLOTS / 32, 32, 0, s>>>(a);
@@ -500,9 +502,8 @@ int run_stage2(int w, int h, int d, const Plan &p, char *ws, int xc0, uint32_t *
         a.inF = b.idx1f; a.inB = b.idx1b; a.in_pool = b.pool1; a.xc0 = xc0; a.xw = xw; a.dir = dir;
         a.out_idx = dir > 0 ? b.idx2f : b.idx2b; a.out_pool = b.pool2; a.out_cap = p.cap2; a.out_counter = b.counters + 1;
         a.poolflag = F_POOL2;
-        const long long nlines = (long long)xw * d;
         cudaMemsetAsync(b.redo_count, 0, 4, s);
-        const unsigned grid = (unsigned)((nlines + TPB - 1) / TPB);
+        const unsigned grid = (unsigned)((sep_patch_threads(xw, d) + TPB - 1) / TPB);
         if (dir > 0) {
             sep_dyn_kernel<PACKED, 2, +1><<<grid, TPB, 0, s>>>(a);
             sep_dyn_redo_kernel<PACKED, 2, +1><<<NSLOTS / 32, 32, 0, s>>>(a);
@@ -528,9 +529,8 @@ int run_stage3(int w, int h, int d, const Plan &p, char *ws, int xc0, const SepI
         a.inF = b.idx2f; a.inB = b.idx2b; a.in_pool = b.pool2; a.xc0 = xc0; a.xw = xw; a.dir = dir;
         a.out = rsq;
         if (imp) a.imp = *imp;
-        const long long nlines = (long long)xw * h;
         cudaMemsetAsync(b.redo_count, 0, 4, s);
-        sep_stair_kernel<PACKED><<<(unsigned)((nlines + TPB - 1) / TPB), TPB, 0, s>>>(a);
+        sep_stair_kernel<PACKED><<<(unsigned)((sep_patch_threads(xw, h) + TPB - 1) / TPB), TPB, 0, s>>>(a);
         sep_stair_redo_kernel<PACKED><<<NSLOTS / 32, 32, 0, s>>>(a);
         launches += 2;
     }

@@ -62,6 +62,30 @@ BJT_HD uint32_t sep_isqrt(uint32_t v) {
 // A correctly rounded float sqrt is never below the largest integer <= the true root.
 BJT_HD int sep_sqrt_upper(uint32_t v) { return (int)sep_sqrt_fast((float)v) + 2; }
 
+// ---- lanes of a warp as a patch of lines ----------------------------------------------------------------
+// The lines of a stage form a plane: line = b * na + a (stage 1: a = y, b = z; stage 2: a = x, b = z;
+// stage 3: a = x, b = y).  The lanes of a warp move in lock step, so a position costs the warp what its busiest
+// line costs.  Lines that are close in BOTH directions of the plane have similar active sets; lines 31 apart
+// in one direction sit in different structures.  Measured on the CPU model (tools/study/painter_study.cpp,
+// 256^3 phantom, Tb.Sp): a warp of 8 x 4 lines needs 15.6 loop iterations per position of stage 2 where a
+// warp of 32 x 1 needs 22.3 (stage 1: 3.9 against 5.6; stage 3: 6.7 against 8.5).  Eight lanes along `a` keep
+// the 8-byte index words of a warp in 64-byte pieces.
+// Thread `tid` of the grid -> its line, or -1 where the patch overhangs the plane (and for the threads a grid
+// rounded up to whole blocks has beyond sep_patch_threads()).
+constexpr int SEP_PATCH_A = 8, SEP_PATCH_B = 4;          // SEP_PATCH_A * SEP_PATCH_B == 32
+BJT_HD long long sep_patch_warps(int na, int nb) {
+    return (long long)((na + SEP_PATCH_A - 1) / SEP_PATCH_A) * ((nb + SEP_PATCH_B - 1) / SEP_PATCH_B);
+}
+BJT_HD long long sep_patch_threads(int na, int nb) { return sep_patch_warps(na, nb) * 32; }
+BJT_HD long long sep_patch_line(long long tid, int na, int nb) {
+    const long long warp = tid >> 5;
+    const int lane = (int)(tid & 31);
+    const long long pa = (na + SEP_PATCH_A - 1) / SEP_PATCH_A;
+    const long long a = (warp % pa) * SEP_PATCH_A + lane % SEP_PATCH_A;
+    const long long b = (warp / pa) * SEP_PATCH_B + lane / SEP_PATCH_A;
+    return (a < na && b < nb) ? b * na + a : -1;
+}
+
 // ---- storage policies --------------------------------------------------------------------------------
 // A store holds two buffers ("halves") of up to cap() entries; step() reads one and writes the other.
 // Entries are opaque to step(): the policy names the type and its accessors, so a packed store moves

@@ -184,6 +184,19 @@ def sep_paint_model(ridge_u32):
     return out, info
 
 
+def sep_patch_map(na, nb, threads_per_block=128):
+    """thread -> line map of the painter kernels (sep_patch_line in paint_sep_core.cuh) for a plane of na x nb
+    lines and a grid of whole blocks: int64 array, -1 = idle thread."""
+    L = lib()
+    L.spm_patch_map.restype = C.c_longlong
+    L.spm_patch_map.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.c_longlong]
+    cap = ((na + 7) // 8) * ((nb + 3) // 4) * 32 + threads_per_block
+    lines = np.empty(cap, np.int64)
+    n = L.spm_patch_map(na, nb, threads_per_block, _p(lines, C.c_longlong), cap)
+    assert n >= 0
+    return lines[:n]
+
+
 class SepPaintSession:
     """The CPU model's painter in steps (oracle/sep_paint_model.cpp spm_open .. spm_close): same calls and
     buffer layout as bjt_dev_paint_open .. _close, on numpy arrays.  TEST ONLY."""

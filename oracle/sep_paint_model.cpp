@@ -222,6 +222,15 @@ extern "C" int spm_sweep(void *handle, int n_lo, const uint32_t *const *lo_cnt, 
     return 0;
 }
 
+/* the kernels' thread -> line map (sep_patch_line), evaluated for a whole grid: lines[tid], -1 = idle thread */
+extern "C" long long spm_patch_map(int na, int nb, int threads_per_block, long long *lines, long long capacity) {
+    const long long need = sep_patch_threads(na, nb);
+    const long long grid = (need + threads_per_block - 1) / threads_per_block * threads_per_block;
+    if (grid > capacity) return -grid;
+    for (long long tid = 0; tid < grid; ++tid) lines[tid] = sep_patch_line(tid, na, nb);
+    return grid;
+}
+
 extern "C" long spm_close(void *handle) {
     SpmSession *S = (SpmSession *)handle;
     const long ovf = S->overflow;

@@ -49,3 +49,23 @@ def test_model_degenerate(oracle):
     _check(oracle, np.sqrt(one.astype(np.float32)), one)
     line = np.zeros((1, 1, 40), np.uint32); line[0, 0, 5] = 16; line[0, 0, 30] = 100
     _check(oracle, np.sqrt(line.astype(np.float32)), line)
+
+
+@pytest.mark.parametrize("na,nb", [(1, 1), (7, 3), (8, 4), (9, 5), (37, 28), (33, 37), (512, 128), (100, 1), (1, 100),
+                                   (1024, 31), (250, 250)])
+def test_patch_map_is_a_bijection(oracle, na, nb):
+    """the kernels' thread -> line map (8 x 4 patches of lines per warp): every line exactly once, idle threads -1,
+    and a warp's lines form one patch"""
+    m = oracle.sep_patch_map(na, nb)
+    assert m.size % 128 == 0
+    used = m[m >= 0]
+    assert used.size == na * nb and np.array_equal(np.sort(used), np.arange(na * nb))
+    warps = m.reshape(-1, 32)
+    for wl in warps[:: max(1, len(warps) // 64)]:
+        v = wl[wl >= 0]
+        if v.size == 0:
+            continue
+        a, b = v % na, v // na
+        assert a.max() - a.min() < 8 and b.max() - b.min() < 4
+        lanes = np.nonzero(wl >= 0)[0]
+        assert np.array_equal(a - a.min() + (a.min() % 8), lanes % 8) and np.array_equal(b - (b.min() // 4) * 4, lanes // 8)
