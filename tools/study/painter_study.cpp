@@ -72,6 +72,41 @@ int main(int argc, char **argv) {
            g_cnt[0], g_cnt[0] / (2.0 * N), 100.0 * g_cnt[1] / g_cnt[0], 100.0 * g_cnt[2] / g_cnt[0], 100.0 * g_cnt[3] / g_cnt[0],
            100.0 * g_cnt[4] / g_cnt[0], 100.0 * g_cnt[5] / g_cnt[0], (l1f.pool.size() + l1b.pool.size()) / (double)N);
 
+    // ---- optional: canonical slack for stage 2 (argv[5] = 1).  What an item (rho, R) still covers in the (y, z) plane
+    // is {dy^2 + dz^2 <= rho}: the same lattice points for every rho between two consecutive sums of two squares,
+    // so rho may be rounded down to the largest sum of two squares, and an item whose rounded slack does not
+    // exceed that of an item with a larger tag is redundant (the 2-D form of stage 2's reach pruning) ----
+    if (argc > 5 && atoi(argv[5]) == 1) {
+        uint32_t maxr = 0;
+        for (size_t i = 0; i < N; ++i) maxr = std::max(maxr, ridge[i]);
+        std::vector<uint32_t> canon(maxr + 1, 0);
+        std::vector<char> is2(maxr + 1, 0);
+        for (uint32_t a = 0; a * a <= maxr; ++a) for (uint32_t b = a; a * a + b * b <= maxr; ++b) is2[a * a + b * b] = 1;
+        uint32_t last = 0, nsum = 0;
+        for (uint32_t r = 0; r <= maxr; ++r) { if (is2[r]) { last = r; ++nsum; } canon[r] = last; }
+        printf("canonical slack: %u of %u values up to max r^2 are sums of two squares\n", nsum, maxr + 1);
+        size_t before = 0, after = 0;
+        for (Lists *Lp : {&l1f, &l1b}) {
+            Lists &Ls = *Lp;
+            before += Ls.pool.size();
+            std::vector<SepItem> np; np.reserve(Ls.pool.size());
+            for (size_t v = 0; v < N; ++v) {
+                const size_t o = Ls.off[v]; const uint32_t c = Ls.cnt[v];
+                Ls.off[v] = np.size();
+                long lastc = -1; uint32_t k2 = 0;
+                for (uint32_t k = 0; k < c; ++k) {
+                    SepItem it = Ls.pool[o + k];
+                    const long cs = canon[it.rho];
+                    if (cs > lastc) { lastc = cs; it.rho = (uint32_t)cs; np.push_back(it); ++k2; }
+                }
+                Ls.cnt[v] = k2;
+            }
+            Ls.pool.swap(np);
+            after += Ls.pool.size();
+        }
+        printf("stage-1 items %zu -> %zu (%.1f %% fewer)\n", before, after, 100.0 * (before - after) / before);
+    }
+
     // ---- stage 2 along y ----
     Lists l2f(N), l2b(N);
     std::vector<uint16_t> v2(2 * N);
