@@ -269,23 +269,24 @@ struct SepStair {
     // Returns false on overflow.
     BJT_HD bool arrive(int u, uint32_t e, uint32_t Rn, int &hint) {
         const int En = u + (int)e;
+        BJT_SEP_COUNT(6);
         // cheap reject against the head: R_n <= R_head and reach_n <= reach_head
-        if (n > 0 && Rn <= st.getR(0) && En <= st.getE(0)) return true;
+        if (n > 0 && Rn <= st.getR(0) && En <= st.getE(0)) { BJT_SEP_COUNT(7); return true; }
         int pos = hint;
-        while (pos < n && st.getR(pos) > Rn) ++pos;
+        while (pos < n && st.getR(pos) > Rn) { ++pos; BJT_SEP_COUNT(8); }
         hint = pos;
-        if (pos > 0 && st.getE(pos - 1) >= En) return true;            // a larger tag reaches at least as far
-        if (pos < n && st.getR(pos) == Rn && st.getE(pos) >= En) return true;
+        if (pos > 0 && st.getE(pos - 1) >= En) { BJT_SEP_COUNT(9); return true; }   // a larger tag reaches at least as far
+        if (pos < n && st.getR(pos) == Rn && st.getE(pos) >= En) { BJT_SEP_COUNT(9); return true; }
         int k = pos;
-        while (k < n && st.getE(k) <= En) ++k;                          // R <= R_n and reach <= reach_n: redundant
+        while (k < n && st.getE(k) <= En) { ++k; BJT_SEP_COUNT(10); }   // R <= R_n and reach <= reach_n: redundant
         const int removed = k - pos;
         if (removed == 0) {
             if (n >= st.cap()) return false;
-            for (int i = n; i > pos; --i) st.put(i, st.getR(i - 1), st.getE(i - 1));
+            for (int i = n; i > pos; --i) { st.put(i, st.getR(i - 1), st.getE(i - 1)); BJT_SEP_COUNT(11); }
             ++n;
         } else if (removed > 1) {
             const int sh = removed - 1;
-            for (int i = k; i < n; ++i) st.put(i - sh, st.getR(i), st.getE(i));
+            for (int i = k; i < n; ++i) { st.put(i - sh, st.getR(i), st.getE(i)); BJT_SEP_COUNT(11); }
             n -= sh;
         }
         st.put(pos, Rn, En);
@@ -298,7 +299,7 @@ struct SepStair {
         int h = 0;
         while (h < n && st.getE(h) < u) ++h;
         if (h > 0) {
-            for (int i = h; i < n; ++i) st.put(i - h, st.getR(i), st.getE(i));
+            for (int i = h; i < n; ++i) { st.put(i - h, st.getR(i), st.getE(i)); BJT_SEP_COUNT(12); }
             n -= h;
         }
         return n > 0 ? st.getR(0) : 0u;

@@ -14,7 +14,7 @@
 #include <algorithm>
 #include <vector>
 
-static long g_cnt[8];
+static long g_cnt[16];
 #define BJT_SEP_COUNT(k) (++g_cnt[k])
 #include "../../bonej2_b200/csrc/paint_sep_core.cuh"
 using namespace bjt;
@@ -231,5 +231,56 @@ int main(int argc, char **argv) {
         printf(" %dx%d: %.3f (%.2f)", LX, LY, useful / issued, issued / 32.0 / npos);
     }
     printf("\n");
+    // ---- stage 3: what the staircase operations cost (loop trips inside arrive() / query()) ----
+    {
+        memset(g_cnt, 0, sizeof g_cnt);
+        static SepStair<SepStairLocal<CAP> > S;
+        std::vector<uint32_t> outv(N, 0);
+        std::vector<uint16_t> c3(2 * N);
+        double sum_n = 0; long max_n = 0;
+        for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x)
+            for (int dir = +1; dir >= -1; dir -= 2) {
+                S.clear();
+                for (int step = 0; step < d; ++step) {
+                    const int z = dir > 0 ? step : d - 1 - step;
+                    const int u = dir > 0 ? z : -z;
+                    const size_t v = (size_t)z * wh + (size_t)y * w + x;
+                    long c0 = 0; for (int k = 6; k <= 12; ++k) c0 += g_cnt[k];
+                    for (int which = 0; which < 2; ++which) {
+                        const Lists &in = which ? l2b : l2f;
+                        int hint = 0;
+                        for (uint32_t k = 0; k < in.cnt[v]; ++k) { const SepItem it = in.pool[in.off[v] + k]; S.arrive(u, it.rho, it.R, hint); }
+                    }
+                    const uint32_t r = S.query(u);
+                    if (dir > 0) outv[v] = r; else if (r > outv[v]) outv[v] = r;
+                    long c1 = 0; for (int k = 6; k <= 12; ++k) c1 += g_cnt[k];
+                    c3[(dir > 0 ? 0 : N) + v] = (uint16_t)(c1 - c0 + 1);
+                    sum_n += S.n; max_n = std::max<long>(max_n, S.n);
+                }
+            }
+        const double per = 2.0 * N;
+        printf("stage 3 (z), per voxel and direction: arrivals %.2f (head rejects %.2f, other rejects %.2f), search steps %.2f, "
+               "removal scan %.2f, shift moves on insert %.2f, shift moves on query %.2f; staircase size mean %.2f max %ld\n",
+               g_cnt[6] / per, g_cnt[7] / per, g_cnt[9] / per, g_cnt[8] / per, g_cnt[10] / per, g_cnt[11] / per, g_cnt[12] / per,
+               sum_n / per, max_n);
+        printf("stage 3 with cost = all loop trips + 1: warp = LX x LY patch: useful / issued (warp cost per position)\n   ");
+        for (int LX : {32, 16, 8, 4}) {
+            const int LY = 32 / LX;
+            double useful = 0, issued = 0, npos = 0;
+            for (int dirsel = 0; dirsel < 2; ++dirsel) {
+                const uint16_t *p = c3.data() + (dirsel ? N : 0);
+                for (int y0 = 0; y0 + LY <= h; y0 += LY) for (int x0 = 0; x0 + LX <= w; x0 += LX) for (int z = 0; z < d; ++z) {
+                    int mx = 0;
+                    for (int ly = 0; ly < LY; ++ly) for (int lx = 0; lx < LX; ++lx) {
+                        const int c = p[(size_t)z * wh + (size_t)(y0 + ly) * w + x0 + lx];
+                        useful += c; mx = std::max(mx, c);
+                    }
+                    issued += 32.0 * mx; npos += 1;
+                }
+            }
+            printf(" %dx%d: %.3f (%.2f)", LX, LY, useful / issued, issued / 32.0 / npos);
+        }
+        printf("\n");
+    }
     return 0;
 }
