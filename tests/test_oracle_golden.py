@@ -85,3 +85,24 @@ def test_paint_invariant_small(oracle):
         m = ((Z - z) ** 2 + (Y - y) ** 2 + (X - x) ** 2) <= R
         out[m] = np.maximum(out[m], R)
     assert np.array_equal(out, from_ridge)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("shape,seed", [((28, 33, 37), 1), ((40, 24, 31), 2), ((17, 50, 23), 3)])
+def test_edt_against_scipy(oracle, shape, seed, inverse):
+    """Independent pin of the EDT restatement: SciPy's exact Euclidean distance transform (a different
+    algorithm and code base) gives the same squared distances wherever the volume has background; the
+    sentinel 3 (n + 1)^2 of EDT_S1D only appears when there is none."""
+    ndi = pytest.importorskip("scipy.ndimage")
+    vol = shapes.random_blobs(shape, seed)
+    _, sq = oracle.edt(vol, inverse=inverse)
+    fg = (vol < 128) if inverse else (vol >= 128)
+    assert (~fg).any()
+    want = np.rint(ndi.distance_transform_edt(fg) ** 2).astype(np.int64)
+    assert np.array_equal(sq.astype(np.int64), want)
+
+
+def test_edt_without_background_is_the_sentinel(oracle):
+    vol = np.full((5, 6, 7), 255, np.uint8)
+    _, sq = oracle.edt(vol)
+    assert (sq == 3 * (7 + 1) ** 2).all()          # n = the largest extent (SURVEY.md A.1)
