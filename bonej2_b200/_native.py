@@ -93,6 +93,8 @@ _SIGS = {
     "bjt_debug_set_paint_limits": ([_VP, _I, _I], _I),
     "bjt_debug_paint_redo_lines": ([_VP], C.c_int64),
     "bjt_debug_set_xslab_cols": ([_I], _I),
+    "bjt_paint_block_cols": ([_I, _I, _I], _I),
+    "bjt_paint_set_block_cols": ([_I], _I),
     "bjt_host_alloc": ([C.c_size_t], _VP),
     "bjt_host_free": ([_VP], None),
     "bjt_thickness_u8": ([_VP, _VP, _I, _I, _I, _I, _I, _I, _D, _VP, C.POINTER(Stats), C.POINTER(Timing)], _I),
@@ -249,6 +251,20 @@ class Context:
     def debug_set_xslab_cols(cols=0):
         if lib().bjt_debug_set_xslab_cols(int(cols)) != 0:
             raise ValueError("x-slab width must be a non-negative multiple of 32")
+
+    @staticmethod
+    def paint_block_cols(w, h, d) -> int:
+        """column-block width the painter chooses for a w x h x d volume (not clipped to w)"""
+        v = lib().bjt_paint_block_cols(int(w), int(h), int(d))
+        if v <= 0:
+            raise ValueError("paint_block_cols: non-positive volume size")
+        return int(v)
+
+    @staticmethod
+    def paint_set_block_cols(cols=0):
+        """use this column-block width (multiple of 32; 0 = the library's choice); process-wide"""
+        if lib().bjt_paint_set_block_cols(int(cols)) != 0:
+            raise ValueError("column-block width must be a non-negative multiple of 32")
 
     def debug_paint_redo_lines(self) -> int:
         return int(lib().bjt_debug_paint_redo_lines(self._h))

@@ -195,11 +195,18 @@ int bjt_debug_set_paint_limits(bjt_ctx *c, int active_cap, int front_cap) {
     return BJT_OK;
 }
 
-int bjt_debug_set_xslab_cols(int cols) {
+int bjt_paint_block_cols(int w, int h, int d) {
+    if (w <= 0 || h <= 0 || d <= 0) return BJT_E_ARG;
+    return paint_sep_natural_xslab_cols(h, d);
+}
+
+int bjt_paint_set_block_cols(int cols) {
     if (cols < 0 || (cols % 32) != 0) return BJT_E_ARG;
     paint_sep_set_xslab_cols(cols);
     return BJT_OK;
 }
+
+int bjt_debug_set_xslab_cols(int cols) { return bjt_paint_set_block_cols(cols); }
 
 int64_t bjt_debug_paint_redo_lines(bjt_ctx *c) {
     if (!c) return -1;

@@ -62,7 +62,8 @@ int launch_fill_u32(uint32_t *p, size_t n, uint32_t v, cudaStream_t s);
 // separable paint (paths 0/1), see paint_sep.cu
 size_t paint_sep_workspace_bytes(int w, int h, int d, int wide);
 void paint_sep_set_limits(int cap, int fmax);          // test hook: 0 = default
-void paint_sep_set_xslab_cols(int cols);               // test hook: 0 = default (process-wide)
+void paint_sep_set_xslab_cols(int cols);               // 0 = the library's choice (process-wide)
+int paint_sep_natural_xslab_cols(int h, int d);        // the library's choice for slabs of h x d per column, unclipped
 unsigned long long paint_sep_redo_lines(const void *workspace);
 int launch_paint_sep(const uint32_t *ridge, int w, int h, int d, int wide, void *workspace, uint32_t *rsq,
                      uint32_t *overflow_flag, cudaStream_t s);

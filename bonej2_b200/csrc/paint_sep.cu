@@ -37,14 +37,17 @@ namespace {
 // x-slab width of stages 2 and 3: as many columns as keep a slab at or below 2^29 voxels (the item pool of
 // stage 2 is sized per slab voxel), at least 512 -- thin z-slabs of a sharded run get the whole width, which
 // keeps the y-stage grid (columns x planes lines) large enough to fill the GPU
-int g_xslab_override = 0;               // test hook (paint_sep_set_xslab_cols)
-inline int xslab_cols(int w, int h, int d) {
-    if (g_xslab_override > 0) return g_xslab_override < w ? g_xslab_override : w;
+int g_xslab_override = 0;               // paint_sep_set_xslab_cols: the ranks of a sharded run agree on one width; tests
+inline int natural_xslab_cols(int h, int d) {          // not clipped to the width of the volume
     const long long per_col = (long long)h * d;
     long long xc = (1ll << 29) / (per_col > 0 ? per_col : 1);
     xc = xc / 128 * 128;
     if (xc < 512) xc = 512;
-    return xc < w ? (int)xc : w;
+    return xc < (1 << 20) ? (int)xc : (1 << 20);
+}
+inline int xslab_cols(int w, int h, int d) {
+    const int xc = g_xslab_override > 0 ? g_xslab_override : natural_xslab_cols(h, d);
+    return xc < w ? xc : w;
 }
 constexpr unsigned long long OFF_MASK = (1ull << 40) - 1ull;
 constexpr int TPB = 128;                // threads per block of the line kernels
@@ -565,6 +568,7 @@ int run_sep(const uint32_t *ridge, int w, int h, int d, const Plan &p, char *ws,
 }  // namespace
 
 void paint_sep_set_xslab_cols(int cols) { g_xslab_override = cols; }
+int paint_sep_natural_xslab_cols(int h, int d) { return natural_xslab_cols(h, d); }
 
 void paint_sep_set_limits(int cap, int fmax) {
     const int c = cap > 0 ? cap : 1 << 30, f = fmax > 0 ? fmax : 1 << 30;

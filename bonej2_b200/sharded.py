@@ -228,6 +228,14 @@ class CudaStages:
     def paint_xslab_cols(self, xs):
         return self.ctx.dev_paint_xslab_width(xs) * self._ps[0].shape[1]
 
+    def paint_block_cols(self, shape):
+        """column-block width the library would choose for a slab of this shape (not clipped to the width)"""
+        dz, h, w = shape
+        return self.ctx.paint_block_cols(w, h, dz)
+
+    def paint_set_block_cols(self, cols):
+        self.ctx.paint_set_block_cols(cols)
+
     def paint_lists(self, xs):
         self.ctx.dev_paint_lists(xs)
 
@@ -313,6 +321,17 @@ def plane_costs(comm: Comm, stages, ridge_own, zs):
     return [x for part in parts for x in part]
 
 
+NO_BLOCK_PREFERENCE = 1 << 20   # column-block width a rank without planes proposes (a multiple of 32 above any width)
+def even_block_cols(w: int, limit: int, quantum: int = 128) -> int:
+    """column-block width <= limit that cuts a width of w into blocks of (nearly) equal size: 1024 columns under a
+    limit of 896 become 2 x 512, not 896 + 128 (a narrow last block leaves the GPU mostly idle)"""
+    if limit >= w:
+        return limit
+    nblocks = -(-w // limit)
+    even = -(-(-(-w // nblocks)) // quantum) * quantum
+    return min(limit, even)
+
+
 BOUNDARY_KCAP = 32          # staircase steps per column a slab face can carry (more: fall back to the halo repaint)
 MAX_SOURCES = 4             # slabs per side a sweep can import from (bjt_dev_paint_sweep)
 
@@ -338,6 +357,14 @@ def paint_exchange(stages, comm: Comm, ridge_own, zs, gmax, kcap=BOUNDARY_KCAP, 
                    sum(1 for p in range(q + 1, G) if within(p, q)) > MAX_SOURCES for q in range(G))
     if too_many:
         return None
+    # Stages 2-3 run per block of columns and staircases are exchanged per block, so every rank must cut the
+    # width the same way -- but the library sizes the blocks by the slab's own volume, and slabs differ in
+    # thickness (uneven division, the cost-balanced split): agree on the narrowest choice.
+    agreed = hasattr(stages, "paint_block_cols")
+    if agreed:
+        mine = stages.paint_block_cols(tuple(ridge_own.shape)) if z1 > z0 else NO_BLOCK_PREFERENCE
+        narrowest = -comm.allreduce_max_int(-int(mine), ridge_own.device)
+        stages.paint_set_block_cols(even_block_cols(int(ridge_own.shape[2]), narrowest))
     flags = 0
     out = None
     t_ = time.perf_counter
@@ -349,33 +376,37 @@ def paint_exchange(stages, comm: Comm, ridge_own, zs, gmax, kcap=BOUNDARY_KCAP, 
             timings[name] = timings.get(name, 0.0) + (t_() - t0)
         return t_()
 
-    if z1 > z0:
-        t0 = t_()
-        nxs = stages.paint_open(ridge_own, gmax)
-        t0 = mark("paint.x_stage", t0)
-        for xs in range(nxs):
-            ncol = stages.paint_xslab_cols(xs)
-            stages.paint_lists(xs)
-            t0 = mark("paint.y_stage", t0)
-            sends, recvs, lo, hi = {}, {}, [], []
-            for p in range(G):
-                if p == r:
-                    continue
-                gap = within(r, p)
-                if gap:                                                   # what I carry across to slab p
-                    buf = stages.boundary_buffer(ncol, kcap)
-                    stages.paint_export(xs, +1 if p > r else -1, gap, nplanes, buf, ncol, kcap)
-                    sends[p] = buf
-                if within(p, r):                                          # what slab p carries across to me
-                    recvs[p] = stages.boundary_buffer(ncol, kcap)
-                    (lo if p < r else hi).append(recvs[p])
-            t0 = mark("paint.export", t0)
-            comm.exchange(sends, recvs)
-            t0 = mark("paint.exchange", t0)
-            stages.paint_sweep(xs, lo, hi, ncol, kcap)
-            t0 = mark("paint.z_stage", t0)
-            del sends, recvs, lo, hi
-        out, flags = stages.paint_close()
+    try:
+        if z1 > z0:
+            t0 = t_()
+            nxs = stages.paint_open(ridge_own, gmax)
+            t0 = mark("paint.x_stage", t0)
+            for xs in range(nxs):
+                ncol = stages.paint_xslab_cols(xs)
+                stages.paint_lists(xs)
+                t0 = mark("paint.y_stage", t0)
+                sends, recvs, lo, hi = {}, {}, [], []
+                for p in range(G):
+                    if p == r:
+                        continue
+                    gap = within(r, p)
+                    if gap:                                                   # what I carry across to slab p
+                        buf = stages.boundary_buffer(ncol, kcap)
+                        stages.paint_export(xs, +1 if p > r else -1, gap, nplanes, buf, ncol, kcap)
+                        sends[p] = buf
+                    if within(p, r):                                          # what slab p carries across to me
+                        recvs[p] = stages.boundary_buffer(ncol, kcap)
+                        (lo if p < r else hi).append(recvs[p])
+                t0 = mark("paint.export", t0)
+                comm.exchange(sends, recvs)
+                t0 = mark("paint.exchange", t0)
+                stages.paint_sweep(xs, lo, hi, ncol, kcap)
+                t0 = mark("paint.z_stage", t0)
+                del sends, recvs, lo, hi
+            out, flags = stages.paint_close()
+    finally:
+        if agreed:
+            stages.paint_set_block_cols(0)
     flags = comm.allreduce_max_int(int(flags != 0), ridge_own.device)
     if flags:
         return None

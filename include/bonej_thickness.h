@@ -69,7 +69,15 @@ int64_t bjt_launch_count(const bjt_ctx *ctx);
 /* test hook: cap the fast painter kernels' per-line capacities (0 = default) so that small volumes exercise
  * the redo kernels; results must not change */
 int  bjt_debug_set_paint_limits(bjt_ctx *ctx, int active_cap, int front_cap);
-/* test hook, process-wide: width of the painter's column blocks (multiple of 32; 0 = default) */
+/* The painter runs its y and z stages per block of columns, sized by the volume of the block (the lists of
+ * a block are held at once).  bjt_paint_block_cols: the width the library chooses for a w x h x d volume, not
+ * clipped to w (a multiple of 128, at least 512; no device needed).  bjt_paint_set_block_cols: use this width
+ * instead (a multiple of 32; 0 = the library's choice again); process-wide.  The ranks of a z-slab sharded run
+ * exchange boundary staircases per block, so they must agree on the width although their slabs may differ in
+ * thickness: bonej2_b200/sharded.py sets the smallest of the ranks' choices on every rank. */
+int  bjt_paint_block_cols(int w, int h, int d);
+int  bjt_paint_set_block_cols(int cols);
+/* test hook: the same call under its older name */
 int  bjt_debug_set_xslab_cols(int cols);
 /* lines the last separable paint of this context sent to its redo kernels */
 int64_t bjt_debug_paint_redo_lines(bjt_ctx *ctx);

@@ -50,3 +50,17 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "lt_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f
+
+
+def test_paint_block_cols_is_a_host_function():
+    """the column-block width rule needs no device (sharded runs query it to agree on one width)"""
+    from bonej2_b200 import _native
+    C = _native.Context
+    assert C.paint_block_cols(1024, 1024, 1024) == 512          # 2^29 voxels per block
+    assert C.paint_block_cols(1024, 1024, 128) == 4096          # not clipped to the width
+    assert C.paint_block_cols(2048, 2048, 256) == 1024 and C.paint_block_cols(2048, 2048, 300) == 768
+    assert C.paint_block_cols(64, 64, 64) % 128 == 0
+    with pytest.raises(ValueError):
+        C.paint_set_block_cols(100)                             # multiples of 32 only
+    C.paint_set_block_cols(512)
+    C.paint_set_block_cols(0)

@@ -26,7 +26,14 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, vol_path, out_dir, inverse, mask, paint_mode, kcap=None):
+def _thicker_slab_narrower_blocks(dz, h, w):
+    """stand-in for the library's rule (column blocks sized by the slab's volume) at test scale: ranks whose slabs
+    differ in thickness prefer different widths, as they do at 2048^3 on 8 GPUs, or at 1024^3 on 2 once the painter's
+    split is cost-balanced"""
+    return max(3, 40 // max(dz, 1))
+
+
+def _worker(rank, world, port, vol_path, out_dir, inverse, mask, paint_mode, kcap=None, blocks=False):
     sys.path.insert(0, ROOT)
     from bonej2_b200 import sharded
     from tests.sharded_cpu_backend import OracleStages
@@ -37,25 +44,28 @@ def _worker(rank, world, port, vol_path, out_dir, inverse, mask, paint_mode, kca
     slab = torch.from_numpy(vol[zs[rank][0]:zs[rank][1]].copy())
     comm = sharded.Comm()
     kw = {} if kcap is None else {"boundary_kcap": kcap}
-    out, stats = sharded.thickness_slab(OracleStages(), comm, slab, (w, h, d), inverse, mask, 0.5, paint_mode=paint_mode, **kw)
+    stages = OracleStages()
+    if blocks:
+        stages.block_rule = _thicker_slab_narrower_blocks
+    out, stats = sharded.thickness_slab(stages, comm, slab, (w, h, d), inverse, mask, 0.5, paint_mode=paint_mode, **kw)
     np.save(os.path.join(out_dir, f"map_{rank}.npy"), out.numpy())
     if rank == 0:
         np.save(os.path.join(out_dir, "stats.npy"), np.array([stats["count"], stats["mean"], stats["sd"], stats["min"], stats["max"]]))
     dist.destroy_process_group()
 
 
-def _run(vol, inverse, mask, tmp_path, world=2, paint_mode="exchange", kcap=None):
+def _run(vol, inverse, mask, tmp_path, world=2, paint_mode="exchange", kcap=None, blocks=False):
     vol_path = os.path.join(tmp_path, "vol.npy")
     np.save(vol_path, vol)
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, vol_path, str(tmp_path), inverse, mask, paint_mode, kcap), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, vol_path, str(tmp_path), inverse, mask, paint_mode, kcap, blocks), nprocs=world, join=True)
     maps = [np.load(os.path.join(tmp_path, f"map_{r}.npy")) for r in range(world)]
     return np.concatenate(maps, axis=0), np.load(os.path.join(tmp_path, "stats.npy"))
 
 
-def _check(vol, inverse, mask, tmp_path, world=2, paint_mode="exchange", kcap=None):
+def _check(vol, inverse, mask, tmp_path, world=2, paint_mode="exchange", kcap=None, blocks=False):
     from oracle import lt_oracle
-    got, st = _run(vol, inverse, mask, tmp_path, world, paint_mode, kcap)
+    got, st = _run(vol, inverse, mask, tmp_path, world, paint_mode, kcap, blocks)
     ref = lt_oracle.process_image(vol, inverse=inverse, mask=mask, pixel_width=0.5)
     assert np.array_equal(np.isnan(got), np.isnan(ref["map"]))
     ok = ~np.isnan(got)
@@ -117,6 +127,36 @@ def test_two_ranks_no_foreground(tmp_path):
 def test_three_ranks_uneven(tmp_path):
     from tests import shapes
     _check(shapes.random_blobs((11, 7, 9), 5), True, True, str(tmp_path), world=3)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("inverse", [False, True])
+def test_two_ranks_column_blocks_agreed(tmp_path, inverse):
+    """the ranks' slabs differ in thickness (9 / 8 planes, and the cost-balanced split of the painter moves more), so
+    each would cut the width into different column blocks; staircases are exchanged per block, so they have to
+    agree first (sharded.paint_exchange) -- without that the exchange does not even terminate"""
+    from tests import shapes
+    _check(shapes.random_blobs((17, 14, 19), 3), inverse, True, str(tmp_path), paint_mode="exchange", blocks=True)
+
+
+@pytest.mark.timeout(300)
+def test_three_ranks_column_blocks_and_an_empty_slab(tmp_path):
+    from tests import shapes
+    _check(shapes.random_blobs((11, 7, 9), 5), True, True, str(tmp_path), world=3, blocks=True)
+    _check(shapes.random_blobs((2, 9, 8), 2), True, False, str(tmp_path), world=3, paint_mode="exchange", blocks=True)
+
+
+def test_even_block_cols():
+    from bonej2_b200.sharded import even_block_cols
+    assert even_block_cols(1024, 896) == 512
+    assert even_block_cols(1024, 1024) == 1024 and even_block_cols(1024, 1 << 20) == 1 << 20
+    assert even_block_cols(2048, 768) == 768           # 3 blocks: 683 -> 768 (the quantum), not above the limit
+    assert even_block_cols(2048, 896) == 768
+    assert even_block_cols(19, 5) == 5                  # test-scale widths: the limit itself
+    for w in (1000, 1024, 2048, 4096, 8192):
+        for limit in range(512, 4097, 128):
+            c = even_block_cols(w, limit)
+            assert c <= limit and c % 32 == 0 and (c >= w or -(-w // c) == -(-w // limit))
 
 
 def test_split_ranges():
