@@ -332,10 +332,11 @@ __global__ void __launch_bounds__(128) edt_line4_kernel(const TIn *__restrict__ 
 // has reached the running minimum of every lane (one vote per step).  No candidate read leaves the SM,
 // nothing depends on a load from global memory inside the loop, and the results go out as contiguous
 // row pieces straight from registers.  HBM traffic is exactly one read and one write per voxel.
+constexpr int LOADS_IN_FLIGHT = 8;
 constexpr int EDT_PAD = 64;     // sentinel rows on either side of the staged lines: walks up to this distance need no clamping
 
 template <typename TIn, int TX, bool WANT_MAX>
-__global__ void __launch_bounds__(1024) edt_tile_kernel(const TIn *__restrict__ in, uint32_t *__restrict__ out, int groups,
+__global__ void __launch_bounds__(1024, 2) edt_tile_kernel(const TIn *__restrict__ in, uint32_t *__restrict__ out, int groups,
                                                          long long outer, long long stride, int L, uint32_t n0,
                                                          uint32_t *__restrict__ maxval) {
     extern __shared__ uint32_t sm_raw[];                 // [EDT_PAD + L + EDT_PAD][TX]: the pad rows hold BIG (beyond the line)
@@ -346,9 +347,22 @@ __global__ void __launch_bounds__(1024) edt_tile_kernel(const TIn *__restrict__ 
     const uint32_t BIG = 0x3FFFFFFFu;
     uint32_t *sm = sm_raw + EDT_PAD * TX;                // sm[t * TX + xx], t in [-EDT_PAD, L + EDT_PAD)
     for (int i = threadIdx.x; i < EDT_PAD * TX; i += blockDim.x) { sm[-EDT_PAD * TX + i] = BIG; sm[L * TX + i] = BIG; }
-    for (int r0 = warp * RPW; r0 < L; r0 += nwarps * RPW) {
-        const int t = r0 + rsub;
-        if (t < L) sm[t * TX + xx] = f_of(__ldg(in + base + (long long)t * stride + xx), n0);
+    // staging: LOADS_IN_FLIGHT independent loads per thread before the first is used -- with one load per trip a
+    // thread waits a full memory latency for every 2-4 bytes (the profile of that form showed 37 % of the kernel's
+    // samples on the store to shared memory waiting for its load)
+    {
+        const int rstep = nwarps * RPW;
+        const long long pstep = (long long)rstep * stride;
+        const TIn *p = in + base + (long long)(warp * RPW + rsub) * stride + xx;
+        uint32_t *q = sm + (warp * RPW + rsub) * TX + xx;
+        for (int t0 = warp * RPW + rsub; t0 < L; t0 += LOADS_IN_FLIGHT * rstep, p += LOADS_IN_FLIGHT * pstep, q += LOADS_IN_FLIGHT * rstep * TX) {
+            TIn v[LOADS_IN_FLIGHT];
+#pragma unroll
+            for (int u = 0; u < LOADS_IN_FLIGHT; ++u) v[u] = t0 + u * rstep < L ? __ldg(p + u * pstep) : TIn(0);
+#pragma unroll
+            for (int u = 0; u < LOADS_IN_FLIGHT; ++u)
+                if (t0 + u * rstep < L) q[u * rstep * TX] = f_of(v[u], n0);
+        }
     }
     __syncthreads();
     uint32_t tmax = 0;

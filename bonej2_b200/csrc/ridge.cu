@@ -111,7 +111,7 @@ int launch_ridge_template_compact(const uint32_t *values, uint32_t nvalues, uint
 constexpr int RTX = 32, RTY = 8, RTZ = 8;
 constexpr int RHX = RTX + 2, RHY = RTY + 2, RHZ = RTZ + 2;
 
-__global__ void __launch_bounds__(RTX *RTY) ridge_kernel(const uint32_t *__restrict__ sq, int w, int h, int d,
+__global__ void __launch_bounds__(RTX *RTY, 8) ridge_kernel(const uint32_t *__restrict__ sq, int w, int h, int d,
                                                          const uint32_t *__restrict__ t1,
                                                          const uint32_t *__restrict__ t2,
                                                          const uint32_t *__restrict__ t3,
@@ -124,13 +124,31 @@ __global__ void __launch_bounds__(RTX *RTY) ridge_kernel(const uint32_t *__restr
     const size_t wh = (size_t)w * h;
     constexpr int NWARP = (RTX * RTY) / 32, NROW = RHZ * RHY;
     const int gx0 = bx + lane - 1, gx1 = bx + lane + 31;
-    for (int r = warp; r < NROW; r += NWARP) {          // independent iterations: the loads overlap
-        const int lz = r / RHY, ly = r % RHY;
-        const int gy = by + ly - 1, gz = bz + lz - 1;
-        const bool row_in = gy >= 0 && gy < h && gz >= 0 && gz < d;
-        const uint32_t *src = sq + (row_in ? gz * wh + (size_t)gy * w : 0);
-        tile[lz][ly][lane] = (row_in && gx0 >= 0 && gx0 < w) ? __ldg(src + gx0) : 0u;
-        if (lane < 2) tile[lz][ly][32 + lane] = (row_in && gx1 < w) ? __ldg(src + gx1) : 0u;
+    // ROWS_IN_FLIGHT tile rows are requested before the first is stored: with one row per trip the warp waited a
+    // full memory latency per 128 bytes (40 % of the kernel's samples sat on the stores to shared memory)
+    constexpr int ROWS_IN_FLIGHT = 4;
+    for (int r0 = warp; r0 < NROW; r0 += ROWS_IN_FLIGHT * NWARP) {
+        uint32_t va[ROWS_IN_FLIGHT], vb[ROWS_IN_FLIGHT];
+#pragma unroll
+        for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {      // straight-line code: predicated loads, no branch between them
+            const int r = r0 + u * NWARP;
+            const int rr = r < NROW ? r : 0;
+            const int lz = rr / RHY, ly = rr % RHY;
+            const int gy = by + ly - 1, gz = bz + lz - 1;
+            const bool row_in = r < NROW && gy >= 0 && gy < h && gz >= 0 && gz < d;
+            const uint32_t *src = sq + (row_in ? gz * wh + (size_t)gy * w : 0);
+            va[u] = (row_in && gx0 >= 0 && gx0 < w) ? __ldg(src + gx0) : 0u;
+            vb[u] = (lane < 2 && row_in && gx1 < w) ? __ldg(src + gx1) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {
+            const int r = r0 + u * NWARP;
+            if (r < NROW) {
+                const int lz = r / RHY, ly = r % RHY;
+                tile[lz][ly][lane] = va[u];
+                if (lane < 2) tile[lz][ly][32 + lane] = vb[u];
+            }
+        }
     }
     __syncthreads();
     const int x = bx + threadIdx.x, y = by + threadIdx.y;
