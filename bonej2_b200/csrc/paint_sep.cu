@@ -342,7 +342,7 @@ struct StairStore : SepStairLocal<CAP_STAIR> {
 template <> struct FastActive<false> { typedef SepActive<WideStore> T; };
 
 template <bool PACKED, int STAGE, int DIR>
-__global__ void __launch_bounds__(TPB) sep_dyn_kernel(SepArgs a) {
+__global__ void __launch_bounds__(TPB, 9) sep_dyn_kernel(SepArgs a) {
     __shared__ unsigned long long sm[PACKED ? 2 * S_SM * TPB : 1];
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long pl = STAGE == 1 ? sep_patch_line(tid, a.h, a.d) : sep_patch_line(tid, a.xw, a.d);
