@@ -1,0 +1,159 @@
+// harness.cpp -- TEST ONLY: C entry points over the kernels compiled against the CPU emulation of CUDA
+// (tests/cuda_emu/cuda_runtime.h), called from tests/test_kernels_emulated.py through ctypes.  Each function
+// replays what the product's driver (bonej2_b200/csrc/api.cu) does around the same launchers.
+#include "common.cuh"
+
+#include <vector>
+
+namespace bjt {
+alignas(16) uint32_t sm_raw[(128 * 1024) / 4];      // the dynamic shared memory of edt_tile_kernel (budget 100 KB)
+}
+
+using namespace bjt;
+
+#include <sys/mman.h>
+#include <unistd.h>
+
+// Buffers with an inaccessible page directly behind (mode 0) or in front of (mode 1) them: a kernel that reads
+// or writes one element outside an array dies here instead of passing by luck.
+namespace {
+int g_guard_mode = 0;
+struct Guarded {
+    char *map = nullptr, *p = nullptr;
+    size_t map_bytes = 0;
+    explicit Guarded(size_t bytes) {
+        const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+        const size_t body = (bytes + page - 1) / page * page + page;          // at least one whole page of payload
+        map_bytes = body + 2 * page;
+        map = (char *)mmap(nullptr, map_bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (map == MAP_FAILED) abort();
+        mprotect(map, page, PROT_NONE);
+        mprotect(map + page + body, page, PROT_NONE);
+        if (g_guard_mode == 1) p = map + page;                                 // starts right behind the front guard
+        else p = map + page + body - (bytes + 15) / 16 * 16;                   // ends (16-byte aligned) at the back guard
+    }
+    ~Guarded() { munmap(map, map_bytes); }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+}
+
+extern "C" {
+
+void emu_set_guard_mode(int mode) { g_guard_mode = mode; }
+
+// api.cu dev_edt: x, y, z passes; *maxval = largest squared distance
+int emu_edt(const uint8_t *in, int w, int h, int d, int inverse, int thresh, uint32_t *sq, uint32_t *maxval) {
+    const size_t N = (size_t)w * h * d;
+    const int n = w > h ? (w > d ? w : d) : (h > d ? h : d);
+    const uint32_t n0 = no_result(n);
+    Guarded g_in(N), g_gx(N * 2), g_gy(N * 4), g_sq(N * 4);
+    memcpy(g_in.p, in, N);
+    uint32_t mv = 0;
+    int launches = launch_edt_x(g_in.as<uint8_t>(), w, h, d, inverse, thresh, g_gx.as<uint16_t>(), nullptr);
+    launches += launch_edt_y(g_gx.as<uint16_t>(), w, h, d, n0, g_gy.as<uint32_t>(), nullptr);
+    launches += launch_edt_z(g_gy.as<uint32_t>(), w, h, d, n0, g_sq.as<uint32_t>(), nullptr, &mv, nullptr);
+    memcpy(sq, g_sq.p, N * 4);
+    if (maxval) *maxval = mv;
+    return launches;
+}
+
+// api.cu dev_ridge, direct-index thresholds (maxval <= 65536)
+int emu_ridge(const uint32_t *sq, int w, int h, int d, uint32_t maxval, uint32_t *ridge, unsigned long long *count) {
+    if (maxval == 0 || maxval > 65536u) return -1;
+    const size_t N = (size_t)w * h * d;
+    std::vector<uint32_t> t1(maxval + 1, 0), t2(maxval + 1, 0), t3(maxval + 1, 0);
+    Guarded g_sq(N * 4), g_ridge(N * 4);
+    memcpy(g_sq.p, sq, N * 4);
+    unsigned long long c = 0;
+    int launches = launch_ridge_template(nullptr, maxval, t1.data(), t2.data(), t3.data(), nullptr);
+    launches += launch_ridge(g_sq.as<uint32_t>(), w, h, d, t1.data(), t2.data(), t3.data(), g_ridge.as<uint32_t>(), &c, nullptr);
+    memcpy(ridge, g_ridge.p, N * 4);
+    if (count) *count = c;
+    return launches;
+}
+
+// api.cu dev_paint, separable painter: variant bit 0 = u64 items, bit 1 = doubled pools.  *flags != 0: overflow.
+// cap / fmax: the test hook that caps the fast kernels' capacities (0 = default); *redo = lines sent to the redo kernels
+int emu_paint(const uint32_t *ridge, int w, int h, int d, int variant, int xslab_cols, int cap, int fmax, uint32_t *rsq,
+              uint32_t *flags, unsigned long long *redo) {
+    const size_t N = (size_t)w * h * d;
+    paint_sep_set_xslab_cols(xslab_cols);
+    paint_sep_set_limits(cap, fmax);
+    const size_t wb = paint_sep_workspace_bytes(w, h, d, variant);
+    Guarded g_ws(wb), g_ridge(N * 4), g_rsq(N * 4);
+    memset(g_ws.p, 0, wb);
+    memcpy(g_ridge.p, ridge, N * 4);
+    memset(g_rsq.p, 0xAB, N * 4);                       // the painter must write every voxel
+    uint32_t f = 0;
+    const int launches = launch_paint_sep(g_ridge.as<uint32_t>(), w, h, d, variant, g_ws.p, g_rsq.as<uint32_t>(), &f, nullptr);
+    memcpy(rsq, g_rsq.p, N * 4);
+    if (flags) *flags = f;
+    if (redo) *redo = paint_sep_redo_lines(g_ws.p);
+    paint_sep_set_xslab_cols(0);
+    paint_sep_set_limits(0, 0);
+    return launches;
+}
+
+// The painter in steps on several z-slabs of one volume, staircases handed from slab to slab in memory: what
+// bonej2_b200/sharded.py does over NCCL and tests/test_gpu_sharded.py does on one GPU.  cuts: nslab + 1 plane
+// indices; rmax: no ball reaches further (floor(sqrt(max r^2))); variant as above.  Returns overflow flags (0 = fine),
+// -1 when a slab has more than SEP_MAX_SOURCES sources on one side.
+int emu_paint_slabs(const uint32_t *ridge, int w, int h, int d, const int *cuts, int nslab, int rmax, int kcap, int variant,
+                    int xslab_cols, uint32_t *rsq) {
+    const size_t wh = (size_t)w * h;
+    paint_sep_set_xslab_cols(xslab_cols);
+    struct Slab { int z0, dz; Guarded *ws, *ridge, *rsq; uint32_t flags; };
+    std::vector<Slab> S;
+    for (int i = 0; i < nslab; ++i) {
+        Slab sl{cuts[i], cuts[i + 1] - cuts[i], nullptr, nullptr, nullptr, 0u};
+        const size_t n = wh * sl.dz;
+        sl.ws = new Guarded(paint_sep_workspace_bytes(w, h, sl.dz, variant));
+        memset(sl.ws->p, 0, paint_sep_workspace_bytes(w, h, sl.dz, variant));
+        sl.ridge = new Guarded(n * 4); sl.rsq = new Guarded(n * 4);
+        memcpy(sl.ridge->p, ridge + wh * sl.z0, n * 4);
+        memset(sl.rsq->p, 0xAB, n * 4);
+        S.push_back(sl);
+    }
+    for (auto &sl : S) paint_sep_stage1(sl.ridge->as<uint32_t>(), w, h, sl.dz, variant, sl.ws->p, &sl.flags, nullptr);
+    auto gap = [&](int p, int q) {          // from slab p's face plane to slab q's first plane; 0 = out of reach
+        const int g = q > p ? S[q].z0 - (S[p].z0 + S[p].dz - 1) : S[p].z0 - (S[q].z0 + S[q].dz - 1);
+        return g <= rmax ? g : 0;
+    };
+    int rc = 0;
+    const int nxs = paint_sep_nxslabs(w, h, S[0].dz);
+    for (int xs = 0; xs < nxs && rc == 0; ++xs) {
+        const size_t ncol = (size_t)paint_sep_xslab_width(w, h, S[0].dz, xs) * h;
+        for (auto &sl : S) paint_sep_stage2(w, h, sl.dz, variant, sl.ws->p, xs, &sl.flags, nullptr);
+        std::vector<std::vector<Guarded *> > cnt(nslab, std::vector<Guarded *>(nslab, nullptr)), items = cnt;
+        for (int p = 0; p < nslab; ++p) for (int q = 0; q < nslab; ++q) {
+            if (p == q || !gap(p, q)) continue;
+            cnt[p][q] = new Guarded(ncol * 4); items[p][q] = new Guarded(ncol * kcap * 8);
+            paint_sep_export(w, h, S[p].dz, variant, S[p].ws->p, xs, q > p ? +1 : -1, gap(p, q), rmax + 1, cnt[p][q]->as<uint32_t>(),
+                             items[p][q]->as<uint2>(), kcap, &S[p].flags, nullptr);
+        }
+        for (int q = 0; q < nslab; ++q) {
+            SepImports imp{};
+            imp.kcap = kcap;
+            for (int p = 0; p < q; ++p) if (cnt[p][q]) {
+                if (imp.n_lo == SEP_MAX_SOURCES) { rc = -1; break; }
+                imp.lo_cnt[imp.n_lo] = cnt[p][q]->as<uint32_t>(); imp.lo_items[imp.n_lo++] = items[p][q]->as<uint2>();
+            }
+            for (int p = q + 1; p < nslab; ++p) if (cnt[p][q]) {
+                if (imp.n_hi == SEP_MAX_SOURCES) { rc = -1; break; }
+                imp.hi_cnt[imp.n_hi] = cnt[p][q]->as<uint32_t>(); imp.hi_items[imp.n_hi++] = items[p][q]->as<uint2>();
+            }
+            if (rc) break;
+            paint_sep_stage3(w, h, S[q].dz, variant, S[q].ws->p, xs, &imp, S[q].rsq->as<uint32_t>(), &S[q].flags, nullptr);
+        }
+        for (auto &row : cnt) for (auto *g : row) delete g;
+        for (auto &row : items) for (auto *g : row) delete g;
+    }
+    for (auto &sl : S) {
+        if (rc == 0) { memcpy(rsq + wh * sl.z0, sl.rsq->p, wh * sl.dz * 4); rc |= (int)sl.flags; }
+        delete sl.ws; delete sl.ridge; delete sl.rsq;
+    }
+    paint_sep_set_xslab_cols(0);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+"""The CUDA kernels' own source, executed on the CPU.  tests/cuda_emu/ compiles bonej2_b200/csrc/{edt,ridge,paint_sep}.cu
+with g++ against a small emulation of the CUDA constructs they use (blocks one after another, the threads of a block
+as fibers, barriers and warp collectives as rendezvous points; every array the kernels see ends or starts at an
+inaccessible page).  What it checks is kernel LOGIC against the oracle without a GPU -- staging loops, tile and
+patch index arithmetic, the warp-aggregated list allocation, redo paths, column blocks -- at sizes the emulation
+finishes in seconds.  It complements, and does not replace, the `-m gpu` parity tests."""
+import numpy as np
+import pytest
+
+from tests import kernels_emu as emu
+from tests import shapes
+
+
+@pytest.fixture(scope="module", params=[0, 1], ids=["guard_behind", "guard_in_front"])
+def guard(request):
+    emu.set_guard_mode(request.param)
+    yield request.param
+    emu.set_guard_mode(0)
+
+
+def _ridge_of(oracle, vol, inverse):
+    dist, sq = oracle.edt(vol, inverse=inverse)
+    rg = oracle.ridge(dist)
+    return rg, np.where(rg > 0, sq, 0).astype(np.uint32), sq
+
+
+# (d, h, w): w = 32 / 64 -> tile kernel (32 columns per block); h or d = 700 -> 16 columns per block (shared-memory
+# budget); w = 12 -> four-column line kernel; w = 13 -> one-thread-per-line kernel; 1100 -> two row segments in the x pass
+EDT_SHAPES = [(9, 20, 32), (5, 33, 64), (1, 700, 32), (700, 1, 32), (7, 9, 12), (6, 5, 13), (3, 4, 1100), (1, 1, 40), (2, 2, 2)]
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("shape", EDT_SHAPES)
+def test_edt_kernels(oracle, guard, shape, inverse):
+    vol = shapes.random_blobs(shape, 7)
+    _, want = oracle.edt(vol, inverse=inverse)
+    got, mx = emu.edt_sq(vol, inverse=inverse)
+    assert np.array_equal(got, want)
+    assert mx == int(want.max())
+
+
+@pytest.mark.parametrize("shape", [(1, 200, 32), (200, 1, 32), (1, 1, 300)])
+def test_edt_kernels_far_from_the_background(oracle, guard, shape):
+    """a single background voxel: the y / z walks run far beyond the 64 sentinel rows either side of the staged lines"""
+    vol = np.full(shape, 255, np.uint8)
+    vol[0, 0, 3] = 0
+    _, want = oracle.edt(vol)
+    got, mx = emu.edt_sq(vol)
+    assert np.array_equal(got, want) and mx == int(want.max())
+
+
+def test_edt_kernels_no_background_and_no_foreground(oracle, guard):
+    full = np.full((4, 6, 32), 255, np.uint8)
+    got, mx = emu.edt_sq(full)
+    assert (got == 3 * 33 * 33).all() and mx == 3 * 33 * 33
+    got, mx = emu.edt_sq(np.zeros((4, 6, 32), np.uint8))
+    assert not got.any() and mx == 0
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("shape", [(9, 20, 32), (11, 13, 35), (8, 8, 31), (1, 30, 40), (17, 3, 5)])
+def test_ridge_kernel(oracle, guard, shape, inverse):
+    vol = shapes.random_blobs(shape, 5)
+    _, want, sq = _ridge_of(oracle, vol, inverse)
+    if not sq.any():
+        pytest.skip("no foreground")
+    got, count = emu.ridge(sq.astype(np.uint32))
+    assert np.array_equal(got, want)
+    assert count == int((want > 0).sum())
+
+
+# partial 8 x 4 patches of lines in every stage (extents that are not multiples of 8 / 4), one line, one plane
+PAINT_SHAPES = [(9, 20, 32), (13, 11, 7), (5, 37, 33), (6, 6, 6), (1, 9, 17), (10, 1, 12), (3, 5, 1)]
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("shape", PAINT_SHAPES)
+def test_painter_kernels(oracle, guard, shape, inverse):
+    vol = shapes.random_blobs(shape, 3)
+    rg, ridge, _ = _ridge_of(oracle, vol, inverse)
+    _, want = oracle.paint(rg)
+    got, flags, _ = emu.paint(ridge)
+    assert flags == 0 and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_painter_kernels_wide_items_and_doubled_pools(oracle, guard, variant):
+    vol = shapes.random_blobs((12, 14, 18), 9)
+    rg, ridge, _ = _ridge_of(oracle, vol, True)
+    _, want = oracle.paint(rg)
+    got, flags, _ = emu.paint(ridge, variant=variant)
+    assert flags == 0 and np.array_equal(got, want)
+
+
+def test_painter_kernels_column_blocks(oracle, guard):
+    """stages 2-3 per block of 32 columns: 32 + 32 + 6"""
+    vol = shapes.random_blobs((6, 9, 70), 4)
+    rg, ridge, _ = _ridge_of(oracle, vol, True)
+    _, want = oracle.paint(rg)
+    got, flags, _ = emu.paint(ridge, xslab_cols=32)
+    assert flags == 0 and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("caps", [(2, 1), (3, 2)])
+def test_painter_kernels_redo_paths(oracle, guard, caps):
+    """capacities of the fast kernels capped: lines are redone by the kernels with global scratch, same map"""
+    from bonej2_b200.phantom import phantom_shapes
+    vol = oracle.phantom_raster(phantom_shapes(24, 24, 24, 1), 24, 24, 24)
+    for inverse in (False, True):
+        rg, ridge, _ = _ridge_of(oracle, vol, inverse)
+        _, want = oracle.paint(rg)
+        got, flags, redo = emu.paint(ridge, cap=caps[0], fmax=caps[1])
+        assert flags == 0 and np.array_equal(got, want)
+        if inverse:
+            assert redo > 10
+
+
+@pytest.mark.parametrize("cuts,xcols", [((0, 9, 17), 0), ((0, 4, 8, 12, 17), 0), ((0, 6, 17), 32), ((0, 1, 2, 17), 0)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_painter_kernels_on_z_slabs(oracle, guard, cuts, xcols, inverse):
+    """the stepwise painter (x / y stages per slab, boundary staircases exported and imported, z sweeps) on slabs of
+    one volume -- also slabs thinner than the largest ball and column blocks -- equals the whole-volume painting"""
+    import math
+    vol = shapes.random_blobs((17, 14, 40), 3)
+    rg, ridge, _ = _ridge_of(oracle, vol, inverse)
+    _, want = oracle.paint(rg)
+    got, rc = emu.paint_slabs(ridge, cuts, math.isqrt(int(ridge.max())), xslab_cols=xcols)
+    assert rc == 0 and np.array_equal(got, want)
+
+
+def test_whole_chain_on_a_phantom(oracle, guard):
+    """EDT -> ridge -> paint, each kernel fed by the one before it"""
+    from bonej2_b200.phantom import phantom_shapes
+    vol = oracle.phantom_raster(phantom_shapes(32, 32, 32, 2), 32, 32, 32)
+    for inverse in (False, True):
+        o = oracle.process_image(vol, inverse=inverse, mask=False, taps=True)
+        sq, mx = emu.edt_sq(vol, inverse=inverse)
+        assert np.array_equal(sq, o["sq"])
+        if mx == 0:
+            continue
+        rg, n = emu.ridge(sq)
+        got, flags, _ = emu.paint(rg)
+        _, want = oracle.paint(o["ridge"]) if "ridge" in o else (None, None)
+        if want is not None:
+            assert flags == 0 and np.array_equal(got, want)
