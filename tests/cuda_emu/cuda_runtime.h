@@ -207,6 +207,12 @@ template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned delta) {
     const unsigned long long *s = emu::warp_gather(emu_bits(v));
     return lane + (int)delta < 32 ? emu_unbits<T>(s[lane + (int)delta]) : v;
 }
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+    const int lane = emu_lane();
+    const unsigned long long *s = emu::warp_gather(emu_bits(v));
+    return emu_unbits<T>(s[(lane ^ lane_mask) & 31]);
+}
+inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
 inline unsigned __ballot_sync(unsigned, int pred) {
     const unsigned long long *s = emu::warp_gather(pred ? 1ull : 0ull);
     unsigned m = 0;

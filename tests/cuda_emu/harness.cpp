@@ -94,6 +94,25 @@ int emu_paint(const uint32_t *ridge, int w, int h, int d, int variant, int xslab
     return launches;
 }
 
+// api.cu dev_finish_range: 2 sqrt, cleanup, mask, NaN / calibration and statistics of planes [z_lo, z_hi).
+// original may be null (mask off).  res = sum, sum2, min, max, count of the non-NaN voxels.
+int emu_finish(const uint32_t *rsq, const uint8_t *original, int w, int h, int d, int z_lo, int z_hi, int inverse, int calibrate,
+               float pixel_width, float *out, double *res) {
+    const size_t N = (size_t)w * h * d, M = (size_t)w * h * (z_hi - z_lo);
+    const int np = finish_partials(w, h, z_hi - z_lo);
+    Guarded g_rsq(N * 4), g_org(N), g_out(M * 4), g_part((size_t)np * sizeof(StatsPartial)), g_res(sizeof(StatsPartial));
+    memcpy(g_rsq.p, rsq, N * 4);
+    if (original) memcpy(g_org.p, original, N);
+    memset(g_out.p, 0xAB, M * 4);
+    const int launches = launch_finish(g_rsq.as<uint32_t>(), original ? g_org.as<uint8_t>() : nullptr, w, h, d, z_lo, z_hi, inverse,
+                                       calibrate, pixel_width, g_out.as<float>(), g_part.as<StatsPartial>(), np,
+                                       g_res.as<StatsPartial>(), nullptr);
+    memcpy(out, g_out.p, M * 4);
+    const StatsPartial r = *g_res.as<StatsPartial>();
+    res[0] = r.sum; res[1] = r.sum2; res[2] = r.mn; res[3] = r.mx; res[4] = (double)r.count;
+    return launches;
+}
+
 // The painter in steps on several z-slabs of one volume, staircases handed from slab to slab in memory: what
 // bonej2_b200/sharded.py does over NCCL and tests/test_gpu_sharded.py does on one GPU.  cuts: nslab + 1 plane
 // indices; rmax: no ball reaches further (floor(sqrt(max r^2))); variant as above.  Returns overflow flags (0 = fine),

@@ -70,3 +70,20 @@ def paint_slabs(ridge_u32, cuts, rmax, kcap=32, variant=0, xslab_cols=0):
     c = np.ascontiguousarray(cuts, np.int32)
     rc = lib().emu_paint_slabs(_p(r), w, h, d, _p(c), len(cuts) - 1, int(rmax), int(kcap), int(variant), int(xslab_cols), _p(out))
     return out, rc
+
+
+def finish(rsq_u32, original_u8, inverse=False, pixel_width=1.0, z_lo=0, z_hi=None):
+    """2 sqrt + cleanup + mask (when original_u8 is given) + NaN / calibration + statistics of planes [z_lo, z_hi):
+    (map float32, dict(sum, sum2, min, max, count))"""
+    r = np.ascontiguousarray(rsq_u32, np.uint32)
+    d, h, w = r.shape
+    z_hi = d if z_hi is None else z_hi
+    o = None if original_u8 is None else np.ascontiguousarray(original_u8, np.uint8)
+    out = np.empty((z_hi - z_lo, h, w), np.float32)
+    res = (C.c_double * 5)()
+    L = lib()
+    L.emu_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                             C.c_void_p, C.POINTER(C.c_double)]
+    rc = L.emu_finish(_p(r), None if o is None else _p(o), w, h, d, z_lo, z_hi, int(inverse), 1, float(pixel_width), _p(out), res)
+    assert rc > 0
+    return out, dict(sum=res[0], sum2=res[1], min=res[2], max=res[3], count=int(res[4]))

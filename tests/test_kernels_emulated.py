@@ -143,3 +143,35 @@ def test_whole_chain_on_a_phantom(oracle, guard):
         _, want = oracle.paint(o["ridge"]) if "ridge" in o else (None, None)
         if want is not None:
             assert flags == 0 and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("mask", [True, False])
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("shape", [(9, 20, 32), (13, 11, 7), (5, 37, 33), (1, 9, 17), (2, 2, 2)])
+def test_finish_kernel(oracle, guard, shape, inverse, mask):
+    """2 sqrt, surface cleanup in the reference's visiting order, mask, NaN background, calibration and the statistics
+    partials: the map within 1e-5 relative of the oracle's (float32, the north star's tolerance) with the same NaN
+    pattern, the count exactly, sums to 1e-5"""
+    vol = shapes.random_blobs(shape, 6)
+    o = oracle.process_image(vol, inverse=inverse, mask=mask, pixel_width=0.5, taps=True)
+    got, st = emu.finish(o["rsq"], vol if mask else None, inverse=inverse, pixel_width=0.5)
+    want = o["map"]
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.allclose(got[ok], want[ok], rtol=1e-5, atol=0)
+    assert st["count"] == o["stats"].count
+    if st["count"]:
+        assert st["sum"] == pytest.approx(o["stats"].sum, rel=1e-5) and st["sum2"] == pytest.approx(o["stats"].sum2, rel=1e-5)
+        assert st["max"] == pytest.approx(o["stats"].max, rel=1e-5) and st["min"] == pytest.approx(o["stats"].min, rel=1e-5)
+
+
+def test_finish_kernel_plane_range(oracle, guard):
+    """output and statistics restricted to planes [z_lo, z_hi) of a slab with halo planes (bjt_dev_finish_range)"""
+    vol = shapes.random_blobs((14, 12, 20), 8)
+    o = oracle.process_image(vol, inverse=True, mask=True, taps=True)
+    got, st = emu.finish(o["rsq"], vol, inverse=True, z_lo=3, z_hi=10)
+    want = o["map"][3:10]
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.allclose(got[ok], want[ok], rtol=1e-5, atol=0)
+    assert st["count"] == int(ok.sum())
