@@ -175,4 +175,79 @@ int emu_paint_slabs(const uint32_t *ridge, int w, int h, int d, const int *cuts,
     return rc;
 }
 
+// ---- the device-level entry points bonej2_b200/sharded.py's CudaStages drives (bjt_dev_* in api.cu), on plain host
+// pointers, so that class can run unchanged on CPU tensors under gloo (tests/test_sharded_emulated.py) ----
+int emu_dev_edt_x(const uint8_t *in, int w, int h, int d, int inverse, int thresh, uint16_t *gx) {
+    return launch_edt_x(in, w, h, d, inverse, thresh, gx, nullptr);
+}
+int emu_dev_edt_y(const uint16_t *gx, int w, int h, int d, int n_sentinel, uint32_t *gy) {
+    return launch_edt_y(gx, w, h, d, no_result(n_sentinel), gy, nullptr);
+}
+int emu_dev_edt_z(const uint32_t *gy, int w, int h, int d, int n_sentinel, uint32_t *sq) {
+    uint32_t mv = 0;
+    return launch_edt_z(gy, w, h, d, no_result(n_sentinel), sq, nullptr, &mv, nullptr);
+}
+int emu_dev_ridge(const uint32_t *sq, int w, int h, int d, uint32_t *ridge) {          // api.cu dev_ridge_full
+    uint32_t maxval = 0;
+    const size_t N = (size_t)w * h * d;
+    for (size_t i = 0; i < N; ++i) maxval = sq[i] > maxval ? sq[i] : maxval;
+    if (maxval == 0) { memset(ridge, 0, N * 4); return 0; }
+    return emu_ridge(sq, w, h, d, maxval, ridge, nullptr);
+}
+int emu_dev_paint(const uint32_t *ridge, int w, int h, int d, uint32_t *rsq) {           // whole slab + halo at once
+    uint32_t flags = 0;
+    const int rc = emu_paint(ridge, w, h, d, 0, 0, 0, 0, rsq, &flags, nullptr);
+    return flags ? -1 : rc;
+}
+
+struct EmuPaintSession { int w, h, d, variant; void *ws; uint32_t flags; };
+
+void *emu_paint_open(const uint32_t *ridge, int w, int h, int d, long long max_rsq) {     // bjt_dev_paint_open
+    EmuPaintSession *S = new EmuPaintSession{w, h, d, max_rsq >= 65536 ? 1 : 0, nullptr, 0u};
+    S->ws = calloc(1, paint_sep_workspace_bytes(w, h, d, S->variant));
+    paint_sep_stage1(ridge, w, h, d, S->variant, S->ws, &S->flags, nullptr);
+    return S;
+}
+int emu_paint_nxslabs(void *h) { EmuPaintSession *S = (EmuPaintSession *)h; return paint_sep_nxslabs(S->w, S->h, S->d); }
+int emu_paint_xslab_width(void *h, int xs) { EmuPaintSession *S = (EmuPaintSession *)h; return paint_sep_xslab_width(S->w, S->h, S->d, xs); }
+int emu_paint_lists(void *h, int xs) {
+    EmuPaintSession *S = (EmuPaintSession *)h;
+    return paint_sep_stage2(S->w, S->h, S->d, S->variant, S->ws, xs, &S->flags, nullptr);
+}
+int emu_paint_export(void *h, int xs, int side, int gap, int nplanes, uint32_t *cnt, void *items, int kcap) {
+    EmuPaintSession *S = (EmuPaintSession *)h;
+    return paint_sep_export(S->w, S->h, S->d, S->variant, S->ws, xs, side, gap, nplanes, cnt, (uint2 *)items, kcap, &S->flags, nullptr);
+}
+int emu_paint_sweep(void *h, int xs, int n_lo, const uint32_t *const *lo_cnt, const void *const *lo_items, int n_hi,
+                    const uint32_t *const *hi_cnt, const void *const *hi_items, int kcap, uint32_t *rsq) {
+    EmuPaintSession *S = (EmuPaintSession *)h;
+    if (n_lo > SEP_MAX_SOURCES || n_hi > SEP_MAX_SOURCES) return -1;
+    SepImports imp{};
+    imp.n_lo = n_lo; imp.n_hi = n_hi; imp.kcap = kcap;
+    for (int i = 0; i < n_lo; ++i) { imp.lo_cnt[i] = lo_cnt[i]; imp.lo_items[i] = (const uint2 *)lo_items[i]; }
+    for (int i = 0; i < n_hi; ++i) { imp.hi_cnt[i] = hi_cnt[i]; imp.hi_items[i] = (const uint2 *)hi_items[i]; }
+    return paint_sep_stage3(S->w, S->h, S->d, S->variant, S->ws, xs, &imp, rsq, &S->flags, nullptr);
+}
+unsigned emu_paint_close(void *h) {
+    EmuPaintSession *S = (EmuPaintSession *)h;
+    const unsigned f = S->flags;
+    free(S->ws);
+    delete S;
+    return f;
+}
+int emu_paint_block_cols(int w, int h, int d) { (void)w; return paint_sep_natural_xslab_cols(h, d); }
+void emu_paint_set_block_cols(int cols) { paint_sep_set_xslab_cols(cols); }
+
+// bjt_dev_finish_range on host pointers; `original` may be null and may point in front of an array (the caller shifts
+// it by z_lo planes, as CudaStages.finish does): no guarded copies here
+int emu_dev_finish_range(const uint32_t *rsq, const uint8_t *original, int w, int h, int d, int z_lo, int z_hi, int inverse,
+                         int calibrate, float pixel_width, float *out, double *res) {
+    const int np = finish_partials(w, h, z_hi - z_lo);
+    std::vector<StatsPartial> part((size_t)np);
+    StatsPartial r;
+    const int launches = launch_finish(rsq, original, w, h, d, z_lo, z_hi, inverse, calibrate, pixel_width, out, part.data(), np, &r, nullptr);
+    res[0] = r.sum; res[1] = r.sum2; res[2] = r.mn; res[3] = r.mx; res[4] = (double)r.count;
+    return launches;
+}
+
 }  // extern "C"

@@ -87,3 +87,97 @@ def finish(rsq_u32, original_u8, inverse=False, pixel_width=1.0, z_lo=0, z_hi=No
     rc = L.emu_finish(_p(r), None if o is None else _p(o), w, h, d, z_lo, z_hi, int(inverse), 1, float(pixel_width), _p(out), res)
     assert rc > 0
     return out, dict(sum=res[0], sum2=res[1], min=res[2], max=res[3], count=int(res[4]))
+
+
+class _FinishStats:
+    def __init__(self, res):
+        self.sum, self.sum2, self.min, self.max, self.count = res[0], res[1], res[2], res[3], int(res[4])
+
+
+class EmuContext:
+    """The subset of bonej2_b200._native.Context that bonej2_b200.sharded.CudaStages calls, served by the kernels on the
+    CPU emulation: CudaStages(EmuContext(), torch.device("cpu")) runs the product's multi-GPU stage code on CPU tensors
+    (their data_ptr() are host addresses).  One process, one painter session at a time, like a bjt_ctx."""
+
+    def __init__(self, block_cols_rule=None):
+        self._L = lib()
+        self._ses = None
+        self._forced = 0
+        self._rule = block_cols_rule          # tests: override of the library's column-block rule (w, h, d) -> width
+        L = self._L
+        L.emu_paint_open.restype = C.c_void_p
+        L.emu_paint_open.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong]
+        for f in (L.emu_paint_nxslabs, L.emu_paint_close):
+            f.argtypes = [C.c_void_p]
+        L.emu_paint_xslab_width.argtypes = [C.c_void_p, C.c_int]
+        L.emu_paint_lists.argtypes = [C.c_void_p, C.c_int]
+        L.emu_paint_export.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.emu_paint_sweep.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.emu_dev_finish_range.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                           C.c_void_p, C.POINTER(C.c_double)]
+        for f in (L.emu_dev_edt_x, L.emu_dev_edt_y, L.emu_dev_edt_z, L.emu_dev_ridge, L.emu_dev_paint):
+            f.argtypes = None
+
+    @staticmethod
+    def _vp(p):
+        return C.c_void_p(int(p))
+
+    def dev_edt_x(self, d_in, w, h, d, inverse, threshold, d_gx):
+        assert self._L.emu_dev_edt_x(self._vp(d_in), w, h, d, int(inverse), int(threshold), self._vp(d_gx)) > 0
+
+    def dev_edt_y(self, d_gx, w, h, d, n_sentinel, d_gy):
+        assert self._L.emu_dev_edt_y(self._vp(d_gx), w, h, d, int(n_sentinel), self._vp(d_gy)) > 0
+
+    def dev_edt_z(self, d_gy, w, h, d, n_sentinel, d_sq):
+        assert self._L.emu_dev_edt_z(self._vp(d_gy), w, h, d, int(n_sentinel), self._vp(d_sq)) > 0
+
+    def dev_ridge(self, d_sq, w, h, d, d_ridge):
+        assert self._L.emu_dev_ridge(self._vp(d_sq), w, h, d, self._vp(d_ridge)) >= 0
+
+    def dev_paint(self, d_ridge, w, h, d, d_rsq, path=-1):
+        assert self._L.emu_dev_paint(self._vp(d_ridge), w, h, d, self._vp(d_rsq)) > 0
+
+    def dev_paint_open(self, d_ridge, w, h, d, max_rsq):
+        assert self._ses is None
+        if self._rule and not self._forced:      # like the library: without a set width, the slab's own choice
+            self._L.emu_paint_set_block_cols(int(self._rule(w, h, d)))
+        self._ses = C.c_void_p(self._L.emu_paint_open(self._vp(d_ridge), w, h, d, int(max_rsq)))
+        return self._L.emu_paint_nxslabs(self._ses)
+
+    def dev_paint_xslab_width(self, xs):
+        return self._L.emu_paint_xslab_width(self._ses, xs)
+
+    def dev_paint_lists(self, xs):
+        assert self._L.emu_paint_lists(self._ses, xs) > 0
+
+    def dev_paint_export(self, xs, side, gap, nplanes, d_count, d_items, kcap):
+        assert self._L.emu_paint_export(self._ses, xs, side, gap, nplanes, self._vp(d_count), self._vp(d_items), kcap) > 0
+
+    def dev_paint_sweep(self, xs, lo, hi, kcap, d_rsq):
+        def arr(pairs, k):
+            a = (C.c_void_p * max(1, len(pairs)))()
+            for i, pr in enumerate(pairs):
+                a[i] = int(pr[k])
+            return a
+        assert self._L.emu_paint_sweep(self._ses, xs, len(lo), arr(lo, 0), arr(lo, 1), len(hi), arr(hi, 0), arr(hi, 1), kcap,
+                                       self._vp(d_rsq)) > 0
+
+    def dev_paint_close(self):
+        f = self._L.emu_paint_close(self._ses)
+        self._ses = None
+        self._L.emu_paint_set_block_cols(self._forced)
+        return int(f)
+
+    def paint_block_cols(self, w, h, d):
+        return int(self._rule(w, h, d)) if self._rule else int(self._L.emu_paint_block_cols(w, h, d))
+
+    def paint_set_block_cols(self, cols):
+        self._forced = int(cols)
+        self._L.emu_paint_set_block_cols(int(cols))
+
+    def dev_finish_range(self, d_rsq, d_original, w, h, d, z_lo, z_hi, inverse, calibrate, pixel_width, d_out):
+        res = (C.c_double * 5)()
+        o = None if d_original is None else self._vp(d_original)
+        assert self._L.emu_dev_finish_range(self._vp(d_rsq), o, w, h, d, int(z_lo), int(z_hi), int(inverse), int(calibrate),
+                                            float(pixel_width), self._vp(d_out), res) > 0
+        return _FinishStats(res)

@@ -1,0 +1,94 @@
+"""The product's multi-GPU stage code on the CPU: bonej2_b200.sharded.CudaStages -- the class that drives the CUDA
+kernels through the C-ABI on a GPU box -- runs here unchanged on CPU tensors, with the kernels served by their
+CPU emulation (tests/kernels_emu.EmuContext), two or three ranks over gloo.  Together with the oracle-backed backend
+of tests/test_sharded_cpu.py this covers what a multi-GPU run does except NCCL and the hardware: slab-local EDT
+passes on u16 / u32 buffers, transposes, the ridge on fetched planes, the cost-balanced split with the product's own
+cost model, agreement on the column-block width, boundary buffers in the kernels' layout, the finish kernel on a
+plane range with a shifted original pointer, statistics combination."""
+import math
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _narrow_blocks(w, h, d):
+    """stand-in for the library's rule at test scale: thicker slab, narrower column blocks (multiples of 8); slabs
+    that differ by one plane already differ in width, as the odd plane counts of the tests guarantee"""
+    return 8 * max(1, 13 - d)
+
+
+def _worker(rank, world, port, vol_path, out_dir, inverse, mask, paint_mode, blocks):
+    sys.path.insert(0, ROOT)
+    from bonej2_b200 import sharded
+    from tests.kernels_emu import EmuContext
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    vol = np.load(vol_path)
+    d, h, w = vol.shape
+    zs = sharded.split_ranges(d, world)
+    slab = torch.from_numpy(vol[zs[rank][0]:zs[rank][1]].copy())
+    stages = sharded.CudaStages(EmuContext(_narrow_blocks if blocks else None), torch.device("cpu"))
+    timings = {}
+    out, stats = sharded.thickness_slab(stages, sharded.Comm(), slab, (w, h, d), inverse, mask, 0.5, timings=timings,
+                                        paint_mode=paint_mode)
+    np.save(os.path.join(out_dir, f"map_{rank}.npy"), out.numpy())
+    if rank == 0:
+        np.save(os.path.join(out_dir, "stats.npy"), np.array([stats["count"], stats["mean"], stats["sd"], stats["min"], stats["max"]]))
+        np.save(os.path.join(out_dir, "stages.npy"), np.array(sorted(timings)))
+    dist.destroy_process_group()
+
+
+def _check(vol, inverse, mask, tmp_path, world=2, paint_mode="exchange", blocks=False):
+    from oracle import lt_oracle
+    vol_path = os.path.join(tmp_path, "vol.npy")
+    np.save(vol_path, vol)
+    mp.spawn(_worker, args=(world, _free_port(), vol_path, str(tmp_path), inverse, mask, paint_mode, blocks), nprocs=world, join=True)
+    got = np.concatenate([np.load(os.path.join(tmp_path, f"map_{r}.npy")) for r in range(world)], axis=0)
+    st = np.load(os.path.join(tmp_path, "stats.npy"))
+    ref = lt_oracle.process_image(vol, inverse=inverse, mask=mask, pixel_width=0.5)
+    assert np.array_equal(np.isnan(got), np.isnan(ref["map"]))
+    ok = ~np.isnan(got)
+    assert np.allclose(got[ok], ref["map"][ok], rtol=1e-5, atol=0)
+    assert int(st[0]) == ref["stats"].count
+    if ref["stats"].count:
+        assert math.isclose(st[1], ref["stats"].mean, rel_tol=1e-5) and math.isclose(st[4], ref["stats"].max, rel_tol=1e-5)
+    return [str(x) for x in np.load(os.path.join(tmp_path, "stages.npy"))]
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("inverse", [False, True])
+def test_two_ranks_product_stages(tmp_path, inverse):
+    from tests import shapes
+    stages = _check(shapes.random_blobs((18, 14, 40), 3), inverse, True, str(tmp_path))
+    assert "paint.exchange" in stages and "rebalance" in stages                 # the stepwise painter ran, on its own split
+
+
+@pytest.mark.timeout(600)
+def test_two_ranks_product_stages_column_blocks(tmp_path):
+    """ranks whose slabs differ in thickness prefer different column blocks; they agree before exchanging staircases"""
+    from tests import shapes
+    _check(shapes.random_blobs((19, 12, 40), 5), True, True, str(tmp_path), blocks=True)
+
+
+@pytest.mark.timeout(600)
+def test_three_ranks_product_stages_halo_repaint_and_mask_off(tmp_path):
+    from tests import shapes
+    _check(shapes.random_blobs((13, 10, 32), 7), True, False, str(tmp_path), world=3, paint_mode="halo")
+    _check(shapes.random_blobs((13, 10, 32), 7), False, False, str(tmp_path), world=3, paint_mode="auto", blocks=True)
