@@ -175,6 +175,32 @@ int emu_paint_slabs(const uint32_t *ridge, int w, int h, int d, const int *cuts,
     return rc;
 }
 
+// api.cu dev_paint, scatter fallback (path 2): count, compact the ridge points, scatter-max every ball
+int emu_paint_scatter(const uint32_t *ridge, int w, int h, int d, uint32_t *rsq) {
+    const size_t N = (size_t)w * h * d;
+    Guarded g_ridge(N * 4), g_rsq(N * 4);
+    memcpy(g_ridge.p, ridge, N * 4);
+    unsigned long long npts = 0;
+    int launches = launch_compact_ridge(g_ridge.as<uint32_t>(), w, h, d, nullptr, &npts, nullptr);
+    Guarded g_pts((size_t)(npts ? npts : 1) * sizeof(uint4));
+    unsigned long long n2 = 0;
+    memset(g_rsq.p, 0, N * 4);
+    launches += launch_compact_ridge(g_ridge.as<uint32_t>(), w, h, d, g_pts.as<uint4>(), &n2, nullptr);
+    launches += launch_paint_scatter(g_pts.as<uint4>(), npts, w, h, d, g_rsq.as<uint32_t>(), nullptr);
+    memcpy(rsq, g_rsq.p, N * 4);
+    return n2 == npts ? launches : -1;
+}
+
+// bjt_dev_phantom_u8: planes [z0, z0 + dz) of the synthetic phantom
+int emu_phantom(const int32_t *shapes, int nshapes, int w, int h, int d, int z0, int dz, uint8_t *out) {
+    const size_t M = (size_t)w * h * dz;
+    Guarded g_out(M);
+    memset(g_out.p, 0xAB, M);
+    const int launches = launch_phantom(shapes, nshapes, w, h, d, z0, dz, g_out.as<uint8_t>(), nullptr);
+    memcpy(out, g_out.p, M);
+    return launches;
+}
+
 // ---- the device-level entry points bonej2_b200/sharded.py's CudaStages drives (bjt_dev_* in api.cu), on plain host
 // pointers, so that class can run unchanged on CPU tensors under gloo (tests/test_sharded_emulated.py) ----
 int emu_dev_edt_x(const uint8_t *in, int w, int h, int d, int inverse, int thresh, uint16_t *gx) {

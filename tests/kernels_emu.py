@@ -89,6 +89,23 @@ def finish(rsq_u32, original_u8, inverse=False, pixel_width=1.0, z_lo=0, z_hi=No
     return out, dict(sum=res[0], sum2=res[1], min=res[2], max=res[3], count=int(res[4]))
 
 
+def paint_scatter(ridge_u32):
+    """the scatter fallback painter (paint path 2)"""
+    r = np.ascontiguousarray(ridge_u32, np.uint32)
+    d, h, w = r.shape
+    out = np.empty(r.shape, np.uint32)
+    assert lib().emu_paint_scatter(_p(r), w, h, d, _p(out)) > 0
+    return out
+
+
+def phantom(shapes_i32, w, h, d, z0=0, dz=None):
+    s = np.ascontiguousarray(shapes_i32, np.int32)
+    dz = d - z0 if dz is None else dz
+    out = np.empty((dz, h, w), np.uint8)
+    assert lib().emu_phantom(_p(s), int(s.shape[0]), w, h, d, z0, dz, _p(out)) > 0
+    return out
+
+
 class _FinishStats:
     def __init__(self, res):
         self.sum, self.sum2, self.min, self.max, self.count = res[0], res[1], res[2], res[3], int(res[4])

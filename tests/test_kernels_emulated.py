@@ -175,3 +175,22 @@ def test_finish_kernel_plane_range(oracle, guard):
     ok = ~np.isnan(want)
     assert np.allclose(got[ok], want[ok], rtol=1e-5, atol=0)
     assert st["count"] == int(ok.sum())
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("shape", [(9, 20, 32), (13, 11, 7), (1, 9, 17)])
+def test_scatter_painter_kernels(oracle, guard, shape, inverse):
+    """the always-correct fallback (paint path 2): ridge compaction and the literal scatter of every ball"""
+    vol = shapes.random_blobs(shape, 3)
+    rg, ridge, _ = _ridge_of(oracle, vol, inverse)
+    _, want = oracle.paint(rg)
+    assert np.array_equal(emu.paint_scatter(ridge), want)
+
+
+def test_phantom_kernel(oracle, guard):
+    """the device rasteriser of the synthetic phantom equals the CPU one, whole and per z-slab"""
+    from bonej2_b200.phantom import phantom_shapes
+    sh = phantom_shapes(40, 36, 28, 5)
+    want = oracle.phantom_raster(sh, 40, 36, 28)
+    assert np.array_equal(emu.phantom(sh, 40, 36, 28), want)
+    assert np.array_equal(emu.phantom(sh, 40, 36, 28, z0=9, dz=11), want[9:20])
