@@ -92,3 +92,21 @@ def test_three_ranks_product_stages_halo_repaint_and_mask_off(tmp_path):
     from tests import shapes
     _check(shapes.random_blobs((13, 10, 32), 7), True, False, str(tmp_path), world=3, paint_mode="halo")
     _check(shapes.random_blobs((13, 10, 32), 7), False, False, str(tmp_path), world=3, paint_mode="auto", blocks=True)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_single_rank_product_stages(oracle, inverse):
+    """world size 1, in process (what tests/test_gpu_sharded.py::test_single_rank_matches_oracle does on a GPU)"""
+    from bonej2_b200 import sharded
+    from tests import shapes
+    from tests.kernels_emu import EmuContext
+    vol = shapes.random_blobs((11, 13, 24), 2)
+    d, h, w = vol.shape
+    stages = sharded.CudaStages(EmuContext(), torch.device("cpu"))
+    out, st = sharded.thickness_slab(stages, sharded.Comm(), torch.from_numpy(vol.copy()), (w, h, d), inverse, True, 0.7)
+    ref = oracle.process_image(vol, inverse=inverse, mask=True, pixel_width=0.7)
+    got = out.numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(ref["map"]))
+    ok = ~np.isnan(got)
+    assert np.allclose(got[ok], ref["map"][ok], rtol=1e-5, atol=0)
+    assert st["count"] == ref["stats"].count
