@@ -279,11 +279,18 @@ __device__ __forceinline__ bool stair_line(const SepArgs &a, long long line, Sta
     const long long step_in = a.dir > 0 ? in_stride : -in_stride;
     long long vi = in_base + (long long)(a.dir > 0 ? 0 : a.d - 1) * in_stride;
     unsigned long long eF_next = __ldg(a.inF + vi), eB_next = __ldg(a.inB + vi);
+    // the backward sweep keeps the larger of its value and what the forward sweep left: that old value is read one
+    // position ahead, so the comparison at the end of a position does not wait for it (5.6 % of the backward sweep's
+    // samples sat on that comparison).  The line's output voxels belong to this thread alone.
+    uint32_t o_next = 0;
+    if (a.dir < 0) o_next = a.out[out_base + (long long)(a.d - 1) * out_stride];
     for (int step = 0; step < a.d; ++step) {
         const int z = a.dir > 0 ? step : a.d - 1 - step;
         const int u = a.dir > 0 ? z : -z;
         const unsigned long long eF = eF_next, eB = eB_next;
         if (step + 1 < a.d) { vi += step_in; eF_next = __ldg(a.inF + vi); eB_next = __ldg(a.inB + vi); }
+        const uint32_t o_old = o_next;
+        if (a.dir < 0 && step + 1 < a.d) o_next = a.out[out_base + (long long)(z - 1) * out_stride];
         unsigned long long pfF = 0ull, pfB = 0ull;          // index words PF_ITEMS positions ahead (prefetch only)
         if (step + PF_ITEMS < a.d) {
             pfF = __ldg(a.inF + vi + (long long)(PF_ITEMS - 1) * step_in);
@@ -321,7 +328,7 @@ __device__ __forceinline__ bool stair_line(const SepArgs &a, long long line, Sta
         const uint32_t r = S.query(u);
         uint32_t *o = a.out + out_base + (long long)z * out_stride;
         if (a.dir > 0) *o = r;
-        else if (r > *o) *o = r;
+        else if (r > o_old) *o = r;
     }
     return ok;
 }
