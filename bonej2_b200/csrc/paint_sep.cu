@@ -68,18 +68,16 @@ template <bool PACKED> struct ItemIO;
 template <> struct ItemIO<true> {
     typedef uint32_t T;
     static __device__ __forceinline__ T pack(SepItem it) { return (it.R << 16) | it.rho; }
-    static __device__ __forceinline__ SepItem get(const T *p, int k) {
-        const T v = __ldg(p + k);
-        SepItem it; it.rho = v & 0xFFFFu; it.R = v >> 16; return it;
-    }
+    static __device__ __forceinline__ T raw(const T *p, int k) { return __ldg(p + k); }
+    static __device__ __forceinline__ SepItem unpack(T v) { SepItem it; it.rho = v & 0xFFFFu; it.R = v >> 16; return it; }
+    static __device__ __forceinline__ SepItem get(const T *p, int k) { return unpack(raw(p, k)); }
 };
 template <> struct ItemIO<false> {
     typedef uint2 T;
     static __device__ __forceinline__ T pack(SepItem it) { return make_uint2(it.rho, it.R); }
-    static __device__ __forceinline__ SepItem get(const T *p, int k) {
-        const T v = __ldg(p + k);
-        SepItem it; it.rho = v.x; it.R = v.y; return it;
-    }
+    static __device__ __forceinline__ T raw(const T *p, int k) { return __ldg(p + k); }
+    static __device__ __forceinline__ SepItem unpack(T v) { SepItem it; it.rho = v.x; it.R = v.y; return it; }
+    static __device__ __forceinline__ SepItem get(const T *p, int k) { return unpack(raw(p, k)); }
 };
 struct PlainIO { static __device__ __forceinline__ SepItem get(const SepItem *p, int k) { return p[k]; } };
 
@@ -302,9 +300,13 @@ __device__ __forceinline__ bool stair_line(const SepArgs &a, long long line, Sta
             const typename IO::T *p = ipool + (e & OFF_MASK);
             const int cnt = (int)(e >> 40);
             int hint = 0;                                   // tags descend within a list: each search resumes at the last
-            for (int k = 0; k < cnt; ++k) {
-                const SepItem it = IO::get(p, k);
-                ok &= S.arrive(u, it.rho, it.R, hint);
+            if (cnt > 0) {
+                typename IO::T v = IO::raw(p, 0);
+                for (int k = 0; k < cnt; ++k) {             // the next item is on its way while this one is inserted
+                    const SepItem it = IO::unpack(v);
+                    if (k + 1 < cnt) v = IO::raw(p, k + 1);
+                    ok &= S.arrive(u, it.rho, it.R, hint);
+                }
             }
         }
         if (pfF >> 40) prefetch_l1(ipool + (pfF & OFF_MASK));   // the lists of plane z +- PF_ITEMS, into L1
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(32) sep_dyn_redo_kernel(SepArgs a) {
 }
 
 template <bool PACKED>
-__global__ void __launch_bounds__(TPB) sep_stair_kernel(SepArgs a) {
+__global__ void __launch_bounds__(TPB, 12) sep_stair_kernel(SepArgs a) {
     const long long line = sep_patch_line((long long)blockIdx.x * blockDim.x + threadIdx.x, a.xw, a.h);
     if (line < 0) return;
     SepStair<StairStore> S;
