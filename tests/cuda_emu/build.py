@@ -117,5 +117,32 @@ def build(force=False):
     return OUT
 
 
+API_OUT = os.path.join(_OUTDIR, "libbonejthickness_emu.so")
+API_SOURCES = ["api.cu", "edt.cu", "ridge.cu", "paint_sep.cu", "paint_scatter.cu", "finish.cu", "phantom.cu"]
+
+
+def build_api(force=False):
+    """the whole C-ABI (include/bonej_thickness.h, api.cu + thickness_wrapper.cpp) on the emulation, for tests that
+    drive the library's entry points without a GPU"""
+    deps = [os.path.join(_CSRC, f) for f in API_SOURCES + ["common.cuh", "paint_sep_core.cuh", "thickness_wrapper.cpp"]] + \
+           [os.path.join(_HERE, f) for f in ("cuda_runtime.h", "api_stubs.cpp", "build.py")] + \
+           [os.path.join(_ROOT, "include", f) for f in ("bonej_thickness.h", "thickness_wrapper.hpp")]
+    stale = (not os.path.exists(API_OUT)) or any(os.path.getmtime(p) > os.path.getmtime(API_OUT) for p in deps)
+    if not (force or stale):
+        return API_OUT
+    os.makedirs(_OUTDIR, exist_ok=True)
+    srcs = []
+    for name in API_SOURCES:
+        cpp = os.path.join(_OUTDIR, "emuapi_" + name.replace(".cu", ".cpp"))
+        with open(cpp, "w") as f:
+            f.write(translate(name))
+        srcs.append(cpp)
+    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w", "-I", _HERE, "-I", _CSRC, "-I", os.path.join(_ROOT, "include"),
+           "-o", API_OUT] + srcs + [os.path.join(_CSRC, "thickness_wrapper.cpp"), os.path.join(_HERE, "api_stubs.cpp"), "-lpthread"]
+    subprocess.check_call(cmd)
+    return API_OUT
+
+
 if __name__ == "__main__":
+    print(build_api(force=True))
     print(build(force=True))

@@ -47,6 +47,41 @@ typedef int cudaError_t;
 enum { cudaSuccess = 0 };
 typedef void *cudaStream_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+// ---- the runtime calls of the host driver (api.cu): one "device", memory = the heap, streams and events = bookkeeping ----
+#include <time.h>
+enum { cudaStreamNonBlocking = 1 };
+struct emu_event { double ms; };
+typedef emu_event *cudaEvent_t;
+struct cudaDeviceProp { char name[256]; int multiProcessorCount, major, minor; };
+inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
+    memset(p, 0, sizeof *p);
+    strcpy(p->name, "CPU emulation (tests/cuda_emu)");
+    p->multiProcessorCount = 1; p->major = 0; p->minor = 0;
+    return cudaSuccess;
+}
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline const char *cudaGetErrorString(cudaError_t) { return "emulated CUDA runtime"; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (cudaStream_t)(uintptr_t)1; return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emu_event{0.0}; return cudaSuccess; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    e->ms = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    return cudaSuccess;
+}
+inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->ms - a->ms); return cudaSuccess; }
+template <class T> inline cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : 2; }
+inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+template <class T> inline cudaError_t cudaMallocHost(T **p, size_t n) { *p = (T *)aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : 2; }
+inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemGetInfo(size_t *free_b, size_t *total_b) { *free_b = (size_t)64 << 30; *total_b = (size_t)64 << 30; return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(dst, src, n); return cudaSuccess; }
+
 #define cudaFuncSetAttribute(...) 0
 #define cudaMemsetAsync(p, v, n, s) (memset((p), (v), (n)), 0)
 #define cudaMemcpyToSymbol(sym, src, n) (memcpy(&(sym), (src), (n)), 0)

@@ -18,6 +18,13 @@ def guard(request):
     emu.set_guard_mode(0)
 
 
+@pytest.fixture(scope="module")
+def guard_behind():
+    """the painter's lists live inside one workspace allocation, so a second guard position buys little there"""
+    emu.set_guard_mode(0)
+    yield 0
+
+
 def _ridge_of(oracle, vol, inverse):
     dist, sq = oracle.edt(vol, inverse=inverse)
     rg = oracle.ridge(dist)
@@ -75,7 +82,7 @@ PAINT_SHAPES = [(9, 20, 32), (13, 11, 7), (5, 37, 33), (6, 6, 6), (1, 9, 17), (1
 
 @pytest.mark.parametrize("inverse", [False, True])
 @pytest.mark.parametrize("shape", PAINT_SHAPES)
-def test_painter_kernels(oracle, guard, shape, inverse):
+def test_painter_kernels(oracle, guard_behind, shape, inverse):
     vol = shapes.random_blobs(shape, 3)
     rg, ridge, _ = _ridge_of(oracle, vol, inverse)
     _, want = oracle.paint(rg)
@@ -84,7 +91,7 @@ def test_painter_kernels(oracle, guard, shape, inverse):
 
 
 @pytest.mark.parametrize("variant", [1, 2, 3])
-def test_painter_kernels_wide_items_and_doubled_pools(oracle, guard, variant):
+def test_painter_kernels_wide_items_and_doubled_pools(oracle, guard_behind, variant):
     vol = shapes.random_blobs((12, 14, 18), 9)
     rg, ridge, _ = _ridge_of(oracle, vol, True)
     _, want = oracle.paint(rg)
@@ -92,7 +99,7 @@ def test_painter_kernels_wide_items_and_doubled_pools(oracle, guard, variant):
     assert flags == 0 and np.array_equal(got, want)
 
 
-def test_painter_kernels_column_blocks(oracle, guard):
+def test_painter_kernels_column_blocks(oracle, guard_behind):
     """stages 2-3 per block of 32 columns: 32 + 32 + 6"""
     vol = shapes.random_blobs((6, 9, 70), 4)
     rg, ridge, _ = _ridge_of(oracle, vol, True)
@@ -102,7 +109,7 @@ def test_painter_kernels_column_blocks(oracle, guard):
 
 
 @pytest.mark.parametrize("caps", [(2, 1), (3, 2)])
-def test_painter_kernels_redo_paths(oracle, guard, caps):
+def test_painter_kernels_redo_paths(oracle, guard_behind, caps):
     """capacities of the fast kernels capped: lines are redone by the kernels with global scratch, same map"""
     from bonej2_b200.phantom import phantom_shapes
     vol = oracle.phantom_raster(phantom_shapes(24, 24, 24, 1), 24, 24, 24)
@@ -117,7 +124,7 @@ def test_painter_kernels_redo_paths(oracle, guard, caps):
 
 @pytest.mark.parametrize("cuts,xcols", [((0, 9, 17), 0), ((0, 4, 8, 12, 17), 0), ((0, 6, 17), 32), ((0, 1, 2, 17), 0)])
 @pytest.mark.parametrize("inverse", [False, True])
-def test_painter_kernels_on_z_slabs(oracle, guard, cuts, xcols, inverse):
+def test_painter_kernels_on_z_slabs(oracle, guard_behind, cuts, xcols, inverse):
     """the stepwise painter (x / y stages per slab, boundary staircases exported and imported, z sweeps) on slabs of
     one volume -- also slabs thinner than the largest ball and column blocks -- equals the whole-volume painting"""
     import math
@@ -128,7 +135,7 @@ def test_painter_kernels_on_z_slabs(oracle, guard, cuts, xcols, inverse):
     assert rc == 0 and np.array_equal(got, want)
 
 
-def test_whole_chain_on_a_phantom(oracle, guard):
+def test_whole_chain_on_a_phantom(oracle, guard_behind):
     """EDT -> ridge -> paint, each kernel fed by the one before it"""
     from bonej2_b200.phantom import phantom_shapes
     vol = oracle.phantom_raster(phantom_shapes(32, 32, 32, 2), 32, 32, 32)
@@ -179,7 +186,7 @@ def test_finish_kernel_plane_range(oracle, guard):
 
 @pytest.mark.parametrize("inverse", [False, True])
 @pytest.mark.parametrize("shape", [(9, 20, 32), (13, 11, 7), (1, 9, 17)])
-def test_scatter_painter_kernels(oracle, guard, shape, inverse):
+def test_scatter_painter_kernels(oracle, guard_behind, shape, inverse):
     """the always-correct fallback (paint path 2): ridge compaction and the literal scatter of every ball"""
     vol = shapes.random_blobs(shape, 3)
     rg, ridge, _ = _ridge_of(oracle, vol, inverse)
