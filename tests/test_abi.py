@@ -52,6 +52,21 @@ def test_product_does_not_import_oracle():
                 assert "lt_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f
 
 
+def test_product_knows_nothing_of_the_test_emulation():
+    """the CPU emulation of CUDA, the JNI test double and the oracle live under tests/ and oracle/; nothing in the
+    package, the headers, bench.py's product arm or the build of the product library refers to them"""
+    pkg = os.path.join(ROOT, "bonej2_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                for word in ("cuda_emu", "kernels_emu", "emu_native", "libbonejthickness_emu", "jni_stub", "BJT_CUDA_EMU"):
+                    assert word not in src, (f, word)
+    from bonej2_b200 import _native
+    assert os.path.basename(_native.SO_PATH) == "libbonejthickness.so" and os.path.dirname(_native.SO_PATH) == pkg
+    assert not any("tests" in os.path.relpath(p, ROOT).split(os.sep) for p in _native.sources())
+
+
 def test_paint_block_cols_is_a_host_function():
     """the column-block width rule needs no device (sharded runs query it to agree on one width)"""
     from bonej2_b200 import _native
