@@ -150,8 +150,9 @@ __device__ __forceinline__ void prefetch_l1(const void *p) {
 }
 
 // How far ahead the line kernels look.  The index words of a position are loaded one position ahead (registers);
-// the items they point to are requested PF_ITEMS positions ahead (L1), from a copy of the index word read at the
-// top of a position and used at its bottom, so nothing waits on it.  The round's ncu captures had 19 % of the
+// the items they point to are requested PF_ITEMS positions ahead (L1): the index word of that position is itself
+// requested into L1 at the top of a position and read at its bottom (an L1 hit), so no register is held across the
+// position and nothing waits on memory.  The round's ncu captures had 19 % of the
 // y-stage sweep's samples and 15 % of the z-stage's on the first use of an item loaded on demand, and 10 % of
 // the x-stage's on the ridge value loaded one position ahead (its rows are read 4 bytes per lane).
 constexpr int PF_ITEMS = 2;             // positions
@@ -219,7 +220,6 @@ __device__ __forceinline__ bool dyn_line(const SepArgs &a, long long line, bool 
     for (int step = 0; step < L; ++step) {
         const int t = DIR > 0 ? step : L - 1 - step;
         int nf = 0;
-        unsigned long long pfF = 0ull, pfB = 0ull;          // index words PF_ITEMS positions ahead (prefetch only)
         if (valid) {
             const uint32_t r = r_next;
             const unsigned long long eF = eF_next, eB = eB_next;
@@ -230,9 +230,9 @@ __device__ __forceinline__ bool dyn_line(const SepArgs &a, long long line, bool 
             }
             if (STAGE == 1) {
                 if (step + PF_RIDGE < L) prefetch_l1(a.ridge + vi + (long long)(PF_RIDGE - 1) * step_in);
-            } else if (step + PF_ITEMS < L) {
-                pfF = __ldg(a.inF + vi + (long long)(PF_ITEMS - 1) * step_in);
-                pfB = __ldg(a.inB + vi + (long long)(PF_ITEMS - 1) * step_in);
+            } else if (step + PF_ITEMS < L) {                // their index words first (no register held across the step)
+                prefetch_l1(a.inF + vi + (long long)(PF_ITEMS - 1) * step_in);
+                prefetch_l1(a.inB + vi + (long long)(PF_ITEMS - 1) * step_in);
             }
             if (STAGE == 1) {
                 if (r | (uint32_t)A.n) {
@@ -245,7 +245,9 @@ __device__ __forceinline__ bool dyn_line(const SepArgs &a, long long line, bool 
                                                              ipool + (eB & OFF_MASK), (int)(eB >> 40), fr, fmax, ok);
             }
             if (nf > fmax) { ok = false; nf = fmax; }
-            if (STAGE != 1) {                                // the lists of position t + PF_ITEMS, into L1
+            if (STAGE != 1 && step + PF_ITEMS < L) {         // the lists of position t + PF_ITEMS, into L1
+                const unsigned long long pfF = __ldg(a.inF + vi + (long long)(PF_ITEMS - 1) * step_in);
+                const unsigned long long pfB = __ldg(a.inB + vi + (long long)(PF_ITEMS - 1) * step_in);
                 if (pfF >> 40) prefetch_l1(ipool + (pfF & OFF_MASK));
                 if (pfB >> 40) prefetch_l1(ipool + (pfB & OFF_MASK));
             }
@@ -289,10 +291,9 @@ __device__ __forceinline__ bool stair_line(const SepArgs &a, long long line, Sta
         if (step + 1 < a.d) { vi += step_in; eF_next = __ldg(a.inF + vi); eB_next = __ldg(a.inB + vi); }
         const uint32_t o_old = o_next;
         if (a.dir < 0 && step + 1 < a.d) o_next = a.out[out_base + (long long)(z - 1) * out_stride];
-        unsigned long long pfF = 0ull, pfB = 0ull;          // index words PF_ITEMS positions ahead (prefetch only)
-        if (step + PF_ITEMS < a.d) {
-            pfF = __ldg(a.inF + vi + (long long)(PF_ITEMS - 1) * step_in);
-            pfB = __ldg(a.inB + vi + (long long)(PF_ITEMS - 1) * step_in);
+        if (step + PF_ITEMS < a.d) {                        // index words PF_ITEMS positions ahead: no register held across the step
+            prefetch_l1(a.inF + vi + (long long)(PF_ITEMS - 1) * step_in);
+            prefetch_l1(a.inB + vi + (long long)(PF_ITEMS - 1) * step_in);
         }
 #pragma unroll
         for (int which = 0; which < 2; ++which) {
@@ -309,8 +310,12 @@ __device__ __forceinline__ bool stair_line(const SepArgs &a, long long line, Sta
                 }
             }
         }
-        if (pfF >> 40) prefetch_l1(ipool + (pfF & OFF_MASK));   // the lists of plane z +- PF_ITEMS, into L1
-        if (pfB >> 40) prefetch_l1(ipool + (pfB & OFF_MASK));
+        if (step + PF_ITEMS < a.d) {                        // the lists of plane z +- PF_ITEMS, into L1
+            const unsigned long long pfF = __ldg(a.inF + vi + (long long)(PF_ITEMS - 1) * step_in);
+            const unsigned long long pfB = __ldg(a.inB + vi + (long long)(PF_ITEMS - 1) * step_in);
+            if (pfF >> 40) prefetch_l1(ipool + (pfF & OFF_MASK));
+            if (pfB >> 40) prefetch_l1(ipool + (pfB & OFF_MASK));
+        }
         if (z == 0) {
             for (int src = 0; src < a.imp.n_lo; ++src) {
                 const int cnt = (int)a.imp.lo_cnt[src][in_base];
