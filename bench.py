@@ -297,11 +297,12 @@ def main():
         launch_ms = per_step["ms_paint_y"] / sweeps_per_step
         launch_bytes = 24.0 * N * 4.0 / sweeps_per_step    # 24 B x voxels of one block: blocks per run = sweeps / (2 runs x 2 directions)
         y_gbs = launch_bytes / (launch_ms * 1e-3) / 1e9
-        traffic = None
+        traffic = traffic_build = None
         try:
             rec = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ystage_traffic.json")))
             if rec.get("volume") == [n, n, n]:
                 traffic = rec["dram_bytes_per_launch"]
+                traffic_build = rec.get("build")
         except (OSError, ValueError, KeyError):
             pass
         roofline = {"kernel": "sep_dyn_kernel<PACKED,2,+-1> (painter y-stage sweep)", "bound": "hbm", "achieved": y_gbs,
@@ -310,6 +311,8 @@ def main():
                     "algorithmic_bytes_per_launch": launch_bytes,
                     "share_of_step": round(per_step["ms_paint_y"] / dev_ms, 4),
                     "note": "instruction-issue bound, not HBM bound (profiles/README.md); `stages` holds the streaming kernels"}
+        if traffic_build:
+            roofline["traffic_capture"] = traffic_build
     else:   # the separable painter did not run (constant fast path / scatter fallback): report the slowest stage
         dom = max(alg, key=lambda k: per_step[k])
         dom_gbs = alg[dom] / (per_step[dom] * 1e-3) / 1e9
