@@ -101,3 +101,9 @@ def test_painter_redo_kernels_through_the_abi(emu_ctx, oracle):
                 assert emu_ctx.debug_paint_redo_lines() > 10
     finally:
         emu_ctx.debug_set_paint_limits(0, 0)
+
+
+def test_graft_entry_smoke(emu_ctx):
+    """__graft_entry__.smoke() -- what the driver runs on the GPU box before the bench -- on the emulated library"""
+    import __graft_entry__ as g
+    g.smoke()
