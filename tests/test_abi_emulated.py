@@ -107,3 +107,13 @@ def test_graft_entry_smoke(emu_ctx):
     """__graft_entry__.smoke() -- what the driver runs on the GPU box before the bench -- on the emulated library"""
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_hyperstack_and_raw_file_front_ends(emu_ctx, oracle, tmp_path):
+    """the callers either side of the path: per-subspace batch over a hyperstack, raw file to raw file
+    through page-locked buffers"""
+    from tests import test_hyperstack as H
+    from tests import test_rawio as R
+    H.test_batched_thickness_matches_oracle(oracle)
+    R.test_thickness_raw_file_to_file(tmp_path, oracle, "Both")
+    R.test_thickness_raw_refuses_non_binary(tmp_path)
