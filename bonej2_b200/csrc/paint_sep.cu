@@ -118,6 +118,7 @@ __device__ __forceinline__ unsigned long long warp_alloc(int nf, unsigned long l
                                                          uint32_t *flags, uint32_t flagbit,
                                                          unsigned long long &chunk_base, int &chunk_left) {
     const int lane = threadIdx.x & 31;
+    if (!__any_sync(0xFFFFFFFFu, nf > 0)) return 0ull;      // nothing emitted by the whole warp: common where a run has no balls
     int incl = nf;
 #pragma unroll
     for (int k = 1; k < 32; k <<= 1) {
