@@ -118,7 +118,8 @@ def build(force=False):
 
 
 API_OUT = os.path.join(_OUTDIR, "libbonejthickness_emu.so")
-API_SOURCES = ["api.cu", "edt.cu", "ridge.cu", "paint_sep.cu", "paint_scatter.cu", "finish.cu", "phantom.cu"]
+API_SOURCES = ["api.cu", "edt.cu", "ridge.cu", "paint_sep.cu", "paint_scatter.cu", "finish.cu", "phantom.cu", "segstats.cu",
+               "ridgepoints.cu"]
 
 
 def build_api(force=False):

@@ -91,11 +91,23 @@ namespace emu {
 
 constexpr size_t STACK_BYTES = 512 * 1024;
 
-struct Warp {
+// One rendezvous per participant mask: the lanes named by the mask of a *_sync call (those of them that are still
+// alive) meet, each leaves a value, all pick up the snapshot.  Full-mask calls use one slot, sub-warp groups
+// (__match_any_sync peers shuffling among themselves) one slot per mask.
+struct Rendezvous {
+    unsigned mask = 0, arrived_bits = 0, gen = 0;
     unsigned long long vals[32], snap[32];
-    bool live[32];
-    int alive = 0, arrived = 0;
-    unsigned gen = 0;
+};
+struct Warp {
+    std::vector<Rendezvous> slots;
+    unsigned live_bits = 0;
+    Rendezvous &slot(unsigned mask) {
+        for (auto &r : slots) if (r.mask == mask) return r;
+        slots.emplace_back();
+        slots.back().mask = mask;
+        memset(slots.back().vals, 0, sizeof slots.back().vals);
+        return slots.back();
+    }
 };
 
 struct Fiber {
@@ -122,11 +134,13 @@ inline Block *&blk() { static Block *b = nullptr; return b; }
 inline Fiber &cur() { return blk()->fibers[blk()->cur]; }
 inline void yield() { swapcontext(&cur().ctx, &blk()->main_ctx); }
 
-inline void warp_release_if_complete(Warp &w) {
-    if (w.alive > 0 && w.arrived == w.alive) {
-        memcpy(w.snap, w.vals, sizeof w.snap);
-        w.arrived = 0;
-        ++w.gen;
+inline void release_if_complete(Warp &w, Rendezvous &r) {
+    const unsigned need = r.mask & w.live_bits;
+    if (r.arrived_bits != 0 && (r.arrived_bits & need) == need) {
+        memcpy(r.snap, r.vals, sizeof r.snap);
+        memset(r.vals, 0, sizeof r.vals);
+        r.arrived_bits = 0;
+        ++r.gen;
     }
 }
 inline void block_release_if_complete(Block &b) {
@@ -140,10 +154,8 @@ inline void trampoline() {
     f.done = true;
     // an exited thread no longer counts at barriers and collectives (CUDA semantics for exited threads)
     Warp &w = b->warps[f.lin >> 5];
-    w.live[f.lin & 31] = false;
-    --w.alive;
-    w.vals[f.lin & 31] = 0;
-    warp_release_if_complete(w);
+    w.live_bits &= ~(1u << (f.lin & 31));
+    for (auto &r : w.slots) release_if_complete(w, r);       // whoever waited for this lane stops waiting
     --b->alive;
     block_release_if_complete(*b);
     swapcontext(&f.ctx, &b->main_ctx);
@@ -157,18 +169,21 @@ inline void sync_block() {
     while (b.gen == g) yield();
 }
 
-// every live lane of the warp contributes one 64-bit value; returns the warp's values (dead lanes: 0)
-inline const unsigned long long *warp_gather(unsigned long long v) {
+// every live lane named by `mask` contributes one 64-bit value; returns the group's values (other lanes: 0).
+// The snapshot stays valid until the same group meets again, which needs this lane too.
+inline const unsigned long long *warp_gather(unsigned mask, unsigned long long v) {
     Block &b = *blk();
     const int lin = cur().lin;
     Warp &w = b.warps[lin >> 5];
-    const unsigned g = w.gen;
-    w.vals[lin & 31] = v;
-    ++w.arrived;
-    warp_release_if_complete(w);
-    while (w.gen == g) yield();
-    return w.snap;
+    const size_t idx = (size_t)(&w.slot(mask) - w.slots.data());          // slots may move when another mask appears
+    const unsigned g = w.slots[idx].gen;
+    w.slots[idx].vals[lin & 31] = v;
+    w.slots[idx].arrived_bits |= 1u << (lin & 31);
+    release_if_complete(w, w.slots[idx]);
+    while (w.slots[idx].gen == g) yield();
+    return w.slots[idx].snap;
 }
+inline unsigned live_lanes() { return blk()->warps[cur().lin >> 5].live_bits; }
 
 template <class F>
 void launch(dim3 grid, dim3 block, F &&body) {
@@ -184,7 +199,7 @@ void launch(dim3 grid, dim3 block, F &&body) {
     for (unsigned bz = 0; bz < grid.z; ++bz) for (unsigned by = 0; by < grid.y; ++by) for (unsigned bx = 0; bx < grid.x; ++bx) {
         b.bidx = emu_uint3{bx, by, bz};
         b.alive = nthreads; b.arrived = 0;
-        for (auto &w : b.warps) { w.alive = 32; w.arrived = 0; for (int l = 0; l < 32; ++l) { w.live[l] = true; w.vals[l] = 0; } }
+        for (auto &w : b.warps) { w.live_bits = 0xFFFFFFFFu; w.slots.clear(); }
         for (int i = 0; i < nthreads; ++i) {
             Fiber &f = b.fibers[i];
             f.done = false; f.lin = i;
@@ -228,43 +243,58 @@ inline int emu_lane() { return emu::cur().lin & 31; }
 template <class T> inline unsigned long long emu_bits(T v) { unsigned long long b = 0; memcpy(&b, &v, sizeof(T)); return b; }
 template <class T> inline T emu_unbits(unsigned long long b) { T v; memcpy(&v, &b, sizeof(T)); return v; }
 
-template <class T> inline T __shfl_sync(unsigned, T v, int src) {
-    const unsigned long long *s = emu::warp_gather(emu_bits(v));
+template <class T> inline T __shfl_sync(unsigned mask, T v, int src) {
+    const unsigned long long *s = emu::warp_gather(mask, emu_bits(v));
     return emu_unbits<T>(s[src & 31]);
 }
-template <class T> inline T __shfl_up_sync(unsigned, T v, unsigned delta) {
+template <class T> inline T __shfl_up_sync(unsigned mask, T v, unsigned delta) {
     const int lane = emu_lane();
-    const unsigned long long *s = emu::warp_gather(emu_bits(v));
+    const unsigned long long *s = emu::warp_gather(mask, emu_bits(v));
     return lane >= (int)delta ? emu_unbits<T>(s[lane - (int)delta]) : v;
 }
-template <class T> inline T __shfl_down_sync(unsigned, T v, unsigned delta) {
+template <class T> inline T __shfl_down_sync(unsigned mask, T v, unsigned delta) {
     const int lane = emu_lane();
-    const unsigned long long *s = emu::warp_gather(emu_bits(v));
+    const unsigned long long *s = emu::warp_gather(mask, emu_bits(v));
     return lane + (int)delta < 32 ? emu_unbits<T>(s[lane + (int)delta]) : v;
 }
-template <class T> inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+template <class T> inline T __shfl_xor_sync(unsigned mask, T v, int lane_mask) {
     const int lane = emu_lane();
-    const unsigned long long *s = emu::warp_gather(emu_bits(v));
+    const unsigned long long *s = emu::warp_gather(mask, emu_bits(v));
     return emu_unbits<T>(s[(lane ^ lane_mask) & 31]);
 }
 inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
-inline unsigned __ballot_sync(unsigned, int pred) {
-    const unsigned long long *s = emu::warp_gather(pred ? 1ull : 0ull);
+inline unsigned __ballot_sync(unsigned mask, int pred) {
+    const unsigned long long *s = emu::warp_gather(mask, pred ? 1ull : 0ull);
     unsigned m = 0;
     for (int l = 0; l < 32; ++l) m |= s[l] ? (1u << l) : 0u;
     return m;
 }
 inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0u; }
-inline unsigned __reduce_max_sync(unsigned, unsigned v) {
-    const unsigned long long *s = emu::warp_gather(v);
+inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
+    const unsigned long long *s = emu::warp_gather(mask, v);
     unsigned m = 0;
     for (int l = 0; l < 32; ++l) m = (unsigned)s[l] > m ? (unsigned)s[l] : m;
     return m;
 }
-inline unsigned __reduce_add_sync(unsigned, unsigned v) {
-    const unsigned long long *s = emu::warp_gather(v);
+inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
+    const unsigned long long *s = emu::warp_gather(mask, v);
     unsigned m = 0;
     for (int l = 0; l < 32; ++l) m += (unsigned)s[l];
+    return m;
+}
+
+// lanes that have not left the kernel: equals the hardware's active mask where lanes only diverge by leaving (the
+// grid-stride loops of segstats.cu); NOT a model of arbitrary divergence
+inline unsigned __activemask() { return emu::live_lanes(); }
+// lanes of `mask` holding the same value as the caller (marks a present lane with bit 32 so that a key of 0 counts)
+template <class T> inline unsigned __match_any_sync(unsigned mask, T v) {
+    const int lane = emu_lane();
+    const unsigned long long mine = (emu_bits(v) & 0xFFFFFFFFull) | (1ull << 32);
+    static_assert(sizeof(T) <= 4, "emulated __match_any_sync: 32-bit keys");
+    const unsigned long long *s = emu::warp_gather(mask, mine);
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) if (s[l] == mine) m |= 1u << l;
+    (void)lane;
     return m;
 }
 
@@ -272,6 +302,9 @@ inline unsigned __reduce_add_sync(unsigned, unsigned v) {
 template <class T> inline T atomicAdd(T *p, T v) { const T o = *p; *p = o + v; return o; }
 template <class T> inline T atomicMax(T *p, T v) { const T o = *p; if (v > o) *p = v; return o; }
 template <class T> inline T atomicOr(T *p, T v) { const T o = *p; *p = o | v; return o; }
+template <class T> inline T atomicExch(T *p, T v) { const T o = *p; *p = v; return o; }
+inline long long __double_as_longlong(double v) { long long b; memcpy(&b, &v, 8); return b; }
+inline unsigned __float_as_uint(float v) { unsigned b; memcpy(&b, &v, 4); return b; }
 
 // ---- integer intrinsics ----
 inline int __popc(unsigned v) { return __builtin_popcount(v); }

@@ -117,3 +117,21 @@ def test_hyperstack_and_raw_file_front_ends(emu_ctx, oracle, tmp_path):
     H.test_batched_thickness_matches_oracle(oracle)
     R.test_thickness_raw_file_to_file(tmp_path, oracle, "Both")
     R.test_thickness_raw_refuses_non_binary(tmp_path)
+
+
+def test_consumers_of_the_map(emu_ctx):
+    """segmented statistics (segstats.cu: __match_any_sync peer groups, two passes) through the C-ABI"""
+    from tests import test_gpu_consumers as K
+    K.test_label_stats_match_get_mean_std_dev(emu_ctx, 1)
+    K.test_label_stats_rejects_unknown_label(emu_ctx)
+    K.test_slice_stats_match_slice_geometry(emu_ctx, (5, 3, 20, 17))
+    K.test_slice_stats_match_slice_geometry(emu_ctx, None)
+    K.test_slice_stats_bad_roi(emu_ctx)
+
+
+def test_find_ridge_points(emu_ctx):
+    """FindRidgePoints (ridgepoints.cu on the CUDA EDT) through the C-ABI"""
+    from tests import test_ridge_points as P
+    P.test_cuda_matches_restatement(emu_ctx, 1, 0.6)
+    P.test_cuda_matches_restatement(emu_ctx, 2, 0.2)
+    P.test_cuda_degenerate(emu_ctx)
