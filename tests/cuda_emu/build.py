@@ -100,6 +100,9 @@ def translate(name):
     return '#line 1 "%s"\n' % os.path.join(_CSRC, name) + text
 
 
+# -fno-gnu-unique / -Bsymbolic: the two emulated libraries define the same symbols (kernels, the emulation's inline
+# statics); each must bind to its own copies when both are loaded into one test process
+
 def build(force=False):
     stale = (not os.path.exists(OUT)) or any(os.path.getmtime(p) > os.path.getmtime(OUT) for p in _DEPS)
     if not (force or stale):
@@ -111,7 +114,7 @@ def build(force=False):
         with open(cpp, "w") as f:
             f.write(translate(name))
         objs.append(cpp)
-    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w", "-I", _HERE, "-I", _CSRC, "-I", os.path.join(_ROOT, "include"),
+    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w", "-fno-gnu-unique", "-Wl,-Bsymbolic", "-I", _HERE, "-I", _CSRC, "-I", os.path.join(_ROOT, "include"),
            "-o", OUT] + objs + [os.path.join(_HERE, "harness.cpp")]
     subprocess.check_call(cmd)
     return OUT
@@ -138,7 +141,7 @@ def build_api(force=False):
         with open(cpp, "w") as f:
             f.write(translate(name))
         srcs.append(cpp)
-    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w", "-I", _HERE, "-I", _CSRC, "-I", os.path.join(_ROOT, "include"),
+    cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w", "-fno-gnu-unique", "-Wl,-Bsymbolic", "-I", _HERE, "-I", _CSRC, "-I", os.path.join(_ROOT, "include"),
            "-o", API_OUT] + srcs + [os.path.join(_CSRC, "thickness_wrapper.cpp"), os.path.join(_HERE, "api_stubs.cpp"), "-lpthread"]
     subprocess.check_call(cmd)
     return API_OUT
