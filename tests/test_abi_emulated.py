@@ -24,8 +24,11 @@ def emu_ctx():
         c.close()
 
 
-@pytest.mark.parametrize("name", SMALL)
-@pytest.mark.parametrize("inverse", [False, True])
+# both runs for the small cases, the background run (larger balls, longer lists) alone for the bigger ones
+STAGE_CASES = [(n, inv) for n in SMALL for inv in (False, True) if inv or G.CASES[n].size <= 20000]
+
+
+@pytest.mark.parametrize("name,inverse", STAGE_CASES)
 def test_stages(emu_ctx, oracle, name, inverse):
     G.test_stages(emu_ctx, oracle, name, inverse)
 
