@@ -39,7 +39,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     stale = (not os.path.exists(SO_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in deps)
     if force or stale:
         nvcc = os.environ.get("NVCC", "nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + ["-o", SO_PATH] + sources()
+        extra = os.environ.get("BJT_NVCC_EXTRA", "").split()        # tuning builds (tools/tune_painter.sh), e.g. -DBJT_S_SM=10
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", SO_PATH] + sources()
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

@@ -51,8 +51,18 @@ inline int xslab_cols(int w, int h, int d) {
 }
 constexpr unsigned long long OFF_MASK = (1ull << 40) - 1ull;
 constexpr int TPB = 128;                // threads per block of the line kernels
-constexpr int S_SM = 12;                // entries per buffer kept in shared memory (PACKED kernels)
-constexpr int CAP_TAIL = 1012;          // entries per buffer in the local frame behind them
+// Tuning knobs with their measured defaults; tools/tune_painter.sh rebuilds with other values (-DBJT_S_SM=.. etc.)
+#ifndef BJT_S_SM
+#define BJT_S_SM 12
+#endif
+#ifndef BJT_DYN_BLOCKS
+#define BJT_DYN_BLOCKS 9                // resident blocks per SM the line kernels of stages 1-2 are compiled for (56 registers)
+#endif
+#ifndef BJT_STAIR_BLOCKS
+#define BJT_STAIR_BLOCKS 12             // the same for the stage-3 kernel (40 registers)
+#endif
+constexpr int S_SM = BJT_S_SM;          // entries per buffer kept in shared memory (PACKED kernels)
+constexpr int CAP_TAIL = 1024 - S_SM;   // entries per buffer in the local frame behind them
 constexpr int CAP_WIDE = 128;           // local-frame capacity of the wide (u64 item) kernels
 constexpr int FMAX_FAST = 256;
 constexpr int CAP_STAIR = 96;         // local-frame capacity of the stage-3 staircase
@@ -357,7 +367,7 @@ struct StairStore : SepStairLocal<CAP_STAIR> {
 template <> struct FastActive<false> { typedef SepActive<WideStore> T; };
 
 template <bool PACKED, int STAGE, int DIR>
-__global__ void __launch_bounds__(TPB, 9) sep_dyn_kernel(SepArgs a) {
+__global__ void __launch_bounds__(TPB, BJT_DYN_BLOCKS) sep_dyn_kernel(SepArgs a) {
     __shared__ unsigned long long sm[PACKED ? 2 * S_SM * TPB : 1];
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long pl = STAGE == 1 ? sep_patch_line(tid, a.h, a.d) : sep_patch_line(tid, a.xw, a.d);
@@ -394,7 +404,7 @@ __global__ void __launch_bounds__(32) sep_dyn_redo_kernel(SepArgs a) {
 }
 
 template <bool PACKED>
-__global__ void __launch_bounds__(TPB, 12) sep_stair_kernel(SepArgs a) {
+__global__ void __launch_bounds__(TPB, BJT_STAIR_BLOCKS) sep_stair_kernel(SepArgs a) {
     const long long line = sep_patch_line((long long)blockIdx.x * blockDim.x + threadIdx.x, a.xw, a.h);
     if (line < 0) return;
     SepStair<StairStore> S;
