@@ -110,3 +110,14 @@ def test_single_rank_product_stages(oracle, inverse):
     ok = ~np.isnan(got)
     assert np.allclose(got[ok], ref["map"][ok], rtol=1e-5, atol=0)
     assert st["count"] == ref["stats"].count
+
+
+@pytest.mark.timeout(600)
+def test_four_ranks_thin_slabs_product_stages(tmp_path):
+    """slabs thinner than the largest ball: staircases cross more than one slab face (several sources per side), with
+    the kernels' own export / import code"""
+    vol = np.zeros((16, 14, 32), np.uint8)
+    vol[1:15, 1:13, 1:31] = 255                                         # r_max = 6 > slab thickness 4
+    vol[7, 6, 6] = 0
+    stages = _check(vol, False, True, str(tmp_path), world=4, paint_mode="exchange")
+    assert "paint.exchange" in stages
