@@ -124,7 +124,7 @@ int main(int argc, char **argv) {
                 out.pool.insert(out.pool.end(), fr, fr + nf);
             }
         }
-    const int Ks[] = {0, 2, 3, 4, 6, 8, 12, 16};
+    const int Ks[] = {0, 2, 3, 4, 6};
     std::vector<uint16_t> it(2 * N);
     Park P;
     for (int K : Ks) {
@@ -169,8 +169,20 @@ int main(int argc, char **argv) {
                 issued += mx;
             }
         }
-        printf("K=%2d: iterations %.3f per voxel and direction, warp iterations (max over lanes) %.3f per position, "
-               "parked %ld, front mismatches %ld\n", K, total / (2.0 * N), issued / (2.0 * N / 32), P.parked, mismatches);
+        // the same with a warp's lanes as an 8 x 4 patch of lines (x by z), the kernels' mapping
+        double issued_patch = 0;
+        for (int dirsel = 0; dirsel < 2; ++dirsel) {
+            const uint16_t *p = it.data() + (dirsel ? N : 0);
+            for (int z0 = 0; z0 + 4 <= d; z0 += 4) for (int x0 = 0; x0 + 8 <= w; x0 += 8) for (int t = 0; t < h; ++t) {
+                int mx = 0;
+                for (int lz = 0; lz < 4; ++lz) for (int lx = 0; lx < 8; ++lx)
+                    mx = std::max(mx, (int)p[(size_t)(z0 + lz) * wh + (size_t)t * w + x0 + lx]);
+                issued_patch += mx;
+            }
+        }
+        printf("K=%2d: iterations %.3f per voxel and direction, warp iterations per position: %.3f (32 x 1 lines), %.3f (8 x 4 patch), "
+               "parked %ld, front mismatches %ld\n", K, total / (2.0 * N), issued / (2.0 * N / 32), issued_patch / (2.0 * N / 32),
+               P.parked, mismatches);
         fflush(stdout);
     }
     return 0;
