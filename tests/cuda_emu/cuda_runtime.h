@@ -1,6 +1,6 @@
 /*
  * cuda_runtime.h -- TEST ONLY: a small CPU emulation of the CUDA constructs this repository's kernels use, so the
- * kernels' own source (bonej2_b200/csrc/*.cu, rewritten only at their <<< >>> launches by tests/cuda_emu/build.py)
+ * kernels' own source (bonej2_b200/csrc/*.cu, rewritten only at their <<< >>> launches by tests/cuda_emu/emu_build.py)
  * can be compiled with g++ and executed without a GPU.  It exists to check kernel LOGIC (index arithmetic, staging
  * loops, thread -> line maps, warp-collective protocols, list plumbing) against the oracle in the CPU test run; it
  * says nothing about speed, memory-model subtleties or real hardware scheduling.  Not part of the product: the

@@ -14,7 +14,7 @@ _OUTDIR = os.path.join(_ROOT, "tests", "_build")
 OUT = os.path.join(_OUTDIR, "libkernels_emu.so")
 KERNEL_SOURCES = ["edt.cu", "ridge.cu", "paint_sep.cu", "finish.cu", "paint_scatter.cu", "phantom.cu"]
 _DEPS = [os.path.join(_CSRC, f) for f in KERNEL_SOURCES + ["common.cuh", "paint_sep_core.cuh"]] + \
-        [os.path.join(_HERE, f) for f in ("cuda_runtime.h", "harness.cpp", "build.py")]
+        [os.path.join(_HERE, f) for f in ("cuda_runtime.h", "harness.cpp", "emu_build.py")]
 
 
 def _match_back(text, i, open_c, close_c):
@@ -129,7 +129,7 @@ def build_api(force=False):
     """the whole C-ABI (include/bonej_thickness.h, api.cu + thickness_wrapper.cpp) on the emulation, for tests that
     drive the library's entry points without a GPU"""
     deps = [os.path.join(_CSRC, f) for f in API_SOURCES + ["common.cuh", "paint_sep_core.cuh", "thickness_wrapper.cpp"]] + \
-           [os.path.join(_HERE, f) for f in ("cuda_runtime.h", "api_stubs.cpp", "build.py")] + \
+           [os.path.join(_HERE, f) for f in ("cuda_runtime.h", "api_stubs.cpp", "emu_build.py")] + \
            [os.path.join(_ROOT, "include", f) for f in ("bonej_thickness.h", "thickness_wrapper.hpp")]
     stale = (not os.path.exists(API_OUT)) or any(os.path.getmtime(p) > os.path.getmtime(API_OUT) for p in deps)
     if not (force or stale):

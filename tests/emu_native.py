@@ -10,7 +10,7 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(_HERE, "cuda_emu"))
-import build as _build  # noqa: E402
+import emu_build as _build  # noqa: E402
 
 from bonej2_b200 import _native  # noqa: E402
 

@@ -8,7 +8,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(_HERE, "cuda_emu"))
-import build as _build  # noqa: E402
+import emu_build as _build  # noqa: E402
 
 _lib = None
 
