@@ -93,6 +93,7 @@ _SIGS = {
     "bjt_dev_paint_close": ([_VP, _VP], _I),
     "bjt_debug_set_paint_limits": ([_VP, _I, _I], _I),
     "bjt_debug_paint_redo_lines": ([_VP], C.c_int64),
+    "bjt_debug_isqrt_check": ([_VP, C.POINTER(C.c_int64)], _I),
     "bjt_debug_set_xslab_cols": ([_I], _I),
     "bjt_paint_block_cols": ([_I, _I, _I], _I),
     "bjt_paint_set_block_cols": ([_I], _I),
@@ -266,6 +267,12 @@ class Context:
         """use this column-block width (multiple of 32; 0 = the library's choice); process-wide"""
         if lib().bjt_paint_set_block_cols(int(cols)) != 0:
             raise ValueError("column-block width must be a non-negative multiple of 32")
+
+    def debug_isqrt_check(self) -> int:
+        """mismatches of the disc painter's integer square root against the exact one (must be 0)"""
+        n = C.c_int64(-1)
+        self._ck(lib().bjt_debug_isqrt_check(self._h, C.byref(n)))
+        return int(n.value)
 
     def debug_paint_redo_lines(self) -> int:
         return int(lib().bjt_debug_paint_redo_lines(self._h))

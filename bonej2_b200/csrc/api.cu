@@ -169,7 +169,7 @@ int bjt_set_stream(bjt_ctx *c, void *stream) {
 }
 
 int bjt_set_paint_path(bjt_ctx *c, int path) {
-    if (!c || path < -1 || path > 2) return BJT_E_ARG;
+    if (!c || path < -1 || path > 4 || path == 3) return BJT_E_ARG;
     c->paint_path = path;
     return BJT_OK;
 }
@@ -207,6 +207,20 @@ int bjt_paint_set_block_cols(int cols) {
 }
 
 int bjt_debug_set_xslab_cols(int cols) { return bjt_paint_set_block_cols(cols); }
+
+int bjt_debug_isqrt_check(bjt_ctx *c, int64_t *mismatches) {
+    if (!c || !mismatches) return BJT_E_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    uint32_t *scal;
+    WS("scalars", 256, scal);
+    CK(cudaMemsetAsync(scal + 16, 0, 4, c->stream));
+    c->launches += launch_isqrt_small_check(scal + 16, c->stream); CKL();
+    CK(peek(c, c->h_scal + 16, scal + 16, 4));
+    CK(cudaStreamSynchronize(c->stream));
+    *mismatches = (int64_t)c->h_scal[16];
+    return BJT_OK;
+}
 
 int64_t bjt_debug_paint_redo_lines(bjt_ctx *c) {
     if (!c) return -1;
@@ -309,21 +323,74 @@ static int dev_ridge_full(bjt_ctx *c, const uint32_t *sq, int w, int h, int d, u
     return dev_ridge(c, sq, w, h, d, c->h_scal[0], ridge, n_ridge);
 }
 
+// Fronts along z, then discs in the plane (paint_disc.cu), over planes [z_lo, z_hi) of a ridge volume of dext
+// planes; rsq points at plane z_lo.  *done = 0 when the item pool could not be made large enough (nothing valid
+// in rsq; the caller takes another path).
+static int dev_paint_disc(bjt_ctx *c, const uint32_t *ridge, int w, int h, int dext, int z_lo, int z_hi, uint32_t max_r,
+                          uint32_t *rsq, int *done) {
+    uint32_t *scal;
+    WS("scalars", 256, scal);
+    *done = 0;
+    for (int ipv = 3; ipv <= 48; ipv *= 4) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        size_t have = 0;
+        { auto it = c->bufs.find("paint_disc"); if (it != c->bufs.end()) have = it->second.cap; }
+        const size_t avail = have + (free_b > ((size_t)1 << 30) ? free_b - ((size_t)1 << 30) : 0);
+        int zc = 0;
+        size_t wb = 0;
+        paint_disc_plan(w, h, z_hi - z_lo, ipv, std::min(avail, (size_t)6 << 30), &zc, &wb);
+        if (wb > avail) return BJT_OK;                         // does not fit: not done
+        void *wsp;
+        WS("paint_disc", wb, wsp);
+        const int nchunks = (z_hi - z_lo + zc - 1) / zc;
+        while (c->pev.size() < (size_t)(2 * nchunks + 1)) { cudaEvent_t e; CK(cudaEventCreate(&e)); c->pev.push_back(e); }
+        CK(cudaMemsetAsync(scal + 8, 0, 4, c->stream));
+        c->launches += launch_paint_disc(ridge, w, h, dext, z_lo, z_hi, max_r, zc, ipv, wsp, rsq, scal + 8, c->pev.data(),
+                                         c->stream); CKL();
+        CK(peek(c, c->h_scal + 8, scal + 8, 4));
+        CK(cudaStreamSynchronize(c->stream));
+        c->paint_ms[0] = c->paint_ms[1] = c->paint_ms[2] = 0.f;
+        for (int k = 0; k < nchunks; ++k) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, c->pev[2 * k], c->pev[2 * k + 1]);
+            cudaEventElapsedTime(&b, c->pev[2 * k + 1], c->pev[2 * k + 2]);
+            c->paint_ms[0] += a; c->paint_ms[1] += b;
+        }
+        c->paint_launches[0] = nchunks; c->paint_launches[1] = nchunks; c->paint_launches[2] = 0;
+        if (c->h_scal[8] == 0) { *done = 1; return BJT_OK; }
+    }
+    return BJT_OK;
+}
+
 static int dev_paint(bjt_ctx *c, const uint32_t *ridge, int w, int h, int d, int path, int64_t n_ridge_known,
                      int64_t max_r, uint32_t *rsq, int *path_used) {
     const size_t N = (size_t)w * h * d;
     if (path < 0) path = c->paint_path;
     const bool forced = path >= 0;
-    if (path <= 1) {
+    if (path <= 1 || path == 4) {
         uint32_t *scal;
         WS("scalars", 256, scal);
-        if (max_r < 0) {   // largest tag decides whether items fit 16+16 bits
+        if (max_r < 0) {   // largest tag: decides the painter and the item width
             CK(cudaMemsetAsync(scal + 14, 0, 4, c->stream));
             c->launches += launch_mark_present(ridge, N, nullptr, scal + 14, c->stream); CKL();
             CK(peek(c, c->h_scal + 14, scal + 14, 4));
             CK(cudaStreamSynchronize(c->stream));
             max_r = c->h_scal[14];
         }
+    }
+    if (path < 0 || path == 4) {
+        if (paint_disc_supports((uint32_t)max_r)) {
+            int done = 0;
+            const int rc = dev_paint_disc(c, ridge, w, h, d, 0, d, (uint32_t)max_r, rsq, &done);
+            if (rc) return rc;
+            if (done) { if (path_used) *path_used = 4; return BJT_OK; }
+        }
+        if (forced) return fail(c, BJT_E_ARG, "paint path 4 cannot take this volume (largest r^2 %lld, or no room for its items)", (long long)max_r);
+    }
+    if (path <= 1) {
+        uint32_t *scal;
+        WS("scalars", 256, scal);
         int wide = max_r >= 65536 ? 1 : 0;
         if (forced && path == 0 && wide) return fail(c, BJT_E_ARG, "paint path 0 needs r^2 < 65536 (largest is %lld)", (long long)max_r);
         if (forced && path == 1) wide = 1;
@@ -476,7 +543,7 @@ static int dev_pipeline(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, in
         tm->rsq_max = maxval;
         tm->paint_path = path_used;
         tm->n_launches = c->launches - launches0;
-        const bool sep = path_used == 0 || path_used == 1;
+        const bool sep = path_used == 0 || path_used == 1 || path_used == 4;
         tm->ms_paint_x = sep ? c->paint_ms[0] : 0.f;
         tm->ms_paint_y = sep ? c->paint_ms[1] : 0.f;
         tm->ms_paint_z = sep ? c->paint_ms[2] : 0.f;

@@ -28,6 +28,32 @@ __device__ __forceinline__ uint32_t isqrt_floor(uint32_t v) {
     while ((r + 1u) * (r + 1u) <= v) ++r;
     return r;
 }
+// the same through the approximate square root (one MUFU): the float root of a value below 2^28 is off by far less
+// than 1, so its truncation is the answer or one beside it
+__device__ __forceinline__ uint32_t isqrt_fast(uint32_t v) {
+#ifdef BJT_CUDA_EMU
+    uint32_t r = (uint32_t)sqrtf((float)v);
+#else
+    float f;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"((float)v));
+    uint32_t r = (uint32_t)f;
+#endif
+    if (r * r > v) --r;
+    else if ((r + 1u) * (r + 1u) <= v) ++r;
+    return r;
+}
+// floor(sqrt(v)) for v < 2^18 without a correction step: sqrt(v + 0.5) lies at least 1 / (4 * 512) away from every
+// integer, the approximate root (a couple of ulp of 2^-15) cannot cross one
+__device__ __forceinline__ int isqrt_small(uint32_t v) {
+#ifdef BJT_CUDA_EMU
+    return (int)sqrtf((float)v + 0.5f);
+#else
+    float f;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(f) : "f"((float)v + 0.5f));
+    return (int)f;
+#endif
+}
+
 __device__ __forceinline__ uint32_t isqrt_ceil(uint32_t v) {
     uint32_t r = isqrt_floor(v);
     return r * r < v ? r + 1u : r;
@@ -58,6 +84,16 @@ int launch_compact_ridge(const uint32_t *ridge, int w, int h, int d, uint4 *poin
 int launch_paint_scatter(const uint4 *points, unsigned long long npoints, int w, int h, int d, uint32_t *rsq,
                          cudaStream_t s);
 int launch_fill_u32(uint32_t *p, size_t n, uint32_t v, cudaStream_t s);
+
+// fronts along z + discs in the plane (path 4), see paint_disc.cu
+bool paint_disc_supports(uint32_t rsq_max);
+void paint_disc_plan(int w, int h, int nplanes, int items_per_voxel, size_t budget_bytes, int *chunk_planes,
+                     size_t *workspace_bytes);
+int launch_paint_disc(const uint32_t *ridge, int w, int h, int dext, int z_lo, int z_hi, uint32_t rsq_max,
+                      int chunk_planes, int items_per_voxel, void *workspace, uint32_t *out, uint32_t *flags,
+                      cudaEvent_t *events, cudaStream_t s);
+
+int launch_isqrt_small_check(uint32_t *mismatches, cudaStream_t s);   // self-check of the disc kernel's square root
 
 // separable paint (paths 0/1), see paint_sep.cu
 size_t paint_sep_workspace_bytes(int w, int h, int d, int wide);

@@ -48,11 +48,14 @@ typedef struct bjt_timing {
     int64_t n_ridge;        /* distance-ridge points painted                                */
     int64_t n_launches;     /* kernels of this library launched by the call                 */
     uint32_t rsq_max;       /* largest squared EDT value                                    */
-    int32_t paint_path;     /* 0 = separable (16-bit items), 1 = separable (32-bit items),
-                               2 = brute-force scatter, 3 = constant fast path (no background) */
-    float   ms_paint_x, ms_paint_y, ms_paint_z;   /* separable painter by stage (0 on the other paths)  */
-    int32_t n_paint_y_sweeps;                     /* launches of the y-stage sweep kernel (the dominant
-                                                     kernel): 2 directions x column blocks               */
+    int32_t paint_path;     /* 0 = separable sweeps (16-bit items), 1 = separable sweeps (32-bit items),
+                               2 = brute-force scatter, 3 = constant fast path (no background),
+                               4 = fronts along z + discs in the plane (the default)                    */
+    float   ms_paint_x, ms_paint_y, ms_paint_z;   /* painter by stage.  Paths 0/1: x, y, z sweeps.  Path 4:
+                                                     ms_paint_x = front kernel, ms_paint_y = disc kernel   */
+    int32_t n_paint_y_sweeps;                     /* launches of the dominant kernel: paths 0/1 the y-stage
+                                                     sweep (2 directions x column blocks), path 4 the disc
+                                                     kernel (one per chunk of planes)                       */
 } bjt_timing;
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -62,7 +65,7 @@ const char *bjt_last_error(const bjt_ctx *ctx);        /* ctx may be NULL (creat
 int  bjt_set_stream(bjt_ctx *ctx, void *cuda_stream);  /* cudaStream_t; NULL = default stream    */
 int  bjt_release_workspace(bjt_ctx *ctx);              /* free cached device buffers             */
 int  bjt_device_info(bjt_ctx *ctx, char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor);
-/* paint_path override for tests: -1 automatic (default), 0/1/2 force that path */
+/* paint_path override for tests: -1 automatic (default), 0/1/2/4 force that path */
 int  bjt_set_paint_path(bjt_ctx *ctx, int path);
 /* kernels of this library launched through this context so far */
 int64_t bjt_launch_count(const bjt_ctx *ctx);
@@ -79,6 +82,9 @@ int  bjt_paint_block_cols(int w, int h, int d);
 int  bjt_paint_set_block_cols(int cols);
 /* test hook: the same call under its older name */
 int  bjt_debug_set_xslab_cols(int cols);
+/* self-check: the disc painter's correction-free integer square root (paint path 4) against the exact one for
+ * every argument it is specified for (values below 2^18); *mismatches must come back 0 */
+int  bjt_debug_isqrt_check(bjt_ctx *ctx, int64_t *mismatches);
 /* lines the last separable paint of this context sent to its redo kernels */
 int64_t bjt_debug_paint_redo_lines(bjt_ctx *ctx);
 /* page-locked host memory (what a JNI direct ByteBuffer / the bench wraps so copies are DMA) */

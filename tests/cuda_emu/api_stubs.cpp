@@ -4,4 +4,5 @@
 
 namespace bjt {
 alignas(16) uint32_t sm_raw[(128 * 1024) / 4];
+namespace disc_detail { alignas(16) uint32_t zf_smem[(224 * 1024) / 4], dk_smem[(128 * 1024) / 4]; }   // paint_disc.cu
 }  // namespace bjt

@@ -270,6 +270,8 @@ inline unsigned __ballot_sync(unsigned mask, int pred) {
     return m;
 }
 inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0u; }
+inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) { (void)emu::warp_gather(mask, 0ull); }
+inline float __fsqrt_rn(float v) { return sqrtf(v); }
 inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
     const unsigned long long *s = emu::warp_gather(mask, v);
     unsigned m = 0;

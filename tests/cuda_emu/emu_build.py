@@ -12,7 +12,7 @@ _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _CSRC = os.path.join(_ROOT, "bonej2_b200", "csrc")
 _OUTDIR = os.path.join(_ROOT, "tests", "_build")
 OUT = os.path.join(_OUTDIR, "libkernels_emu.so")
-KERNEL_SOURCES = ["edt.cu", "ridge.cu", "paint_sep.cu", "finish.cu", "paint_scatter.cu", "phantom.cu"]
+KERNEL_SOURCES = ["edt.cu", "ridge.cu", "paint_sep.cu", "paint_disc.cu", "finish.cu", "paint_scatter.cu", "phantom.cu"]
 _DEPS = [os.path.join(_CSRC, f) for f in KERNEL_SOURCES + ["common.cuh", "paint_sep_core.cuh"]] + \
         [os.path.join(_HERE, f) for f in ("cuda_runtime.h", "harness.cpp", "emu_build.py")]
 
@@ -121,7 +121,7 @@ def build(force=False):
 
 
 API_OUT = os.path.join(_OUTDIR, "libbonejthickness_emu.so")
-API_SOURCES = ["api.cu", "edt.cu", "ridge.cu", "paint_sep.cu", "paint_scatter.cu", "finish.cu", "phantom.cu", "segstats.cu",
+API_SOURCES = ["api.cu", "edt.cu", "ridge.cu", "paint_sep.cu", "paint_disc.cu", "paint_scatter.cu", "finish.cu", "phantom.cu", "segstats.cu",
                "ridgepoints.cu"]
 
 

@@ -6,7 +6,8 @@
 #include <vector>
 
 namespace bjt {
-alignas(16) uint32_t sm_raw[(128 * 1024) / 4];      // the dynamic shared memory of edt_tile_kernel (budget 100 KB)
+alignas(16) uint32_t sm_raw[(128 * 1024) / 4];
+namespace disc_detail { alignas(16) uint32_t zf_smem[(224 * 1024) / 4], dk_smem[(128 * 1024) / 4]; }   // paint_disc.cu      // the dynamic shared memory of edt_tile_kernel (budget 100 KB)
 }
 
 using namespace bjt;
@@ -173,6 +174,30 @@ int emu_paint_slabs(const uint32_t *ridge, int w, int h, int d, const int *cuts,
     }
     paint_sep_set_xslab_cols(0);
     return rc;
+}
+
+// api.cu dev_paint_disc (path 4): planes [z_lo, z_hi) of a ridge volume of d planes, in chunks of chunk_planes
+// (0 = the plan's choice); items_per_voxel sizes the pool.  *flags != 0: pool overflow.
+int emu_paint_disc(const uint32_t *ridge, int w, int h, int d, int z_lo, int z_hi, int chunk_planes, int items_per_voxel,
+                   uint32_t *rsq, uint32_t *flags) {
+    const size_t N = (size_t)w * h * d, M = (size_t)w * h * (z_hi - z_lo);
+    uint32_t max_r = 0;
+    for (size_t i = 0; i < N; ++i) max_r = ridge[i] > max_r ? ridge[i] : max_r;
+    if (!paint_disc_supports(max_r)) return -1;
+    int zc = 0;
+    size_t wb = 0;
+    paint_disc_plan(w, h, z_hi - z_lo, items_per_voxel, 0, &zc, &wb);
+    if (chunk_planes > 0) { zc = chunk_planes; paint_disc_plan(w, h, zc, items_per_voxel, 0, &zc, &wb); zc = chunk_planes; }
+    Guarded g_ws(wb), g_ridge(N * 4), g_rsq(M * 4);
+    memset(g_ws.p, 0xCD, wb);
+    memcpy(g_ridge.p, ridge, N * 4);
+    memset(g_rsq.p, 0xAB, M * 4);                       // the painter must write every voxel
+    uint32_t f = 0;
+    const int launches = launch_paint_disc(g_ridge.as<uint32_t>(), w, h, d, z_lo, z_hi, max_r, zc, items_per_voxel, g_ws.p,
+                                           g_rsq.as<uint32_t>(), &f, nullptr, nullptr);
+    memcpy(rsq, g_rsq.p, M * 4);
+    if (flags) *flags = f;
+    return launches;
 }
 
 // api.cu dev_paint, scatter fallback (path 2): count, compact the ridge points, scatter-max every ball

@@ -89,6 +89,18 @@ def finish(rsq_u32, original_u8, inverse=False, pixel_width=1.0, z_lo=0, z_hi=No
     return out, dict(sum=res[0], sum2=res[1], min=res[2], max=res[3], count=int(res[4]))
 
 
+def paint_disc(ridge_u32, z_lo=0, z_hi=None, chunk_planes=0, items_per_voxel=3):
+    """fronts along z + discs in the plane (paint path 4) over planes [z_lo, z_hi): (painted r^2 of those planes, flags)"""
+    r = np.ascontiguousarray(ridge_u32, np.uint32)
+    d, h, w = r.shape
+    z_hi = d if z_hi is None else z_hi
+    out = np.empty((z_hi - z_lo, h, w), np.uint32)
+    flags = C.c_uint32(0)
+    rc = lib().emu_paint_disc(_p(r), w, h, d, int(z_lo), int(z_hi), int(chunk_planes), int(items_per_voxel), _p(out), C.byref(flags))
+    assert rc > 0, rc
+    return out, int(flags.value)
+
+
 def paint_scatter(ridge_u32):
     """the scatter fallback painter (paint path 2)"""
     r = np.ascontiguousarray(ridge_u32, np.uint32)

@@ -74,7 +74,7 @@ def test_stages(ctx, oracle, name, inverse):
     assert np.array_equal(rg_g > 0, rg_o > 0), "ridge set differs"
     assert np.array_equal(rg_g[rg_g > 0], sq[rg_g > 0])
     lt_o, rsq_o = oracle.paint(rg_o)
-    for path in (2, 0, 1, -1):
+    for path in (2, 0, 1, 4, -1):
         assert np.array_equal(ctx.paint_rsq(rg_g, path=path), rsq_o), f"painted r^2 differs (path {path})"
     cl_o = oracle.cleanup(lt_o)
     cl_g, _ = ctx.cleanup(rsq_o, calibrate=False)
@@ -170,3 +170,22 @@ def test_edt_odd_line_lengths(ctx, oracle, shape, inverse):
     vol = shapes.random_blobs(shape, 11)
     _, want = oracle.edt(vol, inverse=inverse)
     assert np.array_equal(ctx.edt_sq(vol, inverse=inverse), want)
+
+
+def test_disc_painter_integer_root(ctx):
+    """the disc painter's correction-free integer square root is exact for every argument below 2^18"""
+    assert ctx.debug_isqrt_check() == 0
+
+
+@pytest.mark.parametrize("shape,inverse", [((96, 80, 72), True), ((80, 96, 40), False), ((130, 70, 33), True)])
+def test_disc_painter_odd_shapes(ctx, oracle, shape, inverse):
+    from bonej2_b200.phantom import phantom_shapes
+    """paint path 4 (fronts along z + discs in the plane) on extents that are not multiples of its blocks
+    (32 columns x 32 planes for the fronts, 64 x 32 tiles for the discs), bitwise against the oracle's scatter paint"""
+    w, h, d = shape
+    vol = oracle.phantom_raster(phantom_shapes(w, h, d, seed=3), w, h, d)
+    dist, sq = oracle.edt(vol, inverse=inverse)
+    rg = oracle.ridge(dist)
+    _, rsq = oracle.paint(rg)
+    ridge = np.where(rg > 0, sq, 0).astype(np.uint32)
+    assert np.array_equal(ctx.paint_rsq(ridge, path=4), rsq)
