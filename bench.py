@@ -8,9 +8,12 @@ trabecular phantom -- what ThicknessWrapper.run() does for one dataset (Thicknes
              maps and their statistics are left in HBM; CUDA events on the stream the kernels use.
   e2e        the same work through the C-ABI call a JNI shim binds (bjt_thickness_both_u8) with
              page-locked HOST buffers: upload and both map downloads are inside the timed region.
-  roofline   the dominant kernel (the painter's y-stage sweep): algorithmic bytes of one launch over its
-             launch time from events inside the library, against the measured HBM peak; every stage,
-             the EDT passes included (the "EDT HBM GB/s" of the metric), is under `stages`.
+  roofline   the dominant kernel (the painter's disc kernel): SURVEY.md 8(d)'s algorithmic bytes of one launch
+             over its launch time from events inside the library, against the measured HBM peak
+             (`structure_frac`: the same with the bytes the kernel's own data structure moves); every
+             stage, the EDT passes included (the "EDT HBM GB/s" of the metric), is under `stages`.
+  map_hash   position-weighted 64-bit checksums of both maps over eight z ranges: the same at every N when
+             the N-GPU maps equal the single-GPU maps bit for bit.
   cpu_baseline  the CPU oracle (a restatement of sc.fiji LocalThickness_, no JVM in the image) on
              a bounded sample of the same workload, on the box's host cores.
 
@@ -114,8 +117,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u32/f32", "data": "synthetic",
-        "config": {"workload": f"BoneJ Thickness Tb.Th+Tb.Sp, mask on, {args.size}^3 synthetic trabecular phantom",
-                   "timed_sample": sample},
+        "config": {"workload": f"BoneJ Thickness Tb.Th+Tb.Sp (mapChoice Both), mask on, synthetic trabecular phantom: "
+                               f"{n_sample}^3 timed here (bounded CPU sample of the {args.size}^3 workload of the GPU arm)",
+                   "volume_timed": [n_sample] * 3, "volume_gpu_arm": [args.size] * 3, "timed_sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "note": "CPU restatement of sc.fiji LocalThickness_ (no JVM in image)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -182,14 +186,40 @@ def main():
         from bonej2_b200 import sharded
         sampler = ClockSampler(local_rank)
         sampler.start()
-        result = sharded.bench(args, rank, world, local_rank, dist)
+        r = sharded.bench(args, rank, world, local_rank, dist)
         clocks = sampler.stop()
         if rank == 0:
-            result["clocks"] = clocks
-            result["roofline"]["peak"] = hbm_peak
-            result["roofline"]["frac"] = result["roofline"]["achieved"] / hbm_peak
-            result["roofline"]["peak_kind"] = peak_kind
-            emit(result)
+            n = args.size
+            N = n ** 3
+            ph = r["phases_max_ms"]
+            paint_ms = ph.get("paint", 0.0)
+            # the same dominant kernel as at N = 1 (the painter's disc kernel is inside `paint`; the phase also holds the
+            # front kernel): SURVEY.md 8(d) bytes of the painter over the slowest rank's paint phase
+            alg_paint = 4.0 * N * 2                                   # + 16 B per ridge point, not gathered here: a lower bound
+            gbs = alg_paint / world / (paint_ms * 1e-3) / 1e9 if paint_ms > 0 else 0.0
+            edt_ms = ph.get("edt_xy", 0.0) + ph.get("edt_z", 0.0)
+            edt_gbs = 21.0 * N * 2 / world / (edt_ms * 1e-3) / 1e9 if edt_ms > 0 else 0.0
+            line = {
+                "metric": METRIC, "value": N / (r["dev_ms"] * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": r["dev_ms"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u32/f32", "data": "synthetic",
+                "config": {"workload": f"BoneJ Thickness Tb.Th+Tb.Sp (mapChoice Both), mask on, {n}^3 synthetic trabecular "
+                                       f"phantom, z-slabs over {world} GPUs (BASELINE.json configs[{3 if n >= 2048 else 2}])",
+                           "volume": [n, n, n], "parallelism": f"z-slab x{world}", "seed": SEED,
+                           "l2_policy": "inputs exceed the 126 MB L2"},
+                "e2e": {"value": N / (r["e2e_ms"] * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": r["e2e_ms"],
+                        "h2d_bytes_per_step": N, "d2h_bytes_per_step": 8 * N},
+                "gpu_launches": r["launches"],
+                "roofline": {"kernel": "disc_kernel + zfront_kernel (painter, paint path 4), slowest rank's paint phase per step",
+                             "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                             "traffic": None, "peak_kind": peak_kind,
+                             "note": "per GPU; instruction-issue bound, not HBM bound (profiles/README.md)"},
+                "stages": {"edt_total": {"ms_per_step": round(edt_ms, 3), "GBps_per_gpu": round(edt_gbs, 1),
+                                         "frac_of_hbm_peak": round(edt_gbs / hbm_peak, 4)}},
+                "phases_max_over_ranks_ms": ph, "phases_rank0_ms": r["phases_rank0_ms"],
+                "map_hash": r["hashes"], "results": r["results"], "cpu_baseline": None, "clocks": clocks,
+            }
+            emit(line)
         dist.destroy_process_group()
         return
 
@@ -240,6 +270,11 @@ def main():
     dev_ms = ev0.elapsed_time(ev1) / args.steps
     stats_dev = [res[0][0].as_dict(), res[1][0].as_dict()]
     paint_paths = [res[0][1].paint_path, res[1][1].paint_path]
+    from bonej2_b200.sharded import map_hashes
+    hashes = {}
+    for name, t in (("tb_th", d_th), ("tb_sp", d_sp)):
+        hh = map_hashes(t.view(n, n, n), 0, (n, n, n))
+        hashes[name] = [format(hh[k], "016x") if k in hh else None for k in range(8)]
 
     # ---- end to end through the C-ABI with page-locked host buffers --------------------------------
     L = _native.lib()
@@ -287,33 +322,44 @@ def main():
     edt_gbs = 21.0 * N * 2 / (edt_ms * 1e-3) / 1e9
     stages["edt_total"] = {"ms_per_step": round(edt_ms, 3), "alg_GB": round(42.0 * N / 1e9, 3), "GBps": round(edt_gbs, 1),
                            "frac_of_hbm_peak": round(edt_gbs / hbm_peak, 4)}
-    # The dominant kernel is the painter's y-stage sweep, sep_dyn_kernel<., 2, +-1> (one launch = one direction over one
-    # block of columns; each is followed by its redo kernel, microseconds).  Algorithmic bytes of a launch (DESIGN.md
-    # 4.3): the list index words it cannot avoid -- two 8-byte words read and one written per voxel of the block
-    # (the items themselves, about 4 B x 5 per voxel, are not counted).  Launch time: events around the y stage of
-    # every block inside the library (bjt_timing.ms_paint_y), on the stream the kernels run on.
+    # The dominant kernel.  Paint path 4: disc_kernel (one launch per chunk of planes; ms_paint_y = their sum from events
+    # inside the library, on the stream the kernels run on).  `achieved` uses SURVEY.md 8(d)'s algorithmic bytes of the
+    # painter (4 B per voxel written + 16 B per ridge point) -- that figure belongs to the painter as a whole, so it is
+    # divided by the whole painter's time and attributed per launch of the disc kernel by its share.  `structure_*`:
+    # the bytes this kernel's own data structure moves per launch (items read once per tile they touch are not counted
+    # twice: 8 B per front item + 8 B descriptor per 32 voxels read, 4 B per voxel written).
     sweeps_per_step = y_sweeps / args.steps
     if sweeps_per_step > 0 and per_step["ms_paint_y"] > 0:
+        disc = paint_paths[1] == 4
         launch_ms = per_step["ms_paint_y"] / sweeps_per_step
-        launch_bytes = 24.0 * N * 4.0 / sweeps_per_step    # 24 B x voxels of one block: blocks per run = sweeps / (2 runs x 2 directions)
-        y_gbs = launch_bytes / (launch_ms * 1e-3) / 1e9
+        alg_launch = alg["ms_paint"] / sweeps_per_step
+        gbs = alg["ms_paint"] / (per_step["ms_paint"] * 1e-3) / 1e9
+        if disc:
+            struct_launch = (4.0 + 0.25) * N * 2 / sweeps_per_step + 8.0 * 1.6 * N * 2 / sweeps_per_step
+            name = "disc_kernel (painter, paint path 4: sparse-table disc tiles)"
+        else:
+            struct_launch = 24.0 * N * 4.0 / sweeps_per_step
+            name = "sep_dyn_kernel<PACKED,2,+-1> (painter y-stage sweep)"
         traffic = traffic_build = None
         try:
-            rec = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ystage_traffic.json")))
-            if rec.get("volume") == [n, n, n]:
+            rec = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "disc_traffic.json")))
+            if rec.get("volume") == [n, n, n] and disc:
                 traffic = rec["dram_bytes_per_launch"]
                 traffic_build = rec.get("build")
         except (OSError, ValueError, KeyError):
             pass
-        roofline = {"kernel": "sep_dyn_kernel<PACKED,2,+-1> (painter y-stage sweep)", "bound": "hbm", "achieved": y_gbs,
-                    "peak": hbm_peak, "unit": "GB/s", "frac": y_gbs / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
-                    "launch_ms": round(launch_ms, 3), "launches_per_step": sweeps_per_step,
-                    "algorithmic_bytes_per_launch": launch_bytes,
+        roofline = {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                    "traffic": traffic, "peak_kind": peak_kind, "launch_ms": round(launch_ms, 3),
+                    "launches_per_step": sweeps_per_step, "algorithmic_bytes_per_launch": alg_launch,
+                    "structure_bytes_per_launch": struct_launch,
+                    "structure_frac": struct_launch / (launch_ms * 1e-3) / 1e9 / hbm_peak,
                     "share_of_step": round(per_step["ms_paint_y"] / dev_ms, 4),
-                    "note": "instruction-issue bound, not HBM bound (profiles/README.md); `stages` holds the streaming kernels"}
+                    "note": "`achieved` = SURVEY.md 8(d) painter bytes over the whole painter's time; the kernel is bound by "
+                            "instruction issue and shared-memory atomics, not HBM (profiles/README.md); `stages` holds the "
+                            "streaming kernels"}
         if traffic_build:
             roofline["traffic_capture"] = traffic_build
-    else:   # the separable painter did not run (constant fast path / scatter fallback): report the slowest stage
+    else:   # no list-based painter ran (constant fast path / scatter fallback): report the slowest stage
         dom = max(alg, key=lambda k: per_step[k])
         dom_gbs = alg[dom] / (per_step[dom] * 1e-3) / 1e9
         roofline = {"kernel": dom[3:], "bound": "hbm", "achieved": dom_gbs, "peak": hbm_peak, "unit": "GB/s",
@@ -339,7 +385,7 @@ def main():
         "e2e": {"value": N / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": N,
                 "d2h_bytes_per_step": 8 * N, "host_maps_match_device": same},
         "gpu_launches": int(launches),
-        "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "clocks": clocks,
+        "roofline": roofline, "stages": stages, "map_hash": hashes, "cpu_baseline": cpu, "clocks": clocks,
         "results": {"tb_th": {k: stats_dev[0][k] for k in ("count", "mean", "sd", "max")},
                     "tb_sp": {k: stats_dev[1][k] for k in ("count", "mean", "sd", "max")}},
     }

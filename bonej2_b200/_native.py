@@ -84,6 +84,7 @@ _SIGS = {
     "bjt_dev_label_stats_f32": ([_VP, _VP, _VP, C.c_size_t, _I, _VP, _VP], _I),
     "bjt_slice_stats_f32": ([_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP], _I),
     "bjt_dev_slice_stats_f32": ([_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP, _VP], _I),
+    "bjt_dev_paint_range": ([_VP, _VP, _I, _I, _I, _I, _I, C.c_int64, _VP], _I),
     "bjt_dev_paint_open": ([_VP, _VP, _I, _I, _I, C.c_int64], _I),
     "bjt_dev_paint_nxslabs": ([_VP], _I),
     "bjt_dev_paint_xslab_width": ([_VP, _I], _I),
@@ -364,6 +365,9 @@ class Context:
 
     def dev_paint(self, d_ridge, w, h, d, d_rsq, path=-1):
         self._ck(lib().bjt_dev_paint(self._h, d_ridge, w, h, d, int(path), d_rsq))
+
+    def dev_paint_range(self, d_ridge, w, h, d, z_lo, z_hi, max_rsq, d_rsq):
+        self._ck(lib().bjt_dev_paint_range(self._h, d_ridge, w, h, d, int(z_lo), int(z_hi), int(max_rsq), d_rsq))
 
     def dev_finish_range(self, d_rsq, d_original, w, h, d, z_lo, z_hi, inverse, calibrate, pixel_width, d_out):
         st = Stats()

@@ -951,6 +951,42 @@ int bjt_find_ridge_points_u8(bjt_ctx *c, const uint8_t *in, int w, int h, int d,
     return BJT_OK;
 }
 
+// Painted r^2 of planes [z_lo, z_hi) of a ridge volume of d planes (a z-slab with its halo): balls centred on any
+// plane of d_ridge count, only the requested planes are painted.  max_rsq: largest tag anywhere in the whole volume
+// (the ranks of a sharded run pass the same value), < 0: determined here.
+int bjt_dev_paint_range(bjt_ctx *c, const uint32_t *d_ridge, int w, int h, int d, int z_lo, int z_hi, int64_t max_rsq,
+                        uint32_t *d_rsq) {
+    ENTER(c);
+    int rc = check_dims(c, w, h, d);
+    if (rc) return rc;
+    if (!d_ridge || !d_rsq) return fail(c, BJT_E_ARG, "paint_range: null pointer");
+    if (z_lo < 0 || z_hi > d || z_lo >= z_hi) return fail(c, BJT_E_ARG, "paint_range: bad plane range [%d, %d) of %d", z_lo, z_hi, d);
+    const size_t N = (size_t)w * h * d, wh = (size_t)w * h;
+    uint32_t *scal;
+    WS("scalars", 256, scal);
+    if (max_rsq < 0) {
+        CK(cudaMemsetAsync(scal + 14, 0, 4, c->stream));
+        c->launches += launch_mark_present(d_ridge, N, nullptr, scal + 14, c->stream); CKL();
+        CK(peek(c, c->h_scal + 14, scal + 14, 4));
+        CK(cudaStreamSynchronize(c->stream));
+        max_rsq = c->h_scal[14];
+    }
+    if ((c->paint_path < 0 || c->paint_path == 4) && paint_disc_supports((uint32_t)max_rsq)) {
+        int done = 0;
+        rc = dev_paint_disc(c, d_ridge, w, h, d, z_lo, z_hi, (uint32_t)max_rsq, d_rsq, &done);
+        if (rc) return rc;
+        if (done) return BJT_OK;
+    }
+    // radii beyond the disc painter (or a forced path): paint every plane of the slab, keep the requested ones
+    uint32_t *tmp;
+    WS("paint_range_tmp", N * sizeof(uint32_t), tmp);
+    rc = dev_paint(c, d_ridge, w, h, d, c->paint_path == 4 ? -1 : c->paint_path, -1, max_rsq, tmp, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(d_rsq, tmp + (size_t)z_lo * wh, (size_t)(z_hi - z_lo) * wh * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return BJT_OK;
+}
+
 // ---- stepwise painter of one z-slab -------------------------------------------------------------------
 int bjt_dev_paint_open(bjt_ctx *c, const uint32_t *d_ridge, int w, int h, int d, int64_t max_rsq) {
     ENTER(c);

@@ -4,16 +4,13 @@ The volume [d][h][w] is cut into contiguous z-slabs, one per rank
 
   EDT x, y          slab-local kernels
   EDT z             all-to-all transpose z-slabs -> y-slabs, z pass on whole z lines, transpose back
-  ridge             on the slab's own planes (one fetched plane of squared EDT either side)
-  paint             the painter's x and y stages are plane-local; its z sweeps cross slab faces.  What crosses
-                    is, per (x, y) column, the staircase (tag, reach beyond the face) of the balls centred
-                    within r_max planes of the face (r_max from an all-reduce of the largest squared
-                    distance): every rank exports that to the slabs within reach, imports theirs and sweeps
-                    its own planes (the "max-radius halo exchange" of BASELINE.json's north_star, with the
-                    halo reduced to what actually reaches across).  Fallback, and the only path of backends
-                    without the stepwise painter: fetch the squared-EDT planes within r_max + 2 and paint
-                    slab + halo locally.
-  cleanup .. stats  on slab +- 2 painted planes (fetched), output and statistics restricted to the slab
+  r_max             all-reduce of the largest squared distance: no ball reaches further than H = floor(sqrt(max))
+  halo              ONE exchange per run: every rank fetches the squared-EDT planes within H + 3 of its slab (the
+                    "max-radius halo exchange" of BASELINE.json's north_star)
+  ridge             on slab +- (H + 2) planes (the outermost fetched plane only serves as a neighbour)
+  paint             planes slab +- 2 only (bjt_dev_paint_range): the painter's fronts run along z and read the ridge
+                    within H of a plane, its discs are plane-local, so nothing else crosses a slab face
+  cleanup .. stats  on slab +- 2 painted planes, output and statistics restricted to the slab
                     (bjt_dev_finish_range); (n, sum, sum^2, min, max) are combined across ranks before
                     mean and sd are formed, as ij.process.StackStatistics does on the whole stack
 
@@ -212,59 +209,12 @@ class CudaStages:
         self.ctx.dev_ridge(sq_ext.data_ptr(), w, h, de, out.data_ptr())
         return out
 
-    def paint(self, ridge_ext):
+    def paint_range(self, ridge_ext, z_lo, z_hi, max_rsq):
+        """painted r^2 of planes [z_lo, z_hi) of ridge_ext (balls centred on any plane of ridge_ext count)"""
         de, h, w = ridge_ext.shape
-        out = self._i32((de, h, w))
-        self.ctx.dev_paint(ridge_ext.data_ptr(), w, h, de, out.data_ptr())
+        out = self._i32((z_hi - z_lo, h, w))
+        self.ctx.dev_paint_range(ridge_ext.data_ptr(), w, h, de, z_lo, z_hi, max_rsq, out.data_ptr())
         return out
-
-    # stepwise painter (bjt_dev_paint_open .. _close); boundary buffers are int32 tensors [ncol * (2 kcap + 1)]:
-    # items first (8-byte aligned), counts behind
-    def paint_open(self, ridge_own, max_rsq):
-        dz, h, w = ridge_own.shape
-        self._ps = (ridge_own, self._i32((dz, h, w)))
-        return self.ctx.dev_paint_open(ridge_own.data_ptr(), w, h, dz, max_rsq)
-
-    def paint_xslab_cols(self, xs):
-        return self.ctx.dev_paint_xslab_width(xs) * self._ps[0].shape[1]
-
-    def paint_block_cols(self, shape):
-        """column-block width the library would choose for a slab of this shape (not clipped to the width)"""
-        dz, h, w = shape
-        return self.ctx.paint_block_cols(w, h, dz)
-
-    def paint_set_block_cols(self, cols):
-        self.ctx.paint_set_block_cols(cols)
-
-    def paint_lists(self, xs):
-        self.ctx.dev_paint_lists(xs)
-
-    def boundary_buffer(self, ncol, kcap):
-        return torch.empty(ncol * (2 * kcap + 1), dtype=torch.int32, device=self.device)
-
-    @staticmethod
-    def _split(buf, ncol, kcap):
-        return buf.data_ptr() + 8 * ncol * kcap, buf.data_ptr()              # (count pointer, items pointer)
-
-    def paint_export(self, xs, side, gap, nplanes, buf, ncol, kcap):
-        cnt, items = self._split(buf, ncol, kcap)
-        self.ctx.dev_paint_export(xs, side, gap, nplanes, cnt, items, kcap)
-
-    def paint_sweep(self, xs, lo, hi, ncol, kcap):
-        self.ctx.dev_paint_sweep(xs, [self._split(b, ncol, kcap) for b in lo], [self._split(b, ncol, kcap) for b in hi],
-                                 kcap, self._ps[1].data_ptr())
-
-    def paint_close(self):
-        flags = self.ctx.dev_paint_close()
-        out = self._ps[1]
-        self._ps = None
-        return out, flags
-
-    def plane_weights(self, ridge):
-        """cost estimate per plane of a ridge slab (see plane_costs)"""
-        nz, h, w = ridge.shape
-        q = ridge.sum(dim=(1, 2), dtype=torch.float64) / float(h * w)
-        return (float(h * w) * (COST_BASE + q * q)).tolist()
 
     def full(self, shape, value):
         return torch.full(shape, value, dtype=torch.int32, device=self.device)
@@ -285,136 +235,32 @@ def no_result(n: int) -> int:
     return 3 * (n + 1) * (n + 1)
 
 
-def balanced_ranges(weights, parts: int):
-    """contiguous ranges of range(len(weights)) with near-equal weight sums (ranges may be empty)"""
-    n = len(weights)
-    total = float(sum(weights))
-    if n == 0 or total <= 0.0:
-        return split_ranges(n, parts)
-    cuts, acc, k = [0], 0.0, 1
-    for i, wgt in enumerate(weights):
-        acc += float(wgt)
-        while k < parts and acc >= k * total / parts:
-            cuts.append(i + 1)
-            k += 1
-    while len(cuts) < parts:
-        cuts.append(n)
-    cuts.append(n)
-    return [(cuts[i], max(cuts[i], cuts[i + 1])) for i in range(parts)]
+class PhaseTimer:
+    """device time per phase from CUDA events on the current stream (no synchronisation inside the timed loop);
+    on CPU backends wall-clock time"""
+
+    def __init__(self, device):
+        self.cuda = str(device).startswith("cuda")
+        self.marks, self.ms = [], {}
+
+    def mark(self, name):
+        if self.cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((name, ev))
+        else:
+            self.marks.append((name, time.perf_counter()))
+
+    def collect(self):
+        """call after a synchronize: accumulates the intervals between consecutive marks under the later mark's name"""
+        for (_, a), (name, b) in zip(self.marks, self.marks[1:]):
+            if name != "start":
+                self.ms[name] = self.ms.get(name, 0.0) + (a.elapsed_time(b) if self.cuda else 1e3 * (b - a))
+        self.marks = []
+        return self.ms
 
 
-# Painter cost of a plane, from its ridge points.  Measured on 128-plane slabs of the 1024^3 phantom (tools/slab_cost.py):
-# Tb.Th 18-19 ms everywhere; Tb.Sp 45-54 ms inside the volume but 72 and 83 ms for the two face slabs, whose balls are
-# larger.  With q = (sum of the ridge r^2 of the plane) / (voxels of the plane), cost ~ voxels x (113 + q^2) reproduces the
-# three levels (q = 1.5, 13.4, 19.5 -> 115 : 293 : 493 against 18.6 : 47 : 83 ms).  Only the ratios matter, and a poor
-# estimate costs balance, never correctness.
-COST_BASE = 113.0
-
-
-def plane_costs(comm: Comm, stages, ridge_own, zs):
-    """estimated painter cost of every plane of the volume (the same list on every rank)"""
-    mine = stages.plane_weights(ridge_own) if ridge_own.shape[0] else []
-    if comm.size == 1:
-        return list(mine)
-    parts = [None] * comm.size
-    dist.all_gather_object(parts, [float(x) for x in mine], group=comm.group)
-    return [x for part in parts for x in part]
-
-
-NO_BLOCK_PREFERENCE = 1 << 20   # column-block width a rank without planes proposes (a multiple of 32 above any width)
-def even_block_cols(w: int, limit: int, quantum: int = 128) -> int:
-    """column-block width <= limit that cuts a width of w into blocks of (nearly) equal size: 1024 columns under a
-    limit of 896 become 2 x 512, not 896 + 128 (a narrow last block leaves the GPU mostly idle)"""
-    if limit >= w:
-        return limit
-    nblocks = -(-w // limit)
-    even = -(-(-(-w // nblocks)) // quantum) * quantum
-    return min(limit, even)
-
-
-BOUNDARY_KCAP = 32          # staircase steps per column a slab face can carry (more: fall back to the halo repaint)
-MAX_SOURCES = 4             # slabs per side a sweep can import from (bjt_dev_paint_sweep)
-
-
-def paint_exchange(stages, comm: Comm, ridge_own, zs, gmax, kcap=BOUNDARY_KCAP, timings=None):
-    """Painted r^2 of this rank's own planes: plane-local x / y stages, boundary staircases exchanged with the
-    slabs within reach, z sweeps.  Returns None (on every rank alike) when the stepwise painter cannot take
-    the case -- too many slabs within reach or a capacity exceeded -- and the caller repaints slab + halo."""
-    G, r = comm.size, comm.rank
-    z0, z1 = zs[r]
-    rmax = math.isqrt(gmax)                                               # no ball reaches further than this
-    nplanes = rmax + 1
-
-    def within(p, q):
-        """gap from slab p's face plane to slab q's first plane, or 0 when out of reach / empty"""
-        (a0, a1), (b0, b1) = zs[p], zs[q]
-        if a1 == a0 or b1 == b0:
-            return 0
-        gap = b0 - (a1 - 1) if q > p else a0 - (b1 - 1)
-        return gap if gap <= rmax else 0
-
-    too_many = any(sum(1 for p in range(q) if within(p, q)) > MAX_SOURCES or
-                   sum(1 for p in range(q + 1, G) if within(p, q)) > MAX_SOURCES for q in range(G))
-    if too_many:
-        return None
-    # Stages 2-3 run per block of columns and staircases are exchanged per block, so every rank must cut the
-    # width the same way -- but the library sizes the blocks by the slab's own volume, and slabs differ in
-    # thickness (uneven division, the cost-balanced split): agree on the narrowest choice.
-    agreed = hasattr(stages, "paint_block_cols")
-    if agreed:
-        mine = stages.paint_block_cols(tuple(ridge_own.shape)) if z1 > z0 else NO_BLOCK_PREFERENCE
-        narrowest = -comm.allreduce_max_int(-int(mine), ridge_own.device)
-        stages.paint_set_block_cols(even_block_cols(int(ridge_own.shape[2]), narrowest))
-    flags = 0
-    out = None
-    t_ = time.perf_counter
-
-    def mark(name, t0):
-        if timings is not None:
-            if str(getattr(stages, "device", "cpu")).startswith("cuda"):
-                torch.cuda.synchronize()
-            timings[name] = timings.get(name, 0.0) + (t_() - t0)
-        return t_()
-
-    try:
-        if z1 > z0:
-            t0 = t_()
-            nxs = stages.paint_open(ridge_own, gmax)
-            t0 = mark("paint.x_stage", t0)
-            for xs in range(nxs):
-                ncol = stages.paint_xslab_cols(xs)
-                stages.paint_lists(xs)
-                t0 = mark("paint.y_stage", t0)
-                sends, recvs, lo, hi = {}, {}, [], []
-                for p in range(G):
-                    if p == r:
-                        continue
-                    gap = within(r, p)
-                    if gap:                                                   # what I carry across to slab p
-                        buf = stages.boundary_buffer(ncol, kcap)
-                        stages.paint_export(xs, +1 if p > r else -1, gap, nplanes, buf, ncol, kcap)
-                        sends[p] = buf
-                    if within(p, r):                                          # what slab p carries across to me
-                        recvs[p] = stages.boundary_buffer(ncol, kcap)
-                        (lo if p < r else hi).append(recvs[p])
-                t0 = mark("paint.export", t0)
-                comm.exchange(sends, recvs)
-                t0 = mark("paint.exchange", t0)
-                stages.paint_sweep(xs, lo, hi, ncol, kcap)
-                t0 = mark("paint.z_stage", t0)
-                del sends, recvs, lo, hi
-            out, flags = stages.paint_close()
-    finally:
-        if agreed:
-            stages.paint_set_block_cols(0)
-    flags = comm.allreduce_max_int(int(flags != 0), ridge_own.device)
-    if flags:
-        return None
-    return out if out is not None else ridge_own.new_empty((0,) + tuple(ridge_own.shape[1:]))
-
-
-def thickness_slab(stages, comm: Comm, slab_u8, dims, inverse, mask=True, pixel_width=1.0, timings=None,
-                   paint_mode="auto", boundary_kcap=BOUNDARY_KCAP, balance=True):
+def thickness_slab(stages, comm: Comm, slab_u8, dims, inverse, mask=True, pixel_width=1.0, timer=None):
     """One pipeline run (LocalThicknessWrapper.processImage + StackStatistics) on this rank's z-slab.
     slab_u8: [dz][h][w] planes zs[rank] of the volume dims = (w, h, d).  Returns (map slab f32, stats dict)."""
     w, h, d = dims
@@ -423,96 +269,90 @@ def thickness_slab(stages, comm: Comm, slab_u8, dims, inverse, mask=True, pixel_
     z0, z1 = zs[r]
     n = max(w, h, d)
     n0 = no_result(n)
-    t_ = time.perf_counter
+    mark = timer.mark if timer is not None else (lambda name: None)
 
-    def mark(name, t0):
-        if timings is not None:
-            if hasattr(stages, "device") and str(stages.device).startswith("cuda"):
-                torch.cuda.synchronize()
-            timings[name] = timings.get(name, 0.0) + (t_() - t0)
-
-    t0 = t_()
+    mark("start")
     gx = stages.edt_x(slab_u8, inverse)
     gy = stages.edt_y(gx, n)
     del gx
-    mark("edt_xy", t0); t0 = t_()
+    mark("edt_xy")
     gy_t = transpose_z_to_y(comm, gy, zs, ys)
     del gy
-    mark("transpose", t0); t0 = t_()
+    mark("transpose")
     sq_t = stages.edt_z(gy_t, n)
     del gy_t
-    mark("edt_z", t0); t0 = t_()
+    mark("edt_z")
     sq = transpose_y_to_z(comm, sq_t, zs, ys, h)
     del sq_t
-    mark("transpose", t0); t0 = t_()
+    mark("transpose")
     gmax = comm.allreduce_max_int(stages.max_value(sq), slab_u8.device)
+    mark("rmax")
 
     # planes of the painted map the cleanup of this slab reads: slab +- 2, clipped to the volume
-    s_lo, s_hi = max(0, z0 - 2), min(d, z1 + 2)
+    s_lo, s_hi = (max(0, z0 - 2), min(d, z1 + 2)) if z1 > z0 else (z0, z0)
     if gmax == 0:
         rsq_sub = stages.full((s_hi - s_lo, h, w), 0)
     elif gmax >= n0:
         rsq_sub = stages.full((s_hi - s_lo, h, w), n0)                 # no background anywhere (sentinel)
     else:
-        rsq_sub = None
-        if paint_mode != "halo" and hasattr(stages, "paint_open"):
-            # ridge of the slab's own planes: the squared EDT one plane further out on either side
-            needs = [(max(0, a - 1), min(d, b + 1)) if b > a else (a, a) for (a, b) in zs]
-            sq_ext = gather_planes(comm, sq, zs, needs)
-            mark("halo", t0); t0 = t_()
-            ridge_own = stages.ridge(sq_ext)[z0 - needs[r][0]:z1 - needs[r][0]] if z1 > z0 else sq_ext
-            del sq_ext
-            mark("ridge", t0); t0 = t_()
-            # the painter works on its own split of the planes: equal estimated cost instead of equal thickness (balls are
-            # larger near the volume faces and bone is not spread evenly); ridge planes move over, painted planes move back
-            zp = zs
-            if balance and G > 1 and hasattr(stages, "plane_weights"):
-                zp = balanced_ranges(plane_costs(comm, stages, ridge_own, zs), G)
-                if zp != zs:
-                    ridge_own = gather_planes(comm, ridge_own, zs, zp)
-                mark("rebalance", t0); t0 = t_()
-            rsq_own = paint_exchange(stages, comm, ridge_own, zp, gmax, kcap=boundary_kcap, timings=timings)
-            del ridge_own
-            mark("paint", t0); t0 = t_()
-            if rsq_own is not None:
-                needs2 = [(max(0, a - 2), min(d, b + 2)) if b > a else (a, a) for (a, b) in zs]
-                rsq_sub = gather_planes(comm, rsq_own, zp, needs2)
-                del rsq_own
-                mark("halo", t0); t0 = t_()
-            elif paint_mode == "exchange":
-                raise RuntimeError("stepwise painter refused the case (capacity or reach) and paint_mode='exchange' forbids the fallback")
-    if gmax != 0 and gmax < n0 and rsq_sub is None:
-        H = math.isqrt(gmax - 1) + 1 + 2                               # ceil(sqrt(r^2 max)) + 2
-        # ridge of planes [z0-H, z1+H) needs the squared EDT one plane further out
-        needs = []
-        for (a, b) in zs:
-            needs.append((max(0, a - H - 1), min(d, b + H + 1)))
+        H = math.isqrt(gmax)                                           # no ball reaches further
+        # painting [s_lo, s_hi) reads the ridge of [s_lo - H, s_hi + H); the ridge of a plane needs the squared
+        # EDT one plane further out
+        needs = [((max(0, a - 2 - H - 1), min(d, b + 2 + H + 1)) if b > a else (a, a)) for (a, b) in zs]
         e_lo, e_hi = needs[r]
         sq_ext = gather_planes(comm, sq, zs, needs)
-        mark("halo", t0); t0 = t_()
-        ridge_ext = stages.ridge(sq_ext)
+        mark("halo")
+        if z1 > z0:
+            ridge_ext = stages.ridge(sq_ext)
+            # the outermost fetched planes have an incomplete neighbourhood unless they are volume faces; they lie
+            # beyond reach of [s_lo, s_hi) and must not paint
+            if e_lo > 0:
+                ridge_ext[0] = 0
+            if e_hi < d:
+                ridge_ext[-1] = 0
+            mark("ridge")
+            rsq_sub = stages.paint_range(ridge_ext, s_lo - e_lo, s_hi - e_lo, gmax)
+            del ridge_ext
+            mark("paint")
+        else:
+            rsq_sub = stages.full((0, h, w), 0)
         del sq_ext
-        # the outermost fetched planes have an incomplete neighbourhood unless they are volume faces;
-        # they lie beyond reach (H + 1 > r_max + 2) and are dropped
-        if e_lo > 0:
-            ridge_ext[0] = 0
-        if e_hi < d:
-            ridge_ext[-1] = 0
-        mark("ridge", t0); t0 = t_()
-        rsq_ext = stages.paint(ridge_ext)
-        del ridge_ext
-        rsq_sub = rsq_ext[s_lo - e_lo:s_hi - e_lo]
-        mark("paint", t0); t0 = t_()
     out, part = stages.finish(rsq_sub, slab_u8, z0 - s_lo, z1 - s_lo, inverse, mask, pixel_width)
+    mark("finish")
     stats = comm.combine_stats(part, slab_u8.device).finalize()
-    mark("finish", t0)
+    mark("stats")
     return out, stats
+
+
+def map_hashes(map_f32, z0, dims, parts=8):
+    """64-bit position-weighted checksums of the map's bits over the z ranges split_ranges(d, parts) that lie inside
+    this slab (NaN canonicalised): sums of (bits + 1) * (2 * global index + 1) mod 2^64, so the checksums of a range
+    are the same whichever rank computes them and ranks can be compared with a single-GPU run range by range.
+    Returns {range index: checksum as int} for the ranges fully inside [z0, z0 + dz)."""
+    w, h, d = dims
+    dz = map_f32.shape[0]
+    out = {}
+    if dz == 0:
+        return out
+    bits = torch.where(torch.isnan(map_f32), torch.full_like(map_f32, float("nan")), map_f32).contiguous().view(torch.int32)
+    for k, (a, b) in enumerate(split_ranges(d, parts)):
+        if b <= a or a < z0 or b > z0 + dz:
+            continue
+        acc = 0
+        for c0 in range(a, b, 16):                                     # 16 planes at a time: bounded temporaries
+            c1 = min(b, c0 + 16)
+            v = bits[c0 - z0:c1 - z0].reshape(-1).to(torch.int64) + 1
+            idx = torch.arange(c0 * h * w, c1 * h * w, dtype=torch.int64, device=map_f32.device)
+            acc = (acc + int((v * (2 * idx + 1)).sum().item())) & 0xFFFFFFFFFFFFFFFF
+        out[k] = acc
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1)
 
 def bench(args, rank, world, local_rank, dist_mod):
+    """the N > 1 arm of bench.py: returns rank 0's result fields (bench.py adds roofline, clocks and prints)"""
     from . import _native
     from .phantom import phantom_shapes
 
@@ -531,33 +371,46 @@ def bench(args, rank, world, local_rank, dist_mod):
     slab = torch.empty((dz, n, n), dtype=torch.uint8, device=dev)
     ctx.dev_phantom(shapes, n, n, n, z0, dz, slab.data_ptr())
 
-    def step(timings=None):
-        th = thickness_slab(stages, comm, slab, dims, False, True, 1.0, timings)
-        sp = thickness_slab(stages, comm, slab, dims, True, True, 1.0, timings)
+    def step(timer=None):
+        th = thickness_slab(stages, comm, slab, dims, False, True, 1.0, timer)
+        sp = thickness_slab(stages, comm, slab, dims, True, True, 1.0, timer)
         return th, sp
 
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize(); comm.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    timings = {}
+    timer = PhaseTimer(dev)
+    launches0 = ctx.launch_count()
     ev0.record(stream)
     for _ in range(args.steps):
-        th, sp = step(timings)
+        th, sp = step(timer)
     ev1.record(stream)
     torch.cuda.synchronize(); comm.barrier()
+    launches = ctx.launch_count() - launches0
     ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], dtype=torch.float64, device=dev)
     dist_mod.all_reduce(ms, op=dist_mod.ReduceOp.MAX)
     dev_ms = float(ms.item())
+    per = {k: v / args.steps for k, v in timer.collect().items()}
+
+    # the maps of every rank, range by range, as checksums a single-GPU run reproduces (bench.py prints the same
+    # ranges at N = 1): N-GPU == 1-GPU bit for bit is checked where the numbers are compared, not just the statistics
+    mine = {"tb_th": map_hashes(th[0], z0, dims), "tb_sp": map_hashes(sp[0], z0, dims)}
+    gathered = [None] * world
+    dist_mod.all_gather_object(gathered, mine)
+    hashes = {}
+    for name in ("tb_th", "tb_sp"):
+        merged = {}
+        for part in gathered:
+            merged.update(part[name])
+        hashes[name] = [format(merged[k], "016x") if k in merged else None for k in range(8)]
 
     # end to end: page-locked host slab in, both map slabs back out, every step
-    nb = dz * n * n
     h_in = torch.empty((dz, n, n), dtype=torch.uint8, pin_memory=True)
     h_th = torch.empty((dz, n, n), dtype=torch.float32, pin_memory=True)
     h_sp = torch.empty((dz, n, n), dtype=torch.float32, pin_memory=True)
     h_in.copy_(slab)
     slab2 = torch.empty_like(slab)
-    launches0 = ctx.launch_count()
     e2e = []
     copy_stream = torch.cuda.Stream(device=dev)                     # the first map goes home while the second run computes
     for i in range(args.warmup + args.steps):
@@ -574,30 +427,14 @@ def bench(args, rank, world, local_rank, dist_mod):
         torch.cuda.synchronize(); comm.barrier()
         if i >= args.warmup:
             e2e.append(time.perf_counter() - t0)
-    launches = (ctx.launch_count() - launches0) // (args.warmup + args.steps)
     em = torch.tensor([1e3 * sum(e2e) / len(e2e)], dtype=torch.float64, device=dev)
     dist_mod.all_reduce(em, op=dist_mod.ReduceOp.MAX)
     e2e_ms = float(em.item())
-
-    N = n ** 3
-    per = {k: 1e3 * v / args.steps for k, v in timings.items()}
-    dom = max(per, key=per.get) if per else "paint"
-    alg_edt = 21.0 * N * 2 / world
-    edt_ms = per.get("edt_xy", 0.0) + per.get("edt_z", 0.0)
-    return {
-        "metric": "thickness_map_gvoxels_per_s", "value": N / (dev_ms * 1e-3) / 1e9, "unit": "Gvoxel/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "u32/f32", "data": "synthetic",
-        "config": {"workload": f"BoneJ Thickness Tb.Th+Tb.Sp (mapChoice Both), mask on, {n}^3 synthetic trabecular phantom, "
-                               f"z-slabs over {world} GPUs (BASELINE.json configs[2])", "volume": [n, n, n],
-                   "parallelism": f"z-slab x{world}", "l2_policy": "inputs exceed the 126 MB L2"},
-        "e2e": {"value": N / (e2e_ms * 1e-3) / 1e9, "unit": "Gvoxel/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": N, "d2h_bytes_per_step": 8 * N},
-        "gpu_launches": int(launches) * args.steps,
-        "roofline": {"kernel": "edt (x+y+z passes, rank 0, per step)", "bound": "hbm",
-                     "achieved": alg_edt / (edt_ms * 1e-3) / 1e9 if edt_ms > 0 else 0.0, "peak": None, "unit": "GB/s",
-                     "frac": None, "traffic": None},
-        "stages_rank0_ms": {k: round(v, 3) for k, v in per.items()}, "dominant_stage": dom,
-        "results": {"tb_th": th[1], "tb_sp": sp[1]},
-        "cpu_baseline": None,
-    }
+    # per-phase device time: the slowest rank of every phase (what the step waits for)
+    names = sorted(per)
+    pt = torch.tensor([per[k] for k in names], dtype=torch.float64, device=dev)
+    dist_mod.all_reduce(pt, op=dist_mod.ReduceOp.MAX)
+    per_max = {k: float(v) for k, v in zip(names, pt.tolist())}
+    return dict(dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), phases_rank0_ms={k: round(v, 3) for k, v in per.items()},
+                phases_max_ms={k: round(v, 3) for k, v in per_max.items()}, hashes=hashes,
+                results={"tb_th": th[1], "tb_sp": sp[1]})

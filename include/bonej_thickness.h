@@ -166,6 +166,12 @@ int bjt_dev_edt_z(bjt_ctx *ctx, const uint32_t *d_gy, int w, int h, int d, int n
 int bjt_dev_ridge(bjt_ctx *ctx, const uint32_t *d_sq, int w, int h, int d, uint32_t *d_ridge);
 int bjt_dev_paint(bjt_ctx *ctx, const uint32_t *d_ridge, int w, int h, int d, int path, uint32_t *d_rsq);
 
+/* The painter on a z-slab with halo planes (z-slab sharded runs; SURVEY.md 8e "max-radius halo exchange"): d_ridge
+ * holds d planes, balls centred on any of them count, and planes [z_lo, z_hi) are painted into d_rsq (z_hi - z_lo
+ * planes).  max_rsq = the largest r^2 of the WHOLE volume (every rank passes the same value; < 0: found here).      */
+int bjt_dev_paint_range(bjt_ctx *ctx, const uint32_t *d_ridge, int w, int h, int d, int z_lo, int z_hi, int64_t max_rsq,
+                        uint32_t *d_rsq);
+
 /* The painter of one z-slab in steps (Local_Thickness_Parallel over a volume cut along z).  Its x and y
  * stages are plane-local; only the z sweeps cross slab faces, and what crosses is small: per (x, y) column
  * the staircase of (tag, reach beyond the face) of the balls centred next to the face.

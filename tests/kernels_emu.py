@@ -166,6 +166,11 @@ class EmuContext:
     def dev_paint(self, d_ridge, w, h, d, d_rsq, path=-1):
         assert self._L.emu_dev_paint(self._vp(d_ridge), w, h, d, self._vp(d_rsq)) > 0
 
+    def dev_paint_range(self, d_ridge, w, h, d, z_lo, z_hi, max_rsq, d_rsq):
+        flags = C.c_uint32(0)
+        rc = self._L.emu_paint_disc(self._vp(d_ridge), w, h, d, int(z_lo), int(z_hi), 0, 24, self._vp(d_rsq), C.byref(flags))
+        assert rc > 0 and flags.value == 0, (rc, flags.value)
+
     def dev_paint_open(self, d_ridge, w, h, d, max_rsq):
         assert self._ses is None
         if self._rule and not self._forced:      # like the library: without a set width, the slab's own choice

@@ -61,82 +61,8 @@ class OracleStages:
         _, rsq = lt_oracle.paint(np.sqrt(rg.astype(np.float64)).astype(np.float32), nthreads=2)
         return torch.from_numpy(rsq.astype(np.int32))
 
-    # the painter in steps, on the CPU model of the separable painter (same calls and buffer layout as the
-    # CUDA library's bjt_dev_paint_open .. _close), column blocks included: like the library, a rank cuts the
-    # width into blocks of its own choosing unless a width has been set -- block_rule is the stand-in for the
-    # library's "blocks sized by the slab's volume" (thicker slab, narrower blocks)
-    block_rule = None                 # callable (dz, h, w) -> preferred block width; None: the whole width
-    _forced_cols = 0
-
-    def paint_block_cols(self, shape):
-        dz, h, w = shape
-        return int(self.block_rule(dz, h, w)) if self.block_rule else 1 << 20
-
-    def paint_set_block_cols(self, cols):
-        self._forced_cols = int(cols)
-
-    def paint_open(self, ridge_own, max_rsq):
-        self._ses = lt_oracle.SepPaintSession(_np(ridge_own).astype(np.uint32))
-        self._out = None
-        w = self._ses.w
-        cols = min(self._forced_cols or self.paint_block_cols(tuple(ridge_own.shape)), w)
-        self._blocks = [(x0, min(cols, w - x0)) for x0 in range(0, w, cols)]
-        self._imports = None
-        return len(self._blocks)
-
-    def paint_xslab_cols(self, xs):
-        return self._blocks[xs][1] * self._ses.h
-
-    def _block_columns(self, xs):
-        """whole-width column index (y * w + x) of the block's columns, in the block's order (y * xw + lx)"""
-        x0, xw = self._blocks[xs]
-        return (np.arange(self._ses.h)[:, None] * self._ses.w + x0 + np.arange(xw)[None, :]).reshape(-1)
-
-    def paint_lists(self, xs):
-        pass
-
-    def boundary_buffer(self, ncol, kcap):
-        return torch.zeros(ncol * (2 * kcap + 1), dtype=torch.int32)
-
-    @staticmethod
-    def _split(buf, ncol, kcap):
-        a = _np(buf).view(np.uint32)
-        return a[2 * ncol * kcap:], a[:2 * ncol * kcap]
-
-    def paint_export(self, xs, side, gap, nplanes, buf, ncol, kcap):
-        assert ncol == self.paint_xslab_cols(xs)
-        cnt, items = self._ses.export(side, gap, nplanes, kcap)            # whole width; keep this block's columns
-        sel = self._block_columns(xs)
-        c, it = self._split(buf, ncol, kcap)
-        c[:] = cnt[sel]
-        it[:] = items[sel].reshape(-1)
-
-    def paint_sweep(self, xs, lo, hi, ncol, kcap):
-        # the model sweeps the whole width at once: collect the blocks' imports, sweep after the last block
-        assert ncol == self.paint_xslab_cols(xs)
-        ncol_all = self._ses.w * self._ses.h
-        if self._imports is None:
-            mk = lambda n: [(np.zeros(ncol_all, np.uint32), np.zeros((ncol_all, kcap, 2), np.uint32)) for _ in range(n)]
-            self._imports = (mk(len(lo)), mk(len(hi)))
-        sel = self._block_columns(xs)
-        for bufs, full in ((lo, self._imports[0]), (hi, self._imports[1])):
-            assert len(bufs) == len(full)
-            for b, (cnt, items) in zip(bufs, full):
-                c, it = self._split(b, ncol, kcap)
-                cnt[sel] = c
-                items[sel] = it.reshape(-1, kcap, 2)
-        if xs == len(self._blocks) - 1:
-            conv = lambda full: [(c, np.ascontiguousarray(it.reshape(-1))) for c, it in full]
-            self._out = self._ses.sweep(conv(self._imports[0]), conv(self._imports[1]), kcap)
-
-    def paint_close(self):
-        flags = self._ses.close()
-        return torch.from_numpy(self._out.astype(np.int32)), int(flags != 0)
-
-    def plane_weights(self, ridge):
-        """deliberately lopsided, so the painter's split differs from the I/O split in the tests"""
-        r = _np(ridge).astype(np.float64)
-        return (1.0 + 50.0 * np.sqrt(r).sum(axis=(1, 2))).tolist()
+    def paint_range(self, ridge_ext, z_lo, z_hi, max_rsq):
+        return self.paint(ridge_ext)[z_lo:z_hi]
 
     def full(self, shape, value):
         return torch.full(shape, value, dtype=torch.int32)

@@ -77,15 +77,72 @@ def test_two_ranks_nccl_bitwise(oracle, tmp_path, inverse):
     assert int(st[0]) == st1.count and abs(st[1] - st1.mean) <= 1e-9 * abs(st1.mean)
 
 
+@pytest.mark.parametrize("shape,cuts,seed", [((48, 40, 44), [0, 13, 30, 48], 4), ((20, 24, 200), [0, 4, 9, 14, 20], 6)])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_paint_range_slabs_one_gpu(ctx, oracle, shape, cuts, seed, inverse):
+    """bjt_dev_paint_range on z-slabs of one volume: every slab is painted from the ridge of slab + halo (r_max planes
+    either side, as bonej2_b200.sharded fetches them); the slabs' painted r^2 must equal the oracle's on the whole
+    volume, bitwise.  The second case has slabs thinner than the largest ball."""
+    import math
+    vol = shapes.random_blobs(shape, seed)
+    dist_, sq = oracle.edt(vol, inverse=inverse)
+    rg = oracle.ridge(dist_)
+    _, want = oracle.paint(rg)
+    ridge = np.where(rg > 0, sq, 0).astype(np.int32)
+    gmax = int(ridge.max())
+    H = math.isqrt(gmax)
+    d, h, w = shape
+    dev = torch.device("cuda", 0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    got = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        e_lo, e_hi = max(0, a - H), min(d, b + H)
+        ext = torch.from_numpy(ridge[e_lo:e_hi].copy()).to(dev)
+        out = torch.empty((b - a, h, w), dtype=torch.int32, device=dev)
+        ctx.dev_paint_range(ext.data_ptr(), w, h, e_hi - e_lo, a - e_lo, b - e_lo, gmax, out.data_ptr())
+        got.append(out.cpu().numpy())
+    assert np.array_equal(np.concatenate(got).astype(np.uint32), want)
+
+
+class _Stepwise:
+    """thin driver of the stepwise painter entry points (bjt_dev_paint_open .. _close) for the test below"""
+    KCAP, MAX_SOURCES = 32, 4
+
+    def __init__(self, ctx, device):
+        self.ctx, self.device = ctx, device
+
+    def open(self, ridge_own, max_rsq):
+        dz, h, w = ridge_own.shape
+        self.ridge, self.out = ridge_own, torch.empty((dz, h, w), dtype=torch.int32, device=self.device)
+        return self.ctx.dev_paint_open(ridge_own.data_ptr(), w, h, dz, max_rsq)
+
+    def cols(self, xs):
+        return self.ctx.dev_paint_xslab_width(xs) * self.ridge.shape[1]
+
+    def buffer(self, ncol):
+        return torch.empty(ncol * (2 * self.KCAP + 1), dtype=torch.int32, device=self.device)
+
+    def split(self, buf, ncol):
+        return buf.data_ptr() + 8 * ncol * self.KCAP, buf.data_ptr()              # (count pointer, items pointer)
+
+    def export(self, xs, side, gap, nplanes, buf, ncol):
+        cnt, items = self.split(buf, ncol)
+        self.ctx.dev_paint_export(xs, side, gap, nplanes, cnt, items, self.KCAP)
+
+    def sweep(self, xs, lo, hi, ncol):
+        self.ctx.dev_paint_sweep(xs, [self.split(b, ncol) for b in lo], [self.split(b, ncol) for b in hi], self.KCAP,
+                                 self.out.data_ptr())
+
+
 @pytest.mark.parametrize("shape,cuts,seed,xcols", [((48, 40, 44), [0, 13, 30, 48], 4, 0),       # three slabs
                                                     ((20, 24, 200), [0, 4, 9, 14, 20], 6, 64)])  # four column blocks, thin z-slabs
 @pytest.mark.parametrize("inverse,wide", [(False, False), (True, False), (True, True)])
 def test_stepwise_painter_slabs_one_gpu(oracle, shape, cuts, seed, xcols, inverse, wide):
-    """The painter in steps (bjt_dev_paint_open .. _close) on z-slabs of one volume, all on this GPU, one
-    context per slab, boundary staircases handed over in device memory: the slabs' painted r^2 must equal
-    the oracle's on the whole volume, bitwise.  Covers export / import kernels without NCCL."""
+    """The sweep painter in steps (bjt_dev_paint_open .. _close, the large-radius alternative to bjt_dev_paint_range) on
+    z-slabs of one volume, all on this GPU, one context per slab, boundary staircases handed over in device memory:
+    the slabs' painted r^2 must equal the oracle's on the whole volume, bitwise."""
     import math
-    from bonej2_b200 import _native, sharded
+    from bonej2_b200 import _native
     vol = shapes.random_blobs(shape, seed)
     dist_, sq = oracle.edt(vol, inverse=inverse)
     rg = oracle.ridge(dist_)
@@ -97,15 +154,14 @@ def test_stepwise_painter_slabs_one_gpu(oracle, shape, cuts, seed, xcols, invers
     d, h, w = shape
     dev = torch.device("cuda", 0)
     zs = list(zip(cuts[:-1], cuts[1:]))
-    K = sharded.BOUNDARY_KCAP
     ctxs = [_native.Context(0) for _ in zs]
     _native.Context.debug_set_xslab_cols(xcols)
     try:
         st = []
         for c, (a, b) in zip(ctxs, zs):
             c.set_stream(torch.cuda.current_stream().cuda_stream)
-            s = sharded.CudaStages(c, dev)
-            s.nxs = s.paint_open(torch.from_numpy(ridge[a:b].copy()).to(dev), tag_bound)
+            s = _Stepwise(c, dev)
+            s.nxs = s.open(torch.from_numpy(ridge[a:b].copy()).to(dev), tag_bound)
             st.append(s)
         nxs = st[0].nxs
         assert nxs == ((w + xcols - 1) // xcols if xcols else 1)
@@ -115,25 +171,24 @@ def test_stepwise_painter_slabs_one_gpu(oracle, shape, cuts, seed, xcols, invers
             return g if g <= rmax else 0
 
         for xs in range(nxs):
-            ncol = st[0].paint_xslab_cols(xs)
+            ncol = st[0].cols(xs)
             for s in st:
-                s.paint_lists(xs)
+                s.ctx.dev_paint_lists(xs)
             box = {}
             for p, s in enumerate(st):
                 for q in range(len(st)):
                     if q != p and gap(p, q):
-                        box[(p, q)] = s.boundary_buffer(ncol, K)
-                        s.paint_export(xs, +1 if q > p else -1, gap(p, q), rmax + 1, box[(p, q)], ncol, K)
+                        box[(p, q)] = s.buffer(ncol)
+                        s.export(xs, +1 if q > p else -1, gap(p, q), rmax + 1, box[(p, q)], ncol)
             for q, s in enumerate(st):
                 lo = [box[(p, q)] for p in range(q) if (p, q) in box]
                 hi = [box[(p, q)] for p in range(q + 1, len(st)) if (p, q) in box]
-                assert len(lo) <= sharded.MAX_SOURCES and len(hi) <= sharded.MAX_SOURCES
-                s.paint_sweep(xs, lo, hi, ncol, K)
+                assert len(lo) <= s.MAX_SOURCES and len(hi) <= s.MAX_SOURCES
+                s.sweep(xs, lo, hi, ncol)
         got = []
         for s in st:
-            out, flags = s.paint_close()
-            assert flags == 0
-            got.append(out.cpu().numpy())
+            assert s.ctx.dev_paint_close() == 0
+            got.append(s.out.cpu().numpy())
         assert np.array_equal(np.concatenate(got).astype(np.uint32), want)
     finally:
         _native.Context.debug_set_xslab_cols(0)
