@@ -6,21 +6,22 @@
 //   ij.process.StackStatistics              count / sum / sum^2 / min / max in double    (A.7)
 // as driven by ThicknessWrapper.createMap / addMapResults (ThicknessWrapper.java:158-196).
 //
-// One fused kernel.  A block owns 32 x 8 x 8 output voxels and stages 2*sqrt(R) of the (36 x 12 x 12)
-// tile with its 2-voxel halo in shared memory as float (out-of-image cells hold a marker that counts
-// as "not zero", as the reference's look() returns -1 there); "not zero" / "interior" are kept as one
-// 64-bit word per tile row, built with ballots.  From the tile it derives the
-// "interior" flag (non-zero, no zero 26-neighbour) on the 1-voxel halo, then the value of each output
-// voxel: interior voxels keep 2*sqrt(R); surface voxels take the float32 mean of their interior
-// neighbours visited in the order faces, edges, corners (the order fixes the last ulp); then mask,
-// NaN, calibration, and per-block partials of the statistics.  HBM sees r^2 once (plus halo re-reads
-// that hit L2), the original once and the map once: 9 B/voxel of actual traffic.
+// One fused kernel.  A block owns 32 x 8 x 16 output voxels and stages 2*sqrt(R) of the (36 x 12 x 20)
+// tile with its 2-voxel halo in shared memory as float (out-of-image cells hold 0 and are flagged "not zero",
+// as the reference's look() returns -1 there); "not zero" / "interior" are kept as one 64-bit word per tile
+// row, built with ballots.  From the tile it derives the "interior" flag (non-zero, no zero 26-neighbour) on
+// the 1-voxel halo.  Surface voxels (non-zero, not interior, not removed by the mask) are few and scattered, so
+// they are first collected in a list and then averaged with all lanes busy: each takes the float32 mean of its
+// interior neighbours visited in the order faces, edges, corners (the order fixes the last ulp) and overwrites
+// its own cell, which no other voxel reads (only interior cells are read as neighbours).  Then every voxel:
+// mask, NaN, calibration, and per-block partials of the statistics.  HBM sees r^2 once (plus halo re-reads that
+// hit L2), the original once and the map once: 9 B/voxel of actual traffic.
 #include "common.cuh"
 #include <math.h>
 
 namespace bjt {
 
-constexpr int FTX = 32, FTY = 8, FTZ = 8;
+constexpr int FTX = 32, FTY = 8, FTZ = 16;
 constexpr int HX = FTX + 4, HY = FTY + 4, HZ = FTZ + 4;       // r^2 tile with 2-voxel halo
 constexpr int IY = FTY + 2, IZ = FTZ + 2;                      // interior flag rows with 1-voxel halo
 constexpr uint32_t OUTSIDE = 0xFFFFFFFFu;
@@ -65,47 +66,54 @@ __global__ void __launch_bounds__(FTX *FTY, 4) finish_kernel(const uint32_t *__r
     // one 64-bit word per tile row (z, y): bit x set = cell is not zero (outside the image counts as not
     // zero) / cell is inside the image / cell is interior
     __shared__ unsigned long long nzrow[HZ][HY], inrow[HZ][HY], itrow[HZ][HY];
-    __shared__ uint8_t og[FTZ][FTY][FTX];
+    __shared__ uint32_t keptrow[FTZ][FTY];      // bit x: the mask keeps the voxel (or there is no mask)
+    __shared__ uint16_t surf[(FTZ / 2) * FTY * FTX];   // surface voxels of half the block: tz << 8 | ty << 5 | tx
+    __shared__ int nsurf[2];
     const int bx = blockIdx.x * FTX, by = blockIdx.y * FTY, bz = z_lo + blockIdx.z * FTZ;
     const int tid = threadIdx.x + FTX * threadIdx.y;
     const int lane = tid & 31, warp = tid >> 5;
     const size_t wh = (size_t)w * h;
-    // a warp loads whole tile rows (36 cells: lanes 0..31, then lanes 0..3) and ballots the masks
-    constexpr int NWARP = (FTX * FTY) / 32, RPW = (HZ * HY) / NWARP;      // 18 rows per warp
+    if (tid < 2) nsurf[tid] = 0;
+    // a warp loads whole tile rows (36 cells: lanes 0..31, then lanes 0..3) and ballots the masks; row r = warp +
+    // NWARP * j of the HZ * HY rows, (lz, ly) carried along instead of divided out
+    constexpr int NWARP = (FTX * FTY) / 32, RPW = (HZ * HY) / NWARP;      // 30 rows per warp
     static_assert(RPW * NWARP == HZ * HY, "tile rows must divide evenly over the warps");
+    static_assert(NWARP < HY, "the row step must stay below one plane of rows");
+    constexpr int BATCH = 10;                  // rows (x 2 loads) a lane keeps in flight
+    static_assert(RPW % BATCH == 0, "batches must divide the rows of a warp");
     const int gx0 = bx + lane - 2, gx1 = bx + lane + 30;
-    constexpr int BATCH = RPW / 2;             // two batches of 9 rows: 18 independent requests in flight per lane
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
+    const bool x0_in = gx0 >= 0 && gx0 < w, x1_in = lane < 4 && gx1 < w;
+    int lz = 0, ly = warp;                      // row of the next load
+#pragma unroll 1
+    for (int b = 0; b < RPW / BATCH; ++b) {
         uint32_t v0[BATCH], v1[BATCH];
+        int lz2 = lz, ly2 = ly;
 #pragma unroll
         for (int k = 0; k < BATCH; ++k) {
-            const int r = warp + (b * BATCH + k) * NWARP;
-            const int lz = r / HY, ly = r % HY;
-            const int gy = by + ly - 2, gz = bz + lz - 2;
+            const int gy = by + ly2 - 2, gz = bz + lz2 - 2;
             const bool row_in = gy >= 0 && gy < h && gz >= 0 && gz < d;
             const uint32_t *src = rsq + (row_in ? gz * wh + (size_t)gy * w : 0);
-            v0[k] = (row_in && gx0 >= 0 && gx0 < w) ? __ldg(src + gx0) : OUTSIDE;
-            v1[k] = (lane < 4 && row_in && gx1 >= 0 && gx1 < w) ? __ldg(src + gx1) : OUTSIDE;
+            v0[k] = (row_in && x0_in) ? __ldg(src + gx0) : OUTSIDE;
+            v1[k] = (row_in && x1_in) ? __ldg(src + gx1) : OUTSIDE;
+            ly2 += NWARP;
+            if (ly2 >= HY) { ly2 -= HY; ++lz2; }
         }
 #pragma unroll
         for (int k = 0; k < BATCH; ++k) {
-            const int r = warp + (b * BATCH + k) * NWARP;
-            const int lz = r / HY, ly = r % HY;
-            const int gy = by + ly - 2, gz = bz + lz - 2;
-            const bool row_in = gy >= 0 && gy < h && gz >= 0 && gz < d;
-            const bool in0 = row_in && gx0 >= 0 && gx0 < w, in1 = lane < 4 && row_in && gx1 >= 0 && gx1 < w;
-            S[lz][ly][lane] = (v0[k] == OUTSIDE || v0[k] == 0u) ? 0.0f : thickness_of(v0[k]);
-            if (lane < 4) S[lz][ly][32 + lane] = (v1[k] == OUTSIDE || v1[k] == 0u) ? 0.0f : thickness_of(v1[k]);
+            // outside cells: value 0, flagged "not zero"
+            S[lz][ly][lane] = thickness_of(v0[k] == OUTSIDE ? 0u : v0[k]);
+            if (lane < 4) S[lz][ly][32 + lane] = thickness_of(v1[k] == OUTSIDE ? 0u : v1[k]);
             const unsigned nz0 = __ballot_sync(0xFFFFFFFFu, v0[k] != 0u), nz1 = __ballot_sync(0xFFFFFFFFu, lane < 4 && v1[k] != 0u);
-            const unsigned i0 = __ballot_sync(0xFFFFFFFFu, in0), i1 = __ballot_sync(0xFFFFFFFFu, in1);
+            const unsigned i0 = __ballot_sync(0xFFFFFFFFu, v0[k] != OUTSIDE), i1 = __ballot_sync(0xFFFFFFFFu, lane < 4 && v1[k] != OUTSIDE);
             if (lane == 0) {
                 nzrow[lz][ly] = (unsigned long long)nz0 | ((unsigned long long)nz1 << 32);
                 inrow[lz][ly] = (unsigned long long)i0 | ((unsigned long long)i1 << 32);
             }
+            ly += NWARP;
+            if (ly >= HY) { ly -= HY; ++lz; }
         }
     }
-    // the mask bytes of the block's 32 x 8 x 8 voxels
+    // which of the block's voxels the mask keeps
     {
         const int x = bx + threadIdx.x, y = by + threadIdx.y;
         uint8_t o[FTZ];
@@ -116,70 +124,90 @@ __global__ void __launch_bounds__(FTX *FTY, 4) finish_kernel(const uint32_t *__r
             if (original && x < w && y < h && z < z_hi && z < d) o[tz] = __ldg(original + z * wh + (size_t)y * w + x);
         }
 #pragma unroll
-        for (int tz = 0; tz < FTZ; ++tz) og[tz][threadIdx.y][threadIdx.x] = o[tz];
+        for (int tz = 0; tz < FTZ; ++tz) {
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, (int)o[tz] == fgval);
+            if (lane == 0) keptrow[tz][threadIdx.y] = m;
+        }
     }
     __syncthreads();
     // interior(x) = inside && not zero && all 27 cells around it not zero: AND of the 9 neighbouring rows,
     // each already ANDed with its two x-shifts
     if (tid < IZ * IY) {
-        const int lz = 1 + tid / IY, ly = 1 + tid % IY;
+        const int iz = 1 + tid / IY, iy = 1 + tid % IY;
         unsigned long long all = ~0ull;
 #pragma unroll
         for (int dz = -1; dz <= 1; ++dz)
 #pragma unroll
             for (int dy = -1; dy <= 1; ++dy) {
-                const unsigned long long m = nzrow[lz + dz][ly + dy];
+                const unsigned long long m = nzrow[iz + dz][iy + dy];
                 all &= m & (m >> 1) & (m << 1);
             }
-        itrow[lz][ly] = all & inrow[lz][ly];
+        itrow[iz][iy] = all & inrow[iz][iy];
     }
     __syncthreads();
-    double sum = 0, sum2 = 0, mn = INFINITY, mx = -INFINITY;
-    long long cnt = 0;
+    // surface voxels the mask keeps (a voxel the mask removes needs no value: the mask is applied after the cleanup,
+    // so skipping its average changes nothing; its painted value still counts as "not zero" for its neighbours above)
     const int x = bx + threadIdx.x, y = by + threadIdx.y;
-    if (x < w && y < h) {
-        const int cx = threadIdx.x + 2, cy = threadIdx.y + 2;
-#pragma unroll 1
-        for (int tz = 0; tz < FTZ; ++tz) {
+    const int cx = threadIdx.x + 2, cy = threadIdx.y + 2;
+    const bool col_in = x < w && y < h;
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll 4
+        for (int tz = half * (FTZ / 2); tz < (half + 1) * (FTZ / 2); ++tz) {
             const int z = bz + tz;
-            if (z >= z_hi || z >= d) break;
-            const int cz = tz + 2;
-            const float c = S[cz][cy][cx];
-            float v = c;
-            // a voxel the mask removes needs no value (the mask is applied after the cleanup, so skipping its average
-            // changes nothing; its painted value still counts as "not zero" for its neighbours' interior flags above)
-            const bool kept = (int)og[tz][threadIdx.y][threadIdx.x] == fgval;
-            if (kept && c != 0.0f && !((itrow[cz][cy] >> cx) & 1ull)) {
-                // surface voxel: float32 mean of the interior neighbours, faces, edges, corners in turn.
-                // The 9 flag rows sit in registers; adding 0.0f for the other neighbours is exact.
-                unsigned long long rows[3][3];
+            const bool is_surf = col_in && z < z_hi && z < d && ((keptrow[tz][threadIdx.y] >> threadIdx.x) & 1u) &&
+                                 S[tz + 2][cy][cx] != 0.0f && !((itrow[tz + 2][cy] >> cx) & 1ull);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, is_surf);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&nsurf[half], __popc(m));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (is_surf) surf[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(tz << 8 | threadIdx.y << 5 | threadIdx.x);
+            }
+        }
+        __syncthreads();
+        // their values: float32 mean of the interior neighbours, faces, edges, corners in turn.  The 9 flag rows sit
+        // in registers; adding 0.0f for the other neighbours is exact.  The cell is overwritten in place.
+        const int ns = nsurf[half];
+        for (int i = tid; i < ns; i += FTX * FTY) {
+            const int code = surf[i];
+            const int sx = (code & 31) + 2, sy = ((code >> 5) & 7) + 2, sz = (code >> 8) + 2;
+            unsigned long long rows[3][3];
 #pragma unroll
-                for (int dz = 0; dz < 3; ++dz)
+            for (int dz = 0; dz < 3; ++dz)
 #pragma unroll
-                    for (int dy = 0; dy < 3; ++dy) rows[dz][dy] = itrow[cz + dz - 1][cy + dy - 1] >> (cx - 1);
-                float s = 0.0f;
-                int n = 0;
+                for (int dy = 0; dy < 3; ++dy) rows[dz][dy] = itrow[sz + dz - 1][sy + dy - 1] >> (sx - 1);
+            float s = 0.0f;
+            int n = 0;
 #define BJT_NBR(dx, dy, dz)                                                         \
     {                                                                              \
         const bool in_ = (rows[(dz) + 1][(dy) + 1] >> ((dx) + 1)) & 1ull;          \
-        s += in_ ? S[cz + (dz)][cy + (dy)][cx + (dx)] : 0.0f;                      \
+        s += in_ ? S[sz + (dz)][sy + (dy)][sx + (dx)] : 0.0f;                      \
         n += in_ ? 1 : 0;                                                          \
     }
-                BJT_NBR(0, 0, -1) BJT_NBR(0, 0, 1) BJT_NBR(0, -1, 0) BJT_NBR(0, 1, 0) BJT_NBR(-1, 0, 0) BJT_NBR(1, 0, 0)
-                BJT_NBR(0, 1, -1) BJT_NBR(0, 1, 1) BJT_NBR(1, -1, 0) BJT_NBR(1, 1, 0) BJT_NBR(-1, 0, 1) BJT_NBR(1, 0, 1)
-                BJT_NBR(0, -1, -1) BJT_NBR(0, -1, 1) BJT_NBR(-1, -1, 0) BJT_NBR(-1, 1, 0) BJT_NBR(-1, 0, -1) BJT_NBR(1, 0, -1)
-                BJT_NBR(1, 1, 1) BJT_NBR(1, -1, 1) BJT_NBR(-1, 1, 1) BJT_NBR(-1, -1, 1)
-                BJT_NBR(1, 1, -1) BJT_NBR(1, -1, -1) BJT_NBR(-1, 1, -1) BJT_NBR(-1, -1, -1)
+            BJT_NBR(0, 0, -1) BJT_NBR(0, 0, 1) BJT_NBR(0, -1, 0) BJT_NBR(0, 1, 0) BJT_NBR(-1, 0, 0) BJT_NBR(1, 0, 0)
+            BJT_NBR(0, 1, -1) BJT_NBR(0, 1, 1) BJT_NBR(1, -1, 0) BJT_NBR(1, 1, 0) BJT_NBR(-1, 0, 1) BJT_NBR(1, 0, 1)
+            BJT_NBR(0, -1, -1) BJT_NBR(0, -1, 1) BJT_NBR(-1, -1, 0) BJT_NBR(-1, 1, 0) BJT_NBR(-1, 0, -1) BJT_NBR(1, 0, -1)
+            BJT_NBR(1, 1, 1) BJT_NBR(1, -1, 1) BJT_NBR(-1, 1, 1) BJT_NBR(-1, -1, 1)
+            BJT_NBR(1, 1, -1) BJT_NBR(1, -1, -1) BJT_NBR(-1, 1, -1) BJT_NBR(-1, -1, -1)
 #undef BJT_NBR
-                v = n > 0 ? s / (float)n : c;
-            }
-            const size_t p = z * wh + (size_t)y * w + x;
-            if (!kept) v = 0.0f;
+            if (n > 0) S[sz][sy][sx] = s / (float)n;
+        }
+        __syncthreads();
+    }
+    double sum = 0, sum2 = 0, mn = INFINITY, mx = -INFINITY;
+    long long cnt = 0;
+    if (col_in) {
+#pragma unroll 4
+        for (int tz = 0; tz < FTZ; ++tz) {
+            const int z = bz + tz;
+            if (z >= z_hi || z >= d) break;
+            float v = S[tz + 2][cy][cx];
+            if (!((keptrow[tz][threadIdx.y] >> threadIdx.x) & 1u)) v = 0.0f;
             if (calibrate) {
                 if (v == 0.0f) v = __int_as_float(0x7FC00000);
                 v = v * pw;
             }
-            if (out) out[p - (size_t)z_lo * wh] = v;
+            if (out) out[(size_t)(z - z_lo) * wh + (size_t)y * w + x] = v;
             if (v == v) {   // not NaN
                 const double dv = (double)v;
                 sum += dv; sum2 += dv * dv; mn = fmin(mn, dv); mx = fmax(mx, dv); ++cnt;
