@@ -72,6 +72,8 @@ _lib = None
 _VP, _I, _D = C.c_void_p, C.c_int, C.c_double
 _SIGS = {
     "bjt_create": ([C.POINTER(_VP), _I], _I),
+    "bjt_create_multi": ([C.POINTER(_VP), C.POINTER(_I), _I], _I),
+    "bjt_device_count": ([_VP], _I),
     "bjt_destroy": ([_VP], None),
     "bjt_last_error": ([_VP], C.c_char_p),
     "bjt_set_stream": ([_VP, _VP], _I),
@@ -154,11 +156,20 @@ def _ptr(a):
 class Context:
     """One bjt_ctx: a CUDA device, a stream and the cached device workspace."""
 
-    def __init__(self, device: int = -1):
+    def __init__(self, device: int = -1, devices=None):
+        """device: one GPU (bjt_create).  devices: a sequence of GPUs -- the thickness calls then cut the stack into
+        z-slabs over them inside the library (bjt_create_multi); a GPU may be named more than once."""
         self._h = _VP()
-        rc = lib().bjt_create(C.byref(self._h), int(device))
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*[int(x) for x in devices])
+            rc = lib().bjt_create_multi(C.byref(self._h), arr, len(devices))
+        else:
+            rc = lib().bjt_create(C.byref(self._h), int(device))
         if rc != BJT_OK:
             raise ThicknessError(rc, lib().bjt_last_error(None).decode())
+
+    def device_count(self) -> int:
+        return int(lib().bjt_device_count(self._h))
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:

@@ -14,11 +14,13 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <map>
 #include <vector>
 #include <mutex>
 #include <string>
+#include <thread>
 
 using namespace bjt;
 
@@ -42,6 +44,10 @@ struct bjt_ctx {
     int paint_launches[3] = {0, 0, 0};
     // stepwise painter of a z-slab (bjt_dev_paint_open .. _close)
     struct { bool open = false; int w = 0, h = 0, d = 0, variant = 0; void *ws = nullptr; uint32_t *flags = nullptr; } ps;
+    // bjt_create_multi: one single-device context per z-slab (empty for a plain context); the fields below are the
+    // per-slab state of a run, written by the slab's worker and read by the others only after a phase has been joined
+    std::vector<bjt_ctx *> kids;
+    struct { uint32_t maxval = 0, not_binary = 0; StatsPartial part{}; uint32_t *gy = nullptr, *sqt = nullptr; } mg;
 };
 
 static char g_err[512] = "no error";
@@ -107,6 +113,17 @@ static int check_dims(bjt_ctx *c, int w, int h, int d) {
     return BJT_OK;
 }
 
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+#define ENTER(c)                                            \
+    if (!(c)) return fail(nullptr, BJT_E_ARG, "null context"); \
+    std::lock_guard<std::mutex> lk_((c)->mu);               \
+    DeviceGuard dg_((c)->device)
+
 extern "C" {
 
 int bjt_create(bjt_ctx **out, int device) {
@@ -135,10 +152,44 @@ int bjt_create(bjt_ctx **out, int device) {
     return BJT_OK;
 }
 
+int bjt_create_multi(bjt_ctx **out, const int *devices, int ndev) {
+    if (!out) return fail(nullptr, BJT_E_ARG, "null output pointer");
+    *out = nullptr;
+    if (!devices || ndev < 1 || ndev > 64) return fail(nullptr, BJT_E_ARG, "bjt_create_multi: between 1 and 64 devices");
+    int rc = bjt_create(out, devices[0]);
+    if (rc) return rc;
+    bjt_ctx *c = *out;
+    if (ndev == 1) return BJT_OK;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (int i = 0; i < ndev; ++i) {
+        bjt_ctx *k = nullptr;
+        rc = bjt_create(&k, devices[i]);
+        if (rc) { bjt_destroy(c); *out = nullptr; return rc; }
+        c->kids.push_back(k);
+    }
+    // slabs read each other's memory (strided copies over NVLink): map every peer that can be mapped; the copies
+    // still work, staged by the driver, where it cannot
+    for (int i = 0; i < ndev; ++i)
+        for (int j = 0; j < ndev; ++j) {
+            const int a = c->kids[i]->device, b = c->kids[j]->device;
+            int can = 0;
+            if (a == b || cudaDeviceCanAccessPeer(&can, a, b) != cudaSuccess || !can) continue;
+            cudaSetDevice(a);
+            cudaDeviceEnablePeerAccess(b, 0);
+            cudaGetLastError();                                        // "already enabled" is fine
+        }
+    if (prev >= 0) cudaSetDevice(prev);
+    return BJT_OK;
+}
+
+int bjt_device_count(const bjt_ctx *c) { return c ? (c->kids.empty() ? 1 : (int)c->kids.size()) : 0; }
+
 int bjt_release_workspace(bjt_ctx *c) {
     if (!c) return BJT_E_ARG;
+    for (bjt_ctx *k : c->kids) bjt_release_workspace(k);
     std::lock_guard<std::mutex> lk(c->mu);
-    cudaSetDevice(c->device);
+    DeviceGuard dg(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto &kv : c->bufs) if (kv.second.p) cudaFree(kv.second.p);
     c->bufs.clear();
@@ -147,7 +198,10 @@ int bjt_release_workspace(bjt_ctx *c) {
 
 void bjt_destroy(bjt_ctx *c) {
     if (!c) return;
+    for (bjt_ctx *k : c->kids) bjt_destroy(k);
+    c->kids.clear();
     bjt_release_workspace(c);
+    DeviceGuard dg(c->device);
     for (auto &ev : c->ev) cudaEventDestroy(ev);
     for (auto &ev : c->pev) cudaEventDestroy(ev);
     if (c->h_scal) cudaFreeHost(c->h_scal);
@@ -171,6 +225,7 @@ int bjt_set_stream(bjt_ctx *c, void *stream) {
 int bjt_set_paint_path(bjt_ctx *c, int path) {
     if (!c || path < -1 || path > 4 || path == 3) return BJT_E_ARG;
     c->paint_path = path;
+    for (bjt_ctx *k : c->kids) k->paint_path = path;
     return BJT_OK;
 }
 
@@ -460,6 +515,36 @@ static int dev_paint(bjt_ctx *c, const uint32_t *ridge, int w, int h, int d, int
     return BJT_OK;
 }
 
+// planes [z_lo, z_hi) of the painted map of a ridge volume of d planes (bjt_dev_paint_range)
+static int dev_paint_range(bjt_ctx *c, const uint32_t *d_ridge, int w, int h, int d, int z_lo, int z_hi, int64_t max_rsq,
+                           uint32_t *d_rsq) {
+    if (z_lo < 0 || z_hi > d || z_lo >= z_hi) return fail(c, BJT_E_ARG, "paint_range: bad plane range [%d, %d) of %d", z_lo, z_hi, d);
+    const size_t N = (size_t)w * h * d, wh = (size_t)w * h;
+    uint32_t *scal;
+    WS("scalars", 256, scal);
+    if (max_rsq < 0) {
+        CK(cudaMemsetAsync(scal + 14, 0, 4, c->stream));
+        c->launches += launch_mark_present(d_ridge, N, nullptr, scal + 14, c->stream); CKL();
+        CK(peek(c, c->h_scal + 14, scal + 14, 4));
+        CK(cudaStreamSynchronize(c->stream));
+        max_rsq = c->h_scal[14];
+    }
+    if ((c->paint_path < 0 || c->paint_path == 4) && paint_disc_supports((uint32_t)max_rsq)) {
+        int done = 0;
+        const int rc = dev_paint_disc(c, d_ridge, w, h, d, z_lo, z_hi, (uint32_t)max_rsq, d_rsq, &done);
+        if (rc) return rc;
+        if (done) return BJT_OK;
+    }
+    // radii beyond the disc painter (or a forced path): paint every plane of the slab, keep the requested ones
+    uint32_t *tmp;
+    WS("paint_range_tmp", N * sizeof(uint32_t), tmp);
+    const int rc = dev_paint(c, d_ridge, w, h, d, c->paint_path == 4 ? -1 : c->paint_path, -1, max_rsq, tmp, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(d_rsq, tmp + (size_t)z_lo * wh, (size_t)(z_hi - z_lo) * wh * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return BJT_OK;
+}
+
 static int dev_finish_range(bjt_ctx *c, const uint32_t *rsq, const uint8_t *d_original, int w, int h, int d, int z_lo,
                             int z_hi, int inverse, int calibrate, double pixel_width, float *d_out, bjt_stats *stats) {
     if (z_lo < 0 || z_hi > d || z_lo >= z_hi) return fail(c, BJT_E_ARG, "bad plane range [%d, %d) of %d", z_lo, z_hi, d);
@@ -552,16 +637,209 @@ static int dev_pipeline(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, in
     return BJT_OK;
 }
 
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
 
-#define ENTER(c)                                            \
-    if (!(c)) return fail(nullptr, BJT_E_ARG, "null context"); \
-    std::lock_guard<std::mutex> lk_((c)->mu);               \
-    DeviceGuard dg_((c)->device)
+
+// ---------------------------------------------------------------------------------------------------
+// z-slabs over several GPUs behind the same calls (bjt_create_multi).  The reference seam is one blocking call
+// on one thread (ThicknessWrapper.java:127-134, 190-196); here that call cuts the stack into contiguous z-slabs,
+// one per device, and one host thread per device drives its slab.  A run is three phases, joined on the host:
+//   A  upload the slab (first run of a call), 0/255 check, EDT x and y                       slab-local
+//   B  pull my y range of every slab's y-pass result out of the peers' memory (one strided copy per peer over
+//      NVLink), EDT z on whole z lines, largest squared distance
+//   C  pull the squared EDT of my planes +- (H + 3), H = floor(sqrt(largest)), straight out of the peers' y-slab
+//      layout (transpose back and halo in one copy per peer), ridge, paint [slab +- 2], cleanup .. statistics on
+//      the slab, download
+// No ball reaches further than H planes, the ridge of a plane needs one plane either side, the cleanup two: the
+// maps are bitwise those of a single device (the same argument as bonej2_b200/sharded.py, which runs the same
+// split with one process per GPU).  (n, sum, sum^2, min, max) are combined before mean and sd are formed.
+
+static void split_range(int n, int parts, int i, int *lo, int *hi) {
+    const int base = n / parts, rem = n % parts;
+    *lo = i * base + (i < rem ? i : rem);
+    *hi = *lo + base + (i < rem ? 1 : 0);
+}
+
+// f(r) for every slab: one host thread each (the phases block on their own streams), joined before returning.
+// Build option BJT_SINGLE_HOST_THREAD: the slabs take turns on the calling thread (for a runtime that must not be
+// entered from several threads).
+template <class F> static int for_each_slab(bjt_ctx *c, int G, F f) {
+    std::vector<int> rcs((size_t)G, BJT_OK);
+#ifdef BJT_SINGLE_HOST_THREAD
+    for (int r = 0; r < G; ++r) rcs[r] = f(r);
+#else
+    std::vector<std::thread> th;
+    for (int r = 1; r < G; ++r) th.emplace_back([&, r]() { DeviceGuard dg(c->kids[r]->device); rcs[r] = f(r); });
+    { DeviceGuard dg(c->kids[0]->device); rcs[0] = f(0); }
+    for (auto &t : th) t.join();
+#endif
+    for (int r = 0; r < G; ++r)
+        if (rcs[r]) { snprintf(c->err, sizeof c->err, "slab %d (device %d): %.400s", r, c->kids[r]->device, c->kids[r]->err); return rcs[r]; }
+    return BJT_OK;
+}
+
+static int multi_run(bjt_ctx *P, const uint8_t *in, const uint8_t *const *in_slices, int w, int h, int d, int both,
+                     int inverse, int mask, int threshold, double pixel_width, float *out0, float *const *out_slices,
+                     float *out1, bjt_stats *st0, bjt_stats *st1, bjt_timing *tm0, bjt_timing *tm1) {
+    const int G = (int)std::min<size_t>(P->kids.size(), (size_t)d);      // never an empty slab
+    const size_t wh = (size_t)w * h;
+    const int n = w > h ? (w > d ? w : d) : (h > d ? h : d);
+    const uint32_t n0 = no_result(n);
+    if (tm0) memset(tm0, 0, sizeof *tm0);
+    if (tm1) memset(tm1, 0, sizeof *tm1);
+    auto zr = [&](int r, int *lo, int *hi) { split_range(d, G, r, lo, hi); };
+    auto yr = [&](int r, int *lo, int *hi) { split_range(h, G, r, lo, hi); };
+    int64_t launches0 = 0;
+    for (int r = 0; r < G; ++r) launches0 += P->kids[r]->launches;
+
+    for (int run = 0; run < (both ? 2 : 1); ++run) {
+        const int inv = both ? run : inverse;
+        float *out = run == 0 ? out0 : out1;
+        float *const *outs = run == 0 ? out_slices : nullptr;
+        const bool want_map = out || outs;
+        bjt_timing *tm = run == 0 ? tm0 : tm1;
+        const auto t_start = std::chrono::steady_clock::now();
+
+        // ---- phase A ------------------------------------------------------------------------------
+        int rc = for_each_slab(P, G, [&](int r) -> int {
+            bjt_ctx *c = P->kids[r], *k = c;                           // CK / WS report into the slab's context
+            int z0, z1; zr(r, &z0, &z1);
+            const int dz = z1 - z0;
+            const size_t Ns = (size_t)dz * wh;
+            uint8_t *d_in; uint16_t *gx; uint32_t *gy, *scal;
+            WS("in", Ns, d_in); WS("gx", Ns * 2, gx); WS("mg_gy", Ns * 4, gy); WS("scalars", 256, scal);
+            k->mg.gy = gy;
+            if (run == 0) {
+                if (in) CK(cudaMemcpyAsync(d_in, in + (size_t)z0 * wh, Ns, cudaMemcpyHostToDevice, k->stream));
+                else for (int z = z0; z < z1; ++z)
+                    CK(cudaMemcpyAsync(d_in + (size_t)(z - z0) * wh, in_slices[z], wh, cudaMemcpyHostToDevice, k->stream));
+                CK(cudaMemsetAsync(scal + 12, 0, 4, k->stream));
+                k->launches += launch_check_binary(d_in, Ns, scal + 12, k->stream); CKL();
+                CK(peek(k, k->h_scal + 12, scal + 12, 4));
+            }
+            k->launches += launch_edt_x(d_in, w, h, dz, inv, threshold, gx, k->stream); CKL();
+            k->launches += launch_edt_y(gx, w, h, dz, n0, gy, k->stream); CKL();
+            CK(cudaStreamSynchronize(k->stream));
+            if (run == 0) k->mg.not_binary = k->h_scal[12];
+            return BJT_OK;
+        });
+        if (rc) return rc;
+        for (int r = 0; r < G; ++r)
+            if (P->kids[r]->mg.not_binary) return fail(P, BJT_E_NOT_BINARY, "input is not a binary 0/255 image");
+
+        // ---- phase B ------------------------------------------------------------------------------
+        rc = for_each_slab(P, G, [&](int r) -> int {
+            bjt_ctx *c = P->kids[r], *k = c;
+            int y0, y1; yr(r, &y0, &y1);
+            const int hy = y1 - y0;
+            k->mg.maxval = 0;
+            uint32_t *gyt, *sqt, *scal;
+            WS("mg_gyt", (size_t)d * hy * w * 4, gyt); WS("mg_sqt", (size_t)d * hy * w * 4, sqt); WS("scalars", 256, scal);
+            k->mg.sqt = sqt;
+            if (hy == 0) return BJT_OK;
+            const size_t row = (size_t)hy * w * 4;                     // my y range of one plane: contiguous on either side
+            for (int i = 0; i < G; ++i) {
+                const int p = (r + i) % G;                             // every device starts with a different peer
+                int pz0, pz1; zr(p, &pz0, &pz1);
+                CK(cudaMemcpy2DAsync(gyt + (size_t)pz0 * hy * w, row, P->kids[p]->mg.gy + (size_t)y0 * w, wh * 4, row,
+                                     (size_t)(pz1 - pz0), cudaMemcpyDefault, k->stream));
+            }
+            CK(cudaMemsetAsync(scal, 0, 4, k->stream));
+            k->launches += launch_edt_z(gyt, w, hy, d, n0, sqt, nullptr, scal, k->stream); CKL();
+            CK(peek(k, k->h_scal, scal, 4));
+            CK(cudaStreamSynchronize(k->stream));
+            k->mg.maxval = k->h_scal[0];
+            return BJT_OK;
+        });
+        if (rc) return rc;
+        uint32_t gmax = 0;
+        for (int r = 0; r < G; ++r) gmax = std::max(gmax, P->kids[r]->mg.maxval);
+        const int H = (int)std::floor(std::sqrt((double)gmax));
+
+        // ---- phase C ------------------------------------------------------------------------------
+        rc = for_each_slab(P, G, [&](int r) -> int {
+            bjt_ctx *c = P->kids[r], *k = c;
+            int z0, z1; zr(r, &z0, &z1);
+            const int dz = z1 - z0;
+            const int s_lo = std::max(0, z0 - 2), s_hi = std::min(d, z1 + 2);      // painted planes the cleanup reads
+            const int ds = s_hi - s_lo;
+            uint8_t *d_in; uint32_t *rsq; float *d_out;
+            WS("in", (size_t)dz * wh, d_in);
+            WS("mg_rsq", (size_t)ds * wh * 4, rsq);
+            // "Both": the first map goes home on the copy stream while the second run computes into another buffer
+            const bool second_buf = both && run == 1 && out0 && k->copy_stream;
+            if (second_buf) WS("out2", (size_t)dz * wh * 4, d_out); else WS("out", (size_t)dz * wh * 4, d_out);
+            if (gmax == 0 || gmax >= n0) {
+                // no foreground for this run, or no background anywhere (every voxel carries the sentinel radius)
+                if (gmax == 0) CK(cudaMemsetAsync(rsq, 0, (size_t)ds * wh * 4, k->stream));
+                else { k->launches += launch_fill_u32(rsq, (size_t)ds * wh, n0, k->stream); CKL(); }
+            } else {
+                const int e_lo = std::max(0, z0 - 2 - H - 1), e_hi = std::min(d, z1 + 2 + H + 1);
+                const int de = e_hi - e_lo;
+                uint32_t *sq_ext, *ridge;
+                WS("mg_sq_ext", (size_t)de * wh * 4, sq_ext); WS("mg_ridge", (size_t)de * wh * 4, ridge);
+                for (int i = 0; i < G; ++i) {
+                    const int p = (r + i) % G;
+                    int py0, py1; yr(p, &py0, &py1);
+                    const size_t prow = (size_t)(py1 - py0) * w * 4;
+                    if (prow == 0) continue;
+                    CK(cudaMemcpy2DAsync(sq_ext + (size_t)py0 * w, wh * 4, P->kids[p]->mg.sqt + (size_t)e_lo * (py1 - py0) * w, prow,
+                                         prow, (size_t)de, cudaMemcpyDefault, k->stream));
+                }
+                int rc2 = dev_ridge(k, sq_ext, w, h, de, gmax, ridge, nullptr);
+                if (rc2) return rc2;
+                // the outermost fetched planes have an incomplete neighbourhood unless they are volume faces; they lie
+                // beyond reach of [s_lo, s_hi) and must not paint
+                if (e_lo > 0) CK(cudaMemsetAsync(ridge, 0, wh * 4, k->stream));
+                if (e_hi < d) CK(cudaMemsetAsync(ridge + (size_t)(de - 1) * wh, 0, wh * 4, k->stream));
+                rc2 = dev_paint_range(k, ridge, w, h, de, s_lo - e_lo, s_hi - e_lo, (int64_t)gmax, rsq);
+                if (rc2) return rc2;
+            }
+            bjt_stats st;
+            // the kernel indexes the original with the coordinates of rsq: shift the slab's pointer
+            const uint8_t *orig = mask ? d_in - (size_t)(z0 - s_lo) * wh : nullptr;
+            int rc2 = dev_finish_range(k, rsq, orig, w, h, ds, z0 - s_lo, z1 - s_lo, inv, 1, pixel_width, want_map ? d_out : nullptr, &st);
+            if (rc2) return rc2;                                       // returns with the compute stream idle
+            k->mg.part = *k->h_stats;
+            cudaStream_t cs = (both && run == 0 && out0 && k->copy_stream) ? k->copy_stream : k->stream;
+            if (out) CK(cudaMemcpyAsync(out + (size_t)z0 * wh, d_out, (size_t)dz * wh * 4, cudaMemcpyDeviceToHost, cs));
+            else if (outs) for (int z = z0; z < z1; ++z)
+                CK(cudaMemcpyAsync(outs[z], d_out + (size_t)(z - z0) * wh, wh * 4, cudaMemcpyDeviceToHost, cs));
+            if (cs == k->stream) CK(cudaStreamSynchronize(cs));
+            return BJT_OK;
+        });
+        if (rc) return rc;
+
+        StatsPartial tot{0.0, 0.0, 0.0, 0.0, 0};
+        bool first = true;
+        for (int r = 0; r < G; ++r) {                                  // slab order: the same sums whatever the timing
+            const StatsPartial &p = P->kids[r]->mg.part;
+            if (p.count == 0) continue;
+            tot.sum += p.sum; tot.sum2 += p.sum2; tot.count += p.count;
+            tot.mn = first ? p.mn : std::min(tot.mn, p.mn);
+            tot.mx = first ? p.mx : std::max(tot.mx, p.mx);
+            first = false;
+        }
+        if (first) tot = P->kids[0]->mg.part;                          // empty map: min / max as the kernel leaves them
+        stats_out(tot, run == 0 ? st0 : st1);
+        if (tm) {
+            tm->ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+            tm->rsq_max = gmax;
+            tm->paint_path = (gmax == 0 || gmax >= n0) ? 3 : 4;
+        }
+    }
+    // the first map of a "Both" call may still be on its way
+    int rc = for_each_slab(P, G, [&](int r) -> int {
+        bjt_ctx *c = P->kids[r];
+        if (c->copy_stream) CK(cudaStreamSynchronize(c->copy_stream));
+        return BJT_OK;
+    });
+    if (rc) return rc;
+    int64_t launches1 = 0;
+    for (int r = 0; r < G; ++r) launches1 += P->kids[r]->launches;
+    P->launches += launches1 - launches0;
+    if (tm0) tm0->n_launches = launches1 - launches0;
+    return BJT_OK;
+}
 
 extern "C" {
 
@@ -581,6 +859,14 @@ static int host_run(bjt_ctx *c, const uint8_t *in, const uint8_t *const *in_slic
     int rc = check_dims(c, w, h, d);
     if (rc) return rc;
     if (!in && !in_slices) return fail(c, BJT_E_ARG, "null input");
+    // every pointer is checked before anything is queued
+    if (!in) for (int z = 0; z < d; ++z) if (!in_slices[z]) return fail(c, BJT_E_ARG, "null input slice %d", z);
+    if (out_slices) for (int z = 0; z < d; ++z) if (!out_slices[z]) return fail(c, BJT_E_ARG, "null output slice %d", z);
+    if (c->kids.size() > 1 && d > 1)
+        return multi_run(c, in, in_slices, w, h, d, both, inverse, mask, threshold, pixel_width, out0, out_slices, out1, st0,
+                         st1, tm0, tm1);
+    // whatever way this function is left, no copy into or out of caller memory is still in flight
+    struct Drain { bjt_ctx *c; ~Drain() { cudaStreamSynchronize(c->stream); if (c->copy_stream) cudaStreamSynchronize(c->copy_stream); } } drain{c};
     const size_t N = (size_t)w * h * d, wh = (size_t)w * h;
     uint8_t *d_in; float *d_out;
     WS("in", N, d_in);
@@ -589,10 +875,7 @@ static int host_run(bjt_ctx *c, const uint8_t *in, const uint8_t *const *in_slic
     if (tm1) memset(tm1, 0, sizeof *tm1);
     CK(cudaEventRecord(c->ev[8], c->stream));
     if (in) CK(cudaMemcpyAsync(d_in, in, N, cudaMemcpyHostToDevice, c->stream));
-    else for (int z = 0; z < d; ++z) {
-        if (!in_slices[z]) return fail(c, BJT_E_ARG, "null input slice %d", z);
-        CK(cudaMemcpyAsync(d_in + z * wh, in_slices[z], wh, cudaMemcpyHostToDevice, c->stream));
-    }
+    else for (int z = 0; z < d; ++z) CK(cudaMemcpyAsync(d_in + z * wh, in_slices[z], wh, cudaMemcpyHostToDevice, c->stream));
     CK(cudaEventRecord(c->ev[9], c->stream));
     // "Both": the download of the first map runs on the copy stream while the second run computes into
     // a second device buffer
@@ -610,10 +893,8 @@ static int host_run(bjt_ctx *c, const uint8_t *in, const uint8_t *const *in_slic
         cudaStream_t cs = (run == 0 && overlap) ? c->copy_stream : c->stream;
         CK(cudaEventRecord(c->ev[10 + 2 * run], cs));
         if (out) CK(cudaMemcpyAsync(out, d_dst, N * sizeof(float), cudaMemcpyDeviceToHost, cs));
-        else if (run == 0 && out_slices) for (int z = 0; z < d; ++z) {
-            if (!out_slices[z]) return fail(c, BJT_E_ARG, "null output slice %d", z);
+        else if (run == 0 && out_slices) for (int z = 0; z < d; ++z)
             CK(cudaMemcpyAsync(out_slices[z], d_dst + z * wh, wh * sizeof(float), cudaMemcpyDeviceToHost, cs));
-        }
         CK(cudaEventRecord(c->ev[11 + 2 * run], cs));
         if (!(run == 0 && overlap)) CK(cudaStreamSynchronize(cs));
     }
@@ -960,31 +1241,7 @@ int bjt_dev_paint_range(bjt_ctx *c, const uint32_t *d_ridge, int w, int h, int d
     int rc = check_dims(c, w, h, d);
     if (rc) return rc;
     if (!d_ridge || !d_rsq) return fail(c, BJT_E_ARG, "paint_range: null pointer");
-    if (z_lo < 0 || z_hi > d || z_lo >= z_hi) return fail(c, BJT_E_ARG, "paint_range: bad plane range [%d, %d) of %d", z_lo, z_hi, d);
-    const size_t N = (size_t)w * h * d, wh = (size_t)w * h;
-    uint32_t *scal;
-    WS("scalars", 256, scal);
-    if (max_rsq < 0) {
-        CK(cudaMemsetAsync(scal + 14, 0, 4, c->stream));
-        c->launches += launch_mark_present(d_ridge, N, nullptr, scal + 14, c->stream); CKL();
-        CK(peek(c, c->h_scal + 14, scal + 14, 4));
-        CK(cudaStreamSynchronize(c->stream));
-        max_rsq = c->h_scal[14];
-    }
-    if ((c->paint_path < 0 || c->paint_path == 4) && paint_disc_supports((uint32_t)max_rsq)) {
-        int done = 0;
-        rc = dev_paint_disc(c, d_ridge, w, h, d, z_lo, z_hi, (uint32_t)max_rsq, d_rsq, &done);
-        if (rc) return rc;
-        if (done) return BJT_OK;
-    }
-    // radii beyond the disc painter (or a forced path): paint every plane of the slab, keep the requested ones
-    uint32_t *tmp;
-    WS("paint_range_tmp", N * sizeof(uint32_t), tmp);
-    rc = dev_paint(c, d_ridge, w, h, d, c->paint_path == 4 ? -1 : c->paint_path, -1, max_rsq, tmp, nullptr);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(d_rsq, tmp + (size_t)z_lo * wh, (size_t)(z_hi - z_lo) * wh * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    return BJT_OK;
+    return dev_paint_range(c, d_ridge, w, h, d, z_lo, z_hi, max_rsq, d_rsq);
 }
 
 // ---- stepwise painter of one z-slab -------------------------------------------------------------------

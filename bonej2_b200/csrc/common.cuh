@@ -31,7 +31,7 @@ __device__ __forceinline__ uint32_t isqrt_floor(uint32_t v) {
 // the same through the approximate square root (one MUFU): the float root of a value below 2^28 is off by far less
 // than 1, so its truncation is the answer or one beside it
 __device__ __forceinline__ uint32_t isqrt_fast(uint32_t v) {
-#ifdef BJT_CUDA_EMU
+#ifndef __CUDACC__   // a host compiler reading this header: the portable form
     uint32_t r = (uint32_t)sqrtf((float)v);
 #else
     float f;
@@ -45,7 +45,7 @@ __device__ __forceinline__ uint32_t isqrt_fast(uint32_t v) {
 // floor(sqrt(v)) for v < 2^18 without a correction step: sqrt(v + 0.5) lies at least 1 / (4 * 512) away from every
 // integer, the approximate root (a couple of ulp of 2^-15) cannot cross one
 __device__ __forceinline__ int isqrt_small(uint32_t v) {
-#ifdef BJT_CUDA_EMU
+#ifndef __CUDACC__   // a host compiler reading this header: the portable form
     return (int)sqrtf((float)v + 0.5f);
 #else
     float f;

@@ -269,9 +269,15 @@ int launch_stats(const float *map, size_t n, StatsPartial *partials, int npartia
 // ---- LocalThicknessWrapper.processImage input check: only 0 and 255 allowed ------------------------
 __global__ void check_binary_kernel(const uint8_t *__restrict__ in, size_t n, uint32_t *__restrict__ bad) {
     uint32_t b = 0;
-    const size_t n16 = ((uintptr_t)in % 16 == 0) ? n / 16 : 0;
-    const uint4 *v = reinterpret_cast<const uint4 *>(in);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    // the bytes in front of the first 16-byte boundary (a slab of a larger buffer need not start on one) and behind the
+    // last whole vector are checked one by one, a thread each; the aligned middle as 16-byte vectors
+    const size_t head = min(n, (size_t)((16 - ((uintptr_t)in & 15)) & 15));
+    const size_t n16 = (n - head) / 16;
+    const uint4 *v = reinterpret_cast<const uint4 *>(in + head);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid < head) b |= (in[tid] != 0 && in[tid] != 255);
+    if (tid < n - head - n16 * 16) { const uint8_t t = in[head + n16 * 16 + tid]; b |= (t != 0 && t != 255); }
+    for (size_t i = tid; i < n16; i += (size_t)gridDim.x * blockDim.x) {
         const uint4 q = __ldg(v + i);
         // a byte is fine iff it equals 0x00 or 0xFF  <=>  byte ^ (its top bit replicated) == 0
         const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
@@ -281,8 +287,6 @@ __global__ void check_binary_kernel(const uint8_t *__restrict__ in, size_t n, ui
             b |= wds[k] ^ (hi * 0xFFu);
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-        for (size_t i = n16 * 16; i < n; ++i) b |= (in[i] != 0 && in[i] != 255);
     if (__any_sync(0xFFFFFFFFu, b != 0) && (threadIdx.x & 31) == 0) atomicOr(bad, 1u);
 }
 

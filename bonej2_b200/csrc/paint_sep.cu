@@ -28,6 +28,7 @@
 // live in a global scratch; anything beyond that, or a full pool, raises a flag and the caller
 // falls back to the scatter painter -- never silently.
 #include "common.cuh"
+#include <atomic>
 #include "paint_sep_core.cuh"
 
 namespace bjt {
@@ -37,7 +38,7 @@ namespace {
 // x-slab width of stages 2 and 3: as many columns as keep a slab at or below 2^29 voxels (the item pool of
 // stage 2 is sized per slab voxel), at least 512 -- thin z-slabs of a sharded run get the whole width, which
 // keeps the y-stage grid (columns x planes lines) large enough to fill the GPU
-int g_xslab_override = 0;               // paint_sep_set_xslab_cols: the ranks of a sharded run agree on one width; tests
+std::atomic<int> g_xslab_override{0};  // paint_sep_set_xslab_cols: the ranks of a sharded run agree on one width; tests
 inline int natural_xslab_cols(int h, int d) {          // not clipped to the width of the volume
     const long long per_col = (long long)h * d;
     long long xc = (1ll << 29) / (per_col > 0 ? per_col : 1);
@@ -46,7 +47,8 @@ inline int natural_xslab_cols(int h, int d) {          // not clipped to the wid
     return xc < (1 << 20) ? (int)xc : (1 << 20);
 }
 inline int xslab_cols(int w, int h, int d) {
-    const int xc = g_xslab_override > 0 ? g_xslab_override : natural_xslab_cols(h, d);
+    const int ov = g_xslab_override.load();
+    const int xc = ov > 0 ? ov : natural_xslab_cols(h, d);
     return xc < w ? xc : w;
 }
 constexpr unsigned long long OFF_MASK = (1ull << 40) - 1ull;

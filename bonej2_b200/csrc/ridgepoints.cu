@@ -17,8 +17,9 @@ namespace bjt {
 
 namespace {
 
-// the 33 offsets of the radius-2 grid ball
-__constant__ int8_t c_ball[33][3];
+// the 33 offsets of the radius-2 grid ball, handed to the kernels by value (kernel parameters are constant memory of
+// the launch: nothing per device or per process to initialise)
+struct Ball { int8_t o[33][3]; };
 
 __global__ void pad_kernel(const uint8_t *__restrict__ in, int w, int h, int d, uint8_t *__restrict__ out) {
     const int W = w + 2, H = h + 2, D = d + 2;
@@ -39,14 +40,14 @@ __global__ void sqrt_kernel(const uint32_t *__restrict__ sq, size_t n, float *__
 
 // grey erosion (IS_MAX = false) or dilation (IS_MAX = true) by the radius-2 ball, neighbours outside ignored
 template <bool IS_MAX>
-__global__ void morph_kernel(const float *__restrict__ src, int W, int H, int D, float *__restrict__ dst) {
+__global__ void morph_kernel(const float *__restrict__ src, int W, int H, int D, float *__restrict__ dst, const Ball ball) {
     const size_t n = (size_t)W * H * D;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int x = (int)(i % W), y = (int)((i / W) % H), z = (int)(i / ((size_t)W * H));
         float v = IS_MAX ? -INFINITY : INFINITY;
 #pragma unroll 1
         for (int k = 0; k < 33; ++k) {
-            const int xx = x + c_ball[k][0], yy = y + c_ball[k][1], zz = z + c_ball[k][2];
+            const int xx = x + ball.o[k][0], yy = y + ball.o[k][1], zz = z + ball.o[k][2];
             if (xx < 0 || yy < 0 || zz < 0 || xx >= W || yy >= H || zz >= D) continue;
             const float s = __ldg(src + ((size_t)zz * H + yy) * W + xx);
             v = IS_MAX ? fmaxf(v, s) : fminf(v, s);
@@ -83,17 +84,14 @@ unsigned grid_for(size_t n) {
     return (unsigned)(b < 148 * 32 ? (b ? b : 1) : 148 * 32);
 }
 
-bool g_ball_ready = false;
-void ensure_ball() {
-    if (g_ball_ready) return;
-    int8_t ball[33][3];
+Ball make_ball() {
+    Ball b;
     int k = 0;
     for (int z = -2; z <= 2; ++z)
         for (int y = -2; y <= 2; ++y)
             for (int x = -2; x <= 2; ++x)
-                if (x * x + y * y + z * z <= 4) { ball[k][0] = (int8_t)x; ball[k][1] = (int8_t)y; ball[k][2] = (int8_t)z; ++k; }
-    cudaMemcpyToSymbol(c_ball, ball, sizeof ball);
-    g_ball_ready = true;
+                if (x * x + y * y + z * z <= 4) { b.o[k][0] = (int8_t)x; b.o[k][1] = (int8_t)y; b.o[k][2] = (int8_t)z; ++k; }
+    return b;
 }
 
 }  // namespace
@@ -106,14 +104,14 @@ int launch_pad_binary(const uint8_t *in, int w, int h, int d, uint8_t *out, cuda
 // sq: squared EDT of the expanded image (W x H x D); a, b, c: three float scratch volumes; on return `a` holds the ridge.
 int launch_ridge_points_map(const uint32_t *sq, int W, int H, int D, float *a, float *b, float *c, uint32_t *max_bits,
                             cudaStream_t s) {
-    ensure_ball();
+    const Ball ball = make_ball();
     const size_t n = (size_t)W * H * D;
     const unsigned g = grid_for(n);
     sqrt_kernel<<<g, 256, 0, s>>>(sq, n, a);                       // a = dist
-    morph_kernel<false><<<g, 256, 0, s>>>(a, W, H, D, b);          // b = erode(dist)
-    morph_kernel<true><<<g, 256, 0, s>>>(b, W, H, D, c);           // c = open
-    morph_kernel<true><<<g, 256, 0, s>>>(a, W, H, D, b);           // b = dilate(dist)
-    morph_kernel<false><<<g, 256, 0, s>>>(b, W, H, D, a);          // a = close
+    morph_kernel<false><<<g, 256, 0, s>>>(a, W, H, D, b, ball);          // b = erode(dist)
+    morph_kernel<true><<<g, 256, 0, s>>>(b, W, H, D, c, ball);           // c = open
+    morph_kernel<true><<<g, 256, 0, s>>>(a, W, H, D, b, ball);           // b = dilate(dist)
+    morph_kernel<false><<<g, 256, 0, s>>>(b, W, H, D, a, ball);          // a = close
     cudaMemsetAsync(max_bits, 0, 4, s);
     ridge_value_kernel<<<g, 256, 0, s>>>(a, c, n, a, max_bits);    // a = ridge
     return 6;

@@ -60,6 +60,14 @@ typedef struct bjt_timing {
 
 /* ---- context ------------------------------------------------------------------------------- */
 int  bjt_create(bjt_ctx **out, int device);            /* device < 0: current CUDA device        */
+/* One context over several GPUs: the same thickness calls below (bjt_thickness_u8, _u8_slices, _both_u8) cut the
+ * stack into contiguous z-slabs, one per device, driven by one host thread each; slabs exchange EDT lines and a
+ * max-radius halo through peer memory (NVLink), and the maps and statistics are bitwise those of one device.  This
+ * is how the single blocking call of the reference seam (ThicknessWrapper.java:127-134, 190-196) reaches 2 .. 8
+ * GPUs.  devices may name a GPU more than once (slabs then share it).  Every other entry point of a multi-device
+ * context runs on devices[0]. */
+int  bjt_create_multi(bjt_ctx **out, const int *devices, int ndev);
+int  bjt_device_count(const bjt_ctx *ctx);             /* slabs a thickness call is cut into (1 for bjt_create) */
 void bjt_destroy(bjt_ctx *ctx);
 const char *bjt_last_error(const bjt_ctx *ctx);        /* ctx may be NULL (creation failures)    */
 int  bjt_set_stream(bjt_ctx *ctx, void *cuda_stream);  /* cudaStream_t; NULL = default stream    */
@@ -70,7 +78,9 @@ int  bjt_set_paint_path(bjt_ctx *ctx, int path);
 /* kernels of this library launched through this context so far */
 int64_t bjt_launch_count(const bjt_ctx *ctx);
 /* test hook: cap the fast painter kernels' per-line capacities (0 = default) so that small volumes exercise
- * the redo kernels; results must not change */
+ * the redo kernels; results must not change.  This and bjt_paint_set_block_cols below configure the separable
+ * sweeps (paint paths 0 / 1, the fallback painter) for every context on the same device / in the process: set them
+ * only while no other context is painting.  The default painter (path 4) reads neither. */
 int  bjt_debug_set_paint_limits(bjt_ctx *ctx, int active_cap, int front_cap);
 /* The painter runs its y and z stages per block of columns, sized by the volume of the block (the lists of
  * a block are held at once).  bjt_paint_block_cols: the width the library chooses for a w x h x d volume, not

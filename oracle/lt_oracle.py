@@ -16,7 +16,7 @@ _SO = os.path.join(_HERE, "_build", "liblt_oracle.so")
 
 def build(force: bool = False) -> str:
     """Compile the oracle with gcc (oracle/Makefile)."""
-    srcs = [os.path.join(_HERE, f) for f in ("lt_oracle.c", "phantom_cpu.c", "sep_paint_model.cpp", "Makefile",
+    srcs = [os.path.join(_HERE, f) for f in ("lt_oracle.c", "phantom_cpu.c", "edt_exact.c", "sep_paint_model.cpp", "Makefile",
                                               "../bonej2_b200/csrc/paint_sep_core.cuh")]
     stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     if force or stale:
@@ -75,6 +75,16 @@ def edt(vol_u8, inverse=False, threshold=128, nthreads=None):
     lib().lto_edt(_p(v, C.c_uint8), w, h, d, int(inverse), int(threshold), _p(dist, C.c_float),
                   _p(sq, C.c_uint32), nthreads or default_threads())
     return dist, sq
+
+
+def edt_exact_sq(vol_u8, inverse=False, threshold=128, nthreads=None):
+    """the squared map of EDT_S1D by an independent O(N) algorithm (oracle/edt_exact.c): the checker for volumes the
+    brute-force restatement above cannot finish"""
+    v = _vol(vol_u8, np.uint8)
+    d, h, w = v.shape
+    sq = np.empty(v.shape, np.uint32)
+    lib().edt_exact_sq(_p(v, C.c_uint8), w, h, d, int(inverse), int(threshold), _p(sq, C.c_uint32), nthreads or default_threads())
+    return sq
 
 
 def ridge(dist_f32):

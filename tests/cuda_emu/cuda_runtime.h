@@ -13,6 +13,7 @@
  */
 #pragma once
 #define BJT_CUDA_EMU 1
+#define BJT_SINGLE_HOST_THREAD 1   /* api.cu: fibers and function-local statics are not thread-safe */
 
 #include <math.h>
 #include <stddef.h>
@@ -46,7 +47,7 @@ struct emu_uint3 { unsigned x, y, z; };
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };
 typedef void *cudaStream_t;
-enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 // ---- the runtime calls of the host driver (api.cu): one "device", memory = the heap, streams and events = bookkeeping ----
 #include <time.h>
 enum { cudaStreamNonBlocking = 1 };
@@ -81,6 +82,14 @@ template <class T> inline cudaError_t cudaMallocHost(T **p, size_t n) { *p = (T 
 inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMemGetInfo(size_t *free_b, size_t *total_b) { *free_b = (size_t)64 << 30; *total_b = (size_t)64 << 30; return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(dst, src, n); return cudaSuccess; }
+
+inline cudaError_t cudaMemcpy2DAsync(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height, cudaMemcpyKind,
+                                     cudaStream_t) {
+    for (size_t i = 0; i < height; ++i) memcpy((char *)dst + i * dpitch, (const char *)src + i * spitch, width);
+    return cudaSuccess;
+}
+inline cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 
 #define cudaFuncSetAttribute(...) 0
 #define cudaMemsetAsync(p, v, n, s) (memset((p), (v), (n)), 0)

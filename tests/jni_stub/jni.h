@@ -3,7 +3,7 @@
  *
  * The build image has no JDK, so bonej2_b200/csrc/jni_shim.cpp (the JNI half of the seam in
  * INTEGRATION.md) is never compiled into the product library here.  To keep its logic under test anyway
- * (slice pinning and release, null for a non-binary image, RuntimeException with bjt_last_error() on
+ * (slices copied through region calls with every local reference dropped, null for a non-binary image, RuntimeException with bjt_last_error() on
  * failure, MapStats fields), tests/jni_fake_env.cpp compiles the shim against THIS header and drives it
  * with a fake JNIEnv.  Only the types and the JNIEnv members the shim uses exist, in this file's own
  * layout.  It is on the include path of that test build only; a product build with a real JDK picks
@@ -34,6 +34,7 @@ typedef jobject jarray;
 typedef jobject jobjectArray;
 typedef jobject jbyteArray;
 typedef jobject jfloatArray;
+typedef jobject jintArray;
 struct _jfieldID;
 typedef _jfieldID *jfieldID;
 
@@ -50,8 +51,12 @@ struct BjtFakeJniTable {
     void (*SetDoubleField)(JNIEnv *, jobject, jfieldID, jdouble);
     jsize (*GetArrayLength)(JNIEnv *, jarray);
     jobject (*GetObjectArrayElement)(JNIEnv *, jobjectArray, jsize);
-    void *(*GetPrimitiveArrayCritical)(JNIEnv *, jarray, jboolean *);
-    void (*ReleasePrimitiveArrayCritical)(JNIEnv *, jarray, void *, jint);
+    void (*DeleteLocalRef)(JNIEnv *, jobject);
+    void (*GetByteArrayRegion)(JNIEnv *, jbyteArray, jsize, jsize, jbyte *);
+    void (*SetFloatArrayRegion)(JNIEnv *, jfloatArray, jsize, jsize, const jfloat *);
+    void (*GetIntArrayRegion)(JNIEnv *, jintArray, jsize, jsize, jint *);
+    jobjectArray (*NewObjectArray)(JNIEnv *, jsize, jclass, jobject);
+    void (*SetObjectArrayElement)(JNIEnv *, jobjectArray, jsize, jobject);
 };
 
 struct JNIEnv_ {
@@ -65,8 +70,12 @@ struct JNIEnv_ {
     void SetDoubleField(jobject o, jfieldID f, jdouble v) { functions->SetDoubleField(this, o, f, v); }
     jsize GetArrayLength(jarray a) { return functions->GetArrayLength(this, a); }
     jobject GetObjectArrayElement(jobjectArray a, jsize i) { return functions->GetObjectArrayElement(this, a, i); }
-    void *GetPrimitiveArrayCritical(jarray a, jboolean *is_copy) { return functions->GetPrimitiveArrayCritical(this, a, is_copy); }
-    void ReleasePrimitiveArrayCritical(jarray a, void *p, jint mode) { functions->ReleasePrimitiveArrayCritical(this, a, p, mode); }
+    void DeleteLocalRef(jobject o) { functions->DeleteLocalRef(this, o); }
+    void GetByteArrayRegion(jbyteArray a, jsize start, jsize len, jbyte *buf) { functions->GetByteArrayRegion(this, a, start, len, buf); }
+    void SetFloatArrayRegion(jfloatArray a, jsize start, jsize len, const jfloat *buf) { functions->SetFloatArrayRegion(this, a, start, len, buf); }
+    void GetIntArrayRegion(jintArray a, jsize start, jsize len, jint *buf) { functions->GetIntArrayRegion(this, a, start, len, buf); }
+    jobjectArray NewObjectArray(jsize n, jclass c, jobject init) { return functions->NewObjectArray(this, n, c, init); }
+    void SetObjectArrayElement(jobjectArray a, jsize i, jobject o) { functions->SetObjectArrayElement(this, a, i, o); }
 };
 
 #endif

@@ -116,3 +116,53 @@ def test_config2_1024_device_resident_properties(ctx):
         assert (st2.count, st2.mean, st2.sd, st2.max) == (st.count, st.mean, st.sd, st.max)
         assert torch.equal(torch.nan_to_num(first, nan=-1.0), torch.nan_to_num(d_out[::4099], nan=-1.0))
     assert counts == [n_fg, n ** 3 - n_fg]
+
+
+@pytest.mark.parametrize("n", [512, 1024])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_squared_edt_bit_exact_at_bench_sizes(ctx, oracle, n, inverse):
+    """the sizes the benchmark runs (BASELINE.json configs[1], configs[2]): the CUDA squared EDT against an
+    independent exact algorithm (oracle/edt_exact.c, pinned to the restatement in tests/test_oracle_golden.py), every
+    voxel, both runs.  Lines of 1024 with 16-line tiles and the long outward walks of the background run are the
+    paths small cases hardly reach."""
+    import torch
+    if n == 1024 and torch.cuda.mem_get_info()[0] < 24 * (1 << 30):
+        pytest.skip("needs about 24 GB of free device memory")
+    vol = _phantom(ctx, n)
+    got = ctx.edt_sq(vol, inverse=inverse)
+    want = oracle.edt_exact_sq(vol, inverse=inverse)
+    assert got.max() == want.max()
+    for z0 in range(0, n, 64):                                     # bounded temporaries
+        assert np.array_equal(got[z0:z0 + 64], want[z0:z0 + 64]), (n, inverse, z0)
+    if n == 1024:
+        ctx.release_workspace()
+
+
+def test_1024_disc_painter_equals_sweep_painter_on_the_device(ctx):
+    """BASELINE.json configs[2], background run (the large balls): the default painter (path 4, fronts along z + discs
+    in the plane) against the separable sweeps (path 0, a different algorithm, oracle-checked on small volumes), bit
+    for bit, device-resident"""
+    import torch
+    from bonej2_b200.phantom import phantom_shapes
+    n = 1024
+    if torch.cuda.mem_get_info()[0] < 100 * (1 << 30):
+        pytest.skip("needs about 100 GB of free device memory (the sweep painter's lists)")
+    N = n ** 3
+    d_in = torch.empty(N, dtype=torch.uint8, device="cuda")
+    ctx.dev_phantom(phantom_shapes(n, n, n, 1), n, n, n, 0, n, d_in.data_ptr())
+    gx = torch.empty(N, dtype=torch.int16, device="cuda")
+    a = torch.empty(N, dtype=torch.int32, device="cuda")
+    sq = torch.empty(N, dtype=torch.int32, device="cuda")
+    ctx.dev_edt_x(d_in.data_ptr(), n, n, n, True, 128, gx.data_ptr())
+    ctx.dev_edt_y(gx.data_ptr(), n, n, n, n, a.data_ptr())
+    ctx.dev_edt_z(a.data_ptr(), n, n, n, n, sq.data_ptr())
+    del gx
+    ctx.dev_ridge(sq.data_ptr(), n, n, n, a.data_ptr())            # a = ridge
+    ctx.dev_paint(a.data_ptr(), n, n, n, sq.data_ptr(), path=4)    # sq = painted r^2, path 4
+    b = torch.empty(N, dtype=torch.int32, device="cuda")
+    ctx.dev_paint(a.data_ptr(), n, n, n, b.data_ptr(), path=0)
+    torch.cuda.synchronize()
+    same = torch.equal(sq, b)
+    del a, b, sq, d_in
+    ctx.release_workspace()
+    assert same

@@ -108,6 +108,14 @@ def test_not_binary(ctx):
     with pytest.raises(ThicknessError) as e:
         ctx.thickness(v)
     assert e.value.code == BJT_E_NOT_BINARY
+    # every byte position of a volume whose size is not a multiple of the 16-byte vectors the check reads
+    for pos in (0, 1, 15, 16, 17, 5 * 7 * 3 - 1, 5 * 7 * 3 - 2):
+        v = np.full(5 * 7 * 3, 255, np.uint8)
+        v[pos] = 254
+        with pytest.raises(ThicknessError) as e:
+            ctx.thickness(v.reshape(3, 7, 5))
+        assert e.value.code == BJT_E_NOT_BINARY, pos
+    ctx.thickness(np.full((3, 7, 5), 255, np.uint8))
 
 
 def test_input_not_modified_and_slices(ctx, oracle):
