@@ -16,6 +16,19 @@
 //           monotone in y, so the scan for y starts at the previous minimiser and stops as soon as
 //           (y'-y)^2 reaches the running minimum; candidate reads hit L1.
 #include "common.cuh"
+#include <algorithm>
+
+// the z pass stages its tiles with TMA bulk-tensor copies when the toolchain is nvcc (device code only exists there)
+#ifndef BJT_USE_TMA
+#ifdef __CUDACC__
+#define BJT_USE_TMA 1
+#else
+#define BJT_USE_TMA 0
+#endif
+#endif
+#if BJT_USE_TMA
+#include "tma.cuh"
+#endif
 
 namespace bjt {
 
@@ -335,36 +348,13 @@ __global__ void __launch_bounds__(128) edt_line4_kernel(const TIn *__restrict__ 
 constexpr int LOADS_IN_FLIGHT = 8;
 constexpr int EDT_PAD = 64;     // sentinel rows on either side of the staged lines: walks up to this distance need no clamping
 
-template <typename TIn, int TX, bool WANT_MAX>
-__global__ void __launch_bounds__(1024, 2) edt_tile_kernel(const TIn *__restrict__ in, uint32_t *__restrict__ out, int groups,
-                                                         long long outer, long long stride, int L, uint32_t n0,
-                                                         uint32_t *__restrict__ maxval) {
-    extern __shared__ uint32_t sm_raw[];                 // [EDT_PAD + L + EDT_PAD][TX]: the pad rows hold BIG (beyond the line)
+// the walk over a staged tile: sm[t * TX + xx], t in [-EDT_PAD, L + EDT_PAD), pad rows = BIG
+template <int TX, bool WANT_MAX>
+__device__ __forceinline__ uint32_t edt_tile_walk(const uint32_t *sm, uint32_t *__restrict__ out, long long base, long long stride, int L,
+                                                  uint32_t n0) {
     constexpr int RPW = 32 / TX;                         // line positions per warp step
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int xx = lane % TX, rsub = lane / TX;
-    const long long base = (long long)(blockIdx.x / groups) * outer + (long long)(blockIdx.x % groups) * TX;
-    const uint32_t BIG = 0x3FFFFFFFu;
-    uint32_t *sm = sm_raw + EDT_PAD * TX;                // sm[t * TX + xx], t in [-EDT_PAD, L + EDT_PAD)
-    for (int i = threadIdx.x; i < EDT_PAD * TX; i += blockDim.x) { sm[-EDT_PAD * TX + i] = BIG; sm[L * TX + i] = BIG; }
-    // staging: LOADS_IN_FLIGHT independent loads per thread before the first is used -- with one load per trip a
-    // thread waits a full memory latency for every 2-4 bytes (the profile of that form showed 37 % of the kernel's
-    // samples on the store to shared memory waiting for its load)
-    {
-        const int rstep = nwarps * RPW;
-        const long long pstep = (long long)rstep * stride;
-        const TIn *p = in + base + (long long)(warp * RPW + rsub) * stride + xx;
-        uint32_t *q = sm + (warp * RPW + rsub) * TX + xx;
-        for (int t0 = warp * RPW + rsub; t0 < L; t0 += LOADS_IN_FLIGHT * rstep, p += LOADS_IN_FLIGHT * pstep, q += LOADS_IN_FLIGHT * rstep * TX) {
-            TIn v[LOADS_IN_FLIGHT];
-#pragma unroll
-            for (int u = 0; u < LOADS_IN_FLIGHT; ++u) v[u] = t0 + u * rstep < L ? __ldg(p + u * pstep) : TIn(0);
-#pragma unroll
-            for (int u = 0; u < LOADS_IN_FLIGHT; ++u)
-                if (t0 + u * rstep < L) q[u * rstep * TX] = f_of(v[u], n0);
-        }
-    }
-    __syncthreads();
     uint32_t tmax = 0;
     for (int r0 = warp * RPW; r0 < L; r0 += nwarps * RPW) {
         const int t = r0 + rsub;
@@ -372,7 +362,7 @@ __global__ void __launch_bounds__(1024, 2) edt_tile_kernel(const TIn *__restrict
         const int tc = valid ? t : 0;
         const uint32_t *pc = sm + tc * TX + xx;
         uint32_t m = valid ? *pc : 0u;
-        // two distances per vote.  Up to EDT_PAD the pad rows stand in for "beyond the line": no clamping
+        // four distances per vote.  Up to EDT_PAD the pad rows stand in for "beyond the line": no clamping
         int dlt = 1;
         const uint32_t *lo = pc - TX, *hi = pc + TX;
         for (; dlt + 3 <= EDT_PAD; dlt += 4, lo -= 4 * TX, hi += 4 * TX) {
@@ -400,11 +390,83 @@ __global__ void __launch_bounds__(1024, 2) edt_tile_kernel(const TIn *__restrict
             if (WANT_MAX) tmax = max(tmax, res);
         }
     }
-    if (WANT_MAX) {
-        tmax = __reduce_max_sync(0xFFFFFFFFu, tmax);
-        if (lane == 0 && tmax) atomicMax(maxval, tmax);
-    }
+    return tmax;                                         // this lane's largest result (0 unless WANT_MAX)
 }
+
+__device__ __forceinline__ void edt_publish_max(uint32_t tmax, uint32_t *__restrict__ maxval) {
+    tmax = __reduce_max_sync(0xFFFFFFFFu, tmax);
+    if ((threadIdx.x & 31) == 0 && tmax) atomicMax(maxval, tmax);
+}
+
+template <typename TIn, int TX, bool WANT_MAX>
+__global__ void __launch_bounds__(1024, 2) edt_tile_kernel(const TIn *__restrict__ in, uint32_t *__restrict__ out, int groups,
+                                                         long long outer, long long stride, int L, uint32_t n0,
+                                                         uint32_t *__restrict__ maxval) {
+    extern __shared__ uint32_t sm_raw[];                 // [EDT_PAD + L + EDT_PAD][TX]: the pad rows hold BIG (beyond the line)
+    constexpr int RPW = 32 / TX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int xx = lane % TX, rsub = lane / TX;
+    const long long base = (long long)(blockIdx.x / groups) * outer + (long long)(blockIdx.x % groups) * TX;
+    const uint32_t BIG = 0x3FFFFFFFu;
+    uint32_t *sm = sm_raw + EDT_PAD * TX;                // sm[t * TX + xx], t in [-EDT_PAD, L + EDT_PAD)
+    for (int i = threadIdx.x; i < EDT_PAD * TX; i += blockDim.x) { sm[-EDT_PAD * TX + i] = BIG; sm[L * TX + i] = BIG; }
+    // staging: LOADS_IN_FLIGHT independent loads per thread before the first is used -- with one load per trip a
+    // thread waits a full memory latency for every 2-4 bytes (the profile of that form showed 37 % of the kernel's
+    // samples on the store to shared memory waiting for its load)
+    {
+        const int rstep = nwarps * RPW;
+        const long long pstep = (long long)rstep * stride;
+        const TIn *p = in + base + (long long)(warp * RPW + rsub) * stride + xx;
+        uint32_t *q = sm + (warp * RPW + rsub) * TX + xx;
+        for (int t0 = warp * RPW + rsub; t0 < L; t0 += LOADS_IN_FLIGHT * rstep, p += LOADS_IN_FLIGHT * pstep, q += LOADS_IN_FLIGHT * rstep * TX) {
+            TIn v[LOADS_IN_FLIGHT];
+#pragma unroll
+            for (int u = 0; u < LOADS_IN_FLIGHT; ++u) v[u] = t0 + u * rstep < L ? __ldg(p + u * pstep) : TIn(0);
+#pragma unroll
+            for (int u = 0; u < LOADS_IN_FLIGHT; ++u)
+                if (t0 + u * rstep < L) q[u * rstep * TX] = f_of(v[u], n0);
+        }
+    }
+    __syncthreads();
+    const uint32_t tmax = edt_tile_walk<TX, WANT_MAX>(sm, out, base, stride, L, n0);
+    if (WANT_MAX) edt_publish_max(tmax, maxval);
+}
+
+#if BJT_USE_TMA
+// The z pass with its tile brought in by the TMA: the [L][16] tile of 16 adjacent z lines is exactly a (16, 1, L) box of
+// the [d][h][w] volume, copied into shared memory in boxes of BZ planes by one thread's cp.async.bulk.tensor
+// instructions -- no load, address or store instruction per voxel in the staging phase (it was ~10 of the kernel's
+// ~75 instructions per voxel, and the kernel is bound by instruction issue).  The other threads write the pad rows
+// meanwhile; one warp then polls the tile's mbarrier while the rest sleep in the block barrier (with every warp
+// polling, the block that waits takes issue slots from the block that walks: measured 4.7 ms against 2.7 ms).
+// Two blocks share an SM: one walks while the other's copies are in flight.
+// Measured and rejected (1024^3, both runs): a persistent block per SM with a ring of three tile buffers, two tiles
+// always in flight: 3.2 / 3.2 ms against 2.7 / 3.1 -- the copies, not the walk, then bound the kernel: 64-byte rows
+// are 1024 requests per tile, and with 8-column tiles (32-byte rows, room for a ring in each of two blocks) the time
+// doubles to 6.2 ms: the TMA's rate here is per row, not per byte.  L2 promotion off costs the same factor.
+template <bool WANT_MAX>
+__global__ void __launch_bounds__(1024, 2) edt_tile_z_tma_kernel(const __grid_constant__ CUtensorMap map, uint32_t *__restrict__ out,
+                                                               int groups, int w, long long plane, int L, int BZ, uint32_t n0,
+                                                               uint32_t *__restrict__ maxval) {
+    constexpr int TX = 16;
+    extern __shared__ __align__(128) uint32_t sm_raw[];
+    __shared__ uint64_t bar;
+    const int y = blockIdx.x / groups, x0 = (blockIdx.x % groups) * TX;
+    const uint32_t BIG = 0x3FFFFFFFu;
+    uint32_t *sm = sm_raw + EDT_PAD * TX;
+    if (threadIdx.x == 0) tma::mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tma::mbar_expect_tx(&bar, (uint32_t)L * TX * 4u);
+        for (int z0 = 0; z0 < L; z0 += BZ) tma::load_3d(sm + z0 * TX, &map, x0, y, z0, &bar);
+    }
+    for (int i = threadIdx.x; i < EDT_PAD * TX; i += blockDim.x) { sm[-EDT_PAD * TX + i] = BIG; sm[L * TX + i] = BIG; }
+    if (threadIdx.x < 32) tma::mbar_wait(&bar, 0);
+    __syncthreads();
+    const uint32_t tmax = edt_tile_walk<TX, WANT_MAX>(sm, out, (long long)y * w + x0, plane, L, n0);
+    if (WANT_MAX) edt_publish_max(tmax, maxval);
+}
+#endif
 
 // returns false when the shape does not fit (caller falls back to the per-thread line kernels)
 template <typename TIn, bool WANT_MAX>
@@ -446,8 +508,25 @@ int launch_edt_y(const uint16_t *gx, int w, int h, int d, uint32_t n0, uint32_t 
     return 1;
 }
 
+#if BJT_USE_TMA
+// false: this shape or driver cannot take the TMA kernel
+static bool launch_edt_z_tma(const uint32_t *gy, int w, int h, int d, uint32_t n0, uint32_t *sq, uint32_t *maxval, cudaStream_t s) {
+    const size_t smem = (size_t)(d + 2 * EDT_PAD) * 16 * 4;
+    if (w % 16 != 0 || d % 64 != 0 || smem > 100 * 1024 || !maxval) return false;
+    const int bz = d % 256 == 0 ? 256 : (d % 128 == 0 ? 128 : 64);         // whole boxes only: nothing may land in the pad rows
+    CUtensorMap map;
+    if (!tma::make_map_3d_u32(&map, gy, w, h, d, 16, 1, bz)) return false;
+    cudaFuncSetAttribute(edt_tile_z_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    edt_tile_z_tma_kernel<true><<<(unsigned)((long long)h * (w / 16)), 1024, smem, s>>>(map, sq, w / 16, w, (long long)w * h, d, bz, n0, maxval);
+    return true;
+}
+#endif
+
 int launch_edt_z(const uint32_t *gy, int w, int h, int d, uint32_t n0, uint32_t *sq, uint8_t *present,
                  uint32_t *maxval, cudaStream_t s) {
+#if BJT_USE_TMA
+    if (!present && launch_edt_z_tma(gy, w, h, d, n0, sq, maxval, s)) return 1;
+#endif
     if (!present && launch_edt_tile<uint32_t, true>(gy, sq, w, h, (long long)w, (long long)w * h, d, n0, maxval, s)) return 1;
     if (w % 4 == 0 && (uintptr_t)gy % 16 == 0 && (uintptr_t)sq % 16 == 0) {
         const long long ng = (long long)(w / 4) * h;

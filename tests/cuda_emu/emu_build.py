@@ -86,6 +86,9 @@ def rewrite_launches(text):
 
 def translate(name):
     text = open(os.path.join(_CSRC, name)).read()
+    # device code that only exists under nvcc (TMA staging: `#if BJT_USE_TMA ... #endif`, off for host compilers) is
+    # cut out before the launches are rewritten; the plain-load kernels beside it are what runs here
+    text = re.sub(r"^#if BJT_USE_TMA\n.*?^#endif\n", "", text, flags=re.S | re.M)
     text = rewrite_launches(text)
     # the few inline-PTX statements: prefetches are no-ops; shared-window loads / stores of the painter's
     # active-set store go through the emulated window address (emu_shared_ptr in cuda_runtime.h)

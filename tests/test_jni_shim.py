@@ -70,16 +70,21 @@ def _handle(emulated, multi=None):
 
 
 @pytest.fixture(scope="module", params=[pytest.param("gpu", marks=pytest.mark.gpu), "emulated"])
-def jni(request):
-    L, h = _handle(request.param == "emulated")
+def kind(request):
+    return request.param
+
+
+@pytest.fixture(scope="module")
+def jni(kind):
+    L, h = _handle(kind == "emulated")
     yield L, h
     L.jt_destroy(h)
 
 
-@pytest.fixture(scope="module", params=[pytest.param("gpu", marks=pytest.mark.gpu), "emulated"])
-def jni_multi(request):
+@pytest.fixture(scope="module")
+def jni_multi(kind):
     """ThicknessNative.createMulti over three slabs (the same device named three times: slabs may share a GPU)"""
-    L, h = _handle(request.param == "emulated", multi=[0, 0, 0])
+    L, h = _handle(kind == "emulated", multi=[0, 0, 0])
     yield L, h
     L.jt_destroy(h)
 
@@ -131,12 +136,12 @@ def test_failure_is_a_runtime_exception(jni):
     assert info["live_refs"] == 0 and info["violations"] == 0 and info["reads"] == 0
 
 
-@pytest.mark.parametrize("kind", [0, 1])
-def test_null_or_short_slice_is_an_illegal_argument(jni, kind):
+@pytest.mark.parametrize("how", [0, 1])
+def test_null_or_short_slice_is_an_illegal_argument(jni, how):
     """validated before anything is copied: nothing was read, nothing written, no reference left"""
     L, h = jni
     vol = shapes.random_blobs((5, 6, 7), 1)
-    rc, _, _, info, err = _call(L, h, vol, False, True, broken=3, broken_kind=kind)
+    rc, _, _, info, err = _call(L, h, vol, False, True, broken=3, broken_kind=how)
     assert rc == -1 and err.startswith("java/lang/IllegalArgumentException: ") and "slices[3]" in err
     assert info["reads"] == 0 and info["writes"] == 0 and info["live_refs"] == 0 and info["violations"] == 0
 
