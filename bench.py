@@ -127,6 +127,111 @@ def run_reference(args, rank, world):
     emit(line)
 
 
+def run_hyperstack(args, rank, world, local_rank, dist):
+    """BASELINE.json configs[4]: a multi-channel / time hyperstack, one Thickness "Both" run per {X, Y, Z} subspace in
+    HyperstackUtils.split3DSubspaces order (HyperstackUtils.java:99-136).  C3 x T2 of --hs-size^3 phantoms (seeds 1..5)
+    with one all-background subspace (NaN Tb.Th row, constant Tb.Sp).  N = 1: the subspaces one after the other on one
+    GPU; N > 1: subspace k on rank k mod N (independent: no data-path collective, only the rows are gathered).
+    value = subspaces resident in HBM, maps left in HBM; e2e = bonej2_b200.hyperstack's public call on host arrays."""
+    import numpy as np
+    import torch
+    from bonej2_b200 import _native, hyperstack
+    from bonej2_b200.phantom import phantom_shapes
+    from bonej2_b200.wrapper import CHANNEL, TIME, X, Y, Z
+    n, C_, T_ = args.hs_size, 3, 2
+    nsub = C_ * T_
+    ctx = _native.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    vols = []
+    for k in range(nsub):
+        if k == nsub - 1:
+            vols.append(np.zeros((n, n, n), np.uint8))                       # the empty subspace
+        else:
+            vols.append(ctx.phantom(phantom_shapes(n, n, n, SEED + k), n, n, n))
+    data = np.stack(vols).reshape(T_, C_, n, n, n)                           # numpy order T, C, Z, Y, X
+    axes = [X, Y, Z, CHANNEL, TIME]
+    mine = [k for k in range(nsub) if k % world == rank]
+    d_in = [torch.from_numpy(vols[k]).cuda() for k in mine]
+    d_out = torch.empty(n ** 3, dtype=torch.float32, device="cuda")
+
+    def dev_step():
+        nl = 0
+        for t in d_in:
+            for inverse in (False, True):
+                _, tm = ctx.dev_thickness(t.data_ptr(), n, n, n, inverse=inverse, mask=True, d_out=d_out.data_ptr())
+                nl += tm.n_launches
+        return nl
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        dev_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    launches = 0
+    for _ in range(args.steps):
+        launches += dev_step()
+    ev1.record(stream)
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    dev_ms = float(ms.item())
+    # end to end: the module's public call, host arrays in, rows (and maps) out
+    e2e = []
+    rows = None
+    for i in range(args.warmup + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        if world > 1:
+            rows = hyperstack.thickness_hyperstack_ranks(data, axes, name="hyper", map_choice="Both", device=local_rank)
+        else:
+            rows, _maps = hyperstack.thickness_hyperstack(data, axes, name="hyper", map_choice="Both", devices=(local_rank,),
+                                                          want_maps=True)
+        barrier()
+        if i >= args.warmup:
+            e2e.append(time.perf_counter() - t0)
+    em = torch.tensor([1e3 * sum(e2e) / len(e2e)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(em, op=dist.ReduceOp.MAX)
+    e2e_ms = float(em.item())
+    clocks = sampler.stop()
+    ctx.close()
+    if rank != 0:
+        return
+    peaks, peak_kind = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    Nvox = nsub * n ** 3
+    edt_note = "per-subspace stage times are those of the volume workload at this size"
+    maps_back = world == 1
+    line = {
+        "metric": METRIC, "value": Nvox / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32/f32", "data": "synthetic",
+        "config": {"workload": f"BoneJ Thickness per subspace of a C{C_} x T{T_} hyperstack of {n}^3 synthetic trabecular phantoms "
+                               f"(one empty), mapChoice Both, mask on; subspace k on GPU k mod {world} (BASELINE.json configs[4])",
+                   "subspaces": nsub, "subspace_volume": [n, n, n], "parallelism": f"subspace x{world}",
+                   "l2_policy": "every subspace (16.8 MB u8, 67 MB intermediates at 256^3) is rewritten between its uses by the "
+                                "other subspaces' runs; inputs of one step exceed the 126 MB L2 together"},
+        "e2e": {"value": Nvox / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": Nvox,
+                "d2h_bytes_per_step": 8 * Nvox if maps_back else 0,
+                "call": "bonej2_b200.hyperstack.thickness_hyperstack" + ("_ranks (rows only)" if world > 1 else " (rows and maps)")},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "disc_kernel (painter, paint path 4)", "bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": None, "traffic": None, "peak_kind": peak_kind, "note": edt_note},
+        "rows": [[label, {k: (None if v != v else v) for k, v in vals.items()}] for label, vals in rows],
+        "cpu_baseline": None, "clocks": clocks,
+    }
+    emit(line)
+
+
 _REAL_STDOUT = None
 
 
@@ -154,6 +259,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-size", type=int, default=256, help="edge of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="volume", choices=["volume", "hyperstack"],
+                    help="volume: one --size^3 phantom (BASELINE.json configs[2] / [3]); hyperstack: configs[4], a C3 x T2 "
+                         "stack of --hs-size^3 phantoms, one of them empty, one Thickness run per subspace")
+    ap.add_argument("--hs-size", type=int, default=256, help="edge of one subspace of the hyperstack workload")
+    ap.add_argument("--no-multi", action="store_true", help="N > 1: skip the one-process bjt_create_multi leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200" and not os.environ.get("BJT_BENCH_SHORT_WARMUP"):
         args.warmup = 3                     # timing rule: at least 3 untimed steps (the profiling scripts set the variable)
@@ -178,6 +288,12 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if args.workload == "hyperstack":
+        run_hyperstack(args, rank, world, local_rank, dist)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     peaks, peak_kind = measured_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -210,7 +326,8 @@ def main():
                 "e2e": {"value": N / (r["e2e_ms"] * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": r["e2e_ms"],
                         "h2d_bytes_per_step": N, "d2h_bytes_per_step": 8 * N},
                 "gpu_launches": r["launches"],
-                "roofline": {"kernel": "disc_kernel + zfront_kernel (painter, paint path 4), slowest rank's paint phase per step",
+                "roofline": {"kernel": "disc_kernel (painter, paint path 4: sparse-table disc tiles); here with the front kernel: the "
+                                       "slowest rank's whole paint phase per step",
                              "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                              "traffic": None, "peak_kind": peak_kind,
                              "note": "per GPU; instruction-issue bound, not HBM bound (profiles/README.md)"},
@@ -218,7 +335,20 @@ def main():
                                          "frac_of_hbm_peak": round(edt_gbs / hbm_peak, 4)}},
                 "phases_max_over_ranks_ms": ph, "phases_rank0_ms": r["phases_rank0_ms"],
                 "map_hash": r["hashes"], "results": r["results"], "cpu_baseline": None, "clocks": clocks,
+                "layout_changes": r.get("layout_changes"),
             }
+            if r.get("multi"):
+                m = r["multi"]
+                line["e2e_one_process"] = {
+                    "value": N / (m["e2e_ms"] * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": m["e2e_ms"], "h2d_bytes_per_step": N,
+                    "d2h_bytes_per_step": 8 * N, "call": f"bjt_create_multi({world} devices) + bjt_thickness_both_u8, page-locked host buffers",
+                    "maps_match_ranks": m["hashes"] == r["hashes"], "map_hash": m["hashes"]}
+            if not args.no_cpu:
+                threads = os.cpu_count() or 1
+                g, dt = cpu_sample(args.cpu_size, threads)
+                line["cpu_baseline"] = {"value": g, "unit": UNIT, "cores": threads, "kind": "port",
+                                        "sample": f"{args.cpu_size}^3 phantom (same recipe, seed {SEED}), Both, mask on, {dt:.1f} s",
+                                        "note": "CPU restatement of sc.fiji LocalThickness_ (no JVM in image)"}
             emit(line)
         dist.destroy_process_group()
         return
@@ -298,7 +428,30 @@ def main():
             launches_e2e = tm0.n_launches + tm1.n_launches
     clocks = sampler.stop()
     e2e_ms = 1e3 * sum(e2e_times) / len(e2e_times)
+    # The path a JVM drives (bonej2_b200/csrc/jni_shim.cpp): one pageable array per slice, copied slice by slice into the
+    # page-locked staging buffers (Get<Type>ArrayRegion is a memcpy out of the Java heap), the same C-ABI call, and the
+    # maps copied back slice by slice (Set<Type>ArrayRegion).  The arrays here are numpy's, the copies the same memcpy.
+    h_in_v = np.ctypeslib.as_array(ctypes.cast(h_in, ctypes.POINTER(ctypes.c_uint8)), shape=(n, n * n))
+    h_th_v = np.ctypeslib.as_array(ctypes.cast(h_th, ctypes.POINTER(ctypes.c_float)), shape=(n, n * n))
+    h_sp_v = np.ctypeslib.as_array(ctypes.cast(h_sp, ctypes.POINTER(ctypes.c_float)), shape=(n, n * n))
+    sl_in = [h_in_v[z].copy() for z in range(n)]
+    sl_th = [np.empty(n * n, np.float32) for _ in range(n)]
+    sl_sp = [np.empty(n * n, np.float32) for _ in range(n)]
+    slice_times = []
+    for i in range(1 + min(args.steps, 3)):
+        t0 = time.perf_counter()
+        for z in range(n):
+            np.copyto(h_in_v[z], sl_in[z])
+        ctx.thickness_both_raw(h_in, n, n, n, True, 128, 1.0, h_th, h_sp)
+        for z in range(n):
+            np.copyto(sl_th[z], h_th_v[z])
+            np.copyto(sl_sp[z], h_sp_v[z])
+        if i >= 1:
+            slice_times.append(time.perf_counter() - t0)
+    e2e_slices_ms = 1e3 * sum(slice_times) / len(slice_times)
+    del sl_in, sl_th, sl_sp, h_in_v, h_sp_v
     # the host maps must agree with the device-resident ones
+    del h_th_v
     th_host = np.ctypeslib.as_array(ctypes.cast(h_th, ctypes.POINTER(ctypes.c_float)), shape=(N,))
     chk = slice(0, N, max(1, N // (1 << 22)))
     same = bool(np.array_equal(np.nan_to_num(th_host[chk], nan=-1.0), np.nan_to_num(d_th[chk].cpu().numpy(), nan=-1.0)))
@@ -384,6 +537,10 @@ def main():
                    "paint_path": paint_paths, "device": info["name"], "sm_count": info["sm_count"]},
         "e2e": {"value": N / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": N,
                 "d2h_bytes_per_step": 8 * N, "host_maps_match_device": same},
+        "e2e_slices": {"value": N / (e2e_slices_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_slices_ms,
+                       "note": "as a JVM drives it: one pageable array per slice, copied through the page-locked staging "
+                               "buffers slice by slice in and out (what jni_shim.cpp does with Get/Set<Type>ArrayRegion), "
+                               "single host thread; the copies of 9 bytes per voxel through host memory dominate"},
         "gpu_launches": int(launches),
         "roofline": roofline, "stages": stages, "map_hash": hashes, "cpu_baseline": cpu, "clocks": clocks,
         "results": {"tb_th": {k: stats_dev[0][k] for k in ("count", "mean", "sd", "max")},

@@ -120,6 +120,12 @@ _SIGS = {
     "bjt_dev_paint": ([_VP, _VP, _I, _I, _I, _I, _VP], _I),
     "bjt_dev_finish": ([_VP, _VP, _VP, _I, _I, _I, _I, _I, _D, _VP, C.POINTER(Stats)], _I),
     "bjt_dev_finish_range": ([_VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _D, _VP, C.POINTER(Stats)], _I),
+    "bjt_dev_alloc": ([_VP, C.c_char_p, C.c_size_t, C.POINTER(_VP)], _I),
+    "bjt_ipc_export": ([_VP, _VP, C.c_char_p], _I),
+    "bjt_ipc_import": ([_VP, C.c_char_p, C.POINTER(_VP)], _I),
+    "bjt_ipc_close": ([_VP, _VP], _I),
+    "bjt_dev_copy2d": ([_VP, _VP, C.c_size_t, _VP, C.c_size_t, C.c_size_t, C.c_size_t], _I),
+    "bjt_dev_copy2d_batch": ([_VP, _I, _VP, _VP, _VP, _VP, _VP, _VP], _I),
     "bjt_phantom_u8": ([_VP, _VP, _I, _I, _I, _I, _VP], _I),
     "bjt_dev_phantom_u8": ([_VP, _VP, _I, _I, _I, _I, _I, _I, _VP], _I),
 }
@@ -362,6 +368,36 @@ class Context:
         return st, tm
 
     # -- stage level, device pointers (ints); used by the z-slab sharded orchestration
+    # ---- buffers other processes read (CUDA IPC), strided device copies ----
+    def dev_alloc(self, name: str, nbytes: int) -> int:
+        p = _VP()
+        self._ck(lib().bjt_dev_alloc(self._h, name.encode(), int(nbytes), C.byref(p)))
+        return int(p.value)
+
+    def ipc_export(self, ptr: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(lib().bjt_ipc_export(self._h, ptr, buf))
+        return buf.raw
+
+    def ipc_import(self, handle: bytes) -> int:
+        p = _VP()
+        self._ck(lib().bjt_ipc_import(self._h, handle, C.byref(p)))
+        return int(p.value)
+
+    def ipc_close(self, ptr: int):
+        self._ck(lib().bjt_ipc_close(self._h, ptr))
+
+    def dev_copy2d(self, dst, dpitch, src, spitch, width, height):
+        self._ck(lib().bjt_dev_copy2d(self._h, int(dst), int(dpitch), int(src), int(spitch), int(width), int(height)))
+
+    def dev_copy2d_batch(self, blocks):
+        """blocks: [(dst, dpitch, src, spitch, width, height)] -- all of them in one launch"""
+        n = len(blocks)
+        cols = list(zip(*blocks)) if n else [[]] * 6
+        arr = [(C.c_void_p * max(n, 1))(*cols[0]), (C.c_size_t * max(n, 1))(*cols[1]), (C.c_void_p * max(n, 1))(*cols[2]),
+               (C.c_size_t * max(n, 1))(*cols[3]), (C.c_size_t * max(n, 1))(*cols[4]), (C.c_size_t * max(n, 1))(*cols[5])]
+        self._ck(lib().bjt_dev_copy2d_batch(self._h, n, *arr))
+
     def dev_edt_x(self, d_in, w, h, d, inverse, threshold, d_gx):
         self._ck(lib().bjt_dev_edt_x(self._h, d_in, w, h, d, int(inverse), int(threshold), d_gx))
 

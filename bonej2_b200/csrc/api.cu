@@ -38,6 +38,7 @@ struct bjt_ctx {
     cudaEvent_t ev[16];
     int paint_path = -1;
     int64_t launches = 0;
+    int sm_count = 0;
     // per-stage device time of the last separable paint (events around the x stage and every column block's y / z stage)
     std::vector<cudaEvent_t> pev;
     float paint_ms[3] = {0, 0, 0};
@@ -64,8 +65,10 @@ static int fail(bjt_ctx *c, int code, const char *fmt, ...) {
 #define CK(call)                                                                                         \
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
-        if (e_ != cudaSuccess)                                                                           \
+        if (e_ != cudaSuccess) {                                                                         \
+            cudaGetLastError();   /* reported here: it must not surface again at the next launch check */  \
             return fail(c, BJT_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                                \
     } while (0)
 
 #define CKL()                                                                                            \
@@ -387,15 +390,21 @@ static int dev_paint_disc(bjt_ctx *c, const uint32_t *ridge, int w, int h, int d
     WS("scalars", 256, scal);
     *done = 0;
     for (int ipv = 3; ipv <= 48; ipv *= 4) {
-        size_t free_b = 0, total_b = 0;
-        CK(cudaMemGetInfo(&free_b, &total_b));
         size_t have = 0;
         { auto it = c->bufs.find("paint_disc"); if (it != c->bufs.end()) have = it->second.cap; }
-        const size_t avail = have + (free_b > ((size_t)1 << 30) ? free_b - ((size_t)1 << 30) : 0);
         int zc = 0;
         size_t wb = 0;
-        paint_disc_plan(w, h, z_hi - z_lo, ipv, std::min(avail, (size_t)6 << 30), &zc, &wb);
-        if (wb > avail) return BJT_OK;                         // does not fit: not done
+        paint_disc_plan(w, h, z_hi - z_lo, ipv, (size_t)6 << 30, &zc, &wb);
+        if (wb > have) {
+            // the workspace has to grow: only now ask the driver how much room there is (cudaMemGetInfo takes
+            // milliseconds on some hosts -- measured 11 ms per call on a two-GPU box -- and a steady-state call with a
+            // cached workspace must not pay it)
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            const size_t avail = have + (free_b > ((size_t)1 << 30) ? free_b - ((size_t)1 << 30) : 0);
+            paint_disc_plan(w, h, z_hi - z_lo, ipv, std::min(avail, (size_t)6 << 30), &zc, &wb);
+            if (wb > avail) return BJT_OK;                     // does not fit: not done
+        }
         void *wsp;
         WS("paint_disc", wb, wsp);
         const int nchunks = (z_hi - z_lo + zc - 1) / zc;
@@ -639,6 +648,33 @@ static int dev_pipeline(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, in
 
 
 
+// n strided blocks (rows of `width` bytes) in one kernel launch when everything is 16-byte aligned, else one
+// cudaMemcpy2DAsync each; on the context's stream
+struct Block2D { void *dst; size_t dpitch; const void *src; size_t spitch, width, height; };
+static int dev_copy_blocks(bjt_ctx *c, const Block2D *blk, int n) {
+    if (c->sm_count == 0) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, c->device);
+        c->sm_count = v > 0 ? v : 148;
+    }
+    CopyBatch b;
+    b.n = 0;
+    for (int i = 0; i < n; ++i) {
+        const Block2D &k = blk[i];
+        if (k.width == 0 || k.height == 0) continue;
+        const bool vec = ((uintptr_t)k.dst | (uintptr_t)k.src | k.dpitch | k.spitch | k.width) % 16 == 0;
+        if (!vec) {
+            CK(cudaMemcpy2DAsync(k.dst, k.dpitch, k.src, k.spitch, k.width, k.height, cudaMemcpyDefault, c->stream));
+            continue;
+        }
+        b.d[b.n++] = CopyDesc{reinterpret_cast<const uint4 *>(k.src), reinterpret_cast<uint4 *>(k.dst), k.spitch / 16, k.dpitch / 16,
+                              k.width / 16, k.height};
+        if (b.n == COPY_BATCH_MAX) { c->launches += launch_copy2d_batch(b, c->sm_count, c->stream); CKL(); b.n = 0; }
+    }
+    if (b.n) { c->launches += launch_copy2d_batch(b, c->sm_count, c->stream); CKL(); }
+    return BJT_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // z-slabs over several GPUs behind the same calls (bjt_create_multi).  The reference seam is one blocking call
 // on one thread (ThicknessWrapper.java:127-134, 190-196); here that call cuts the stack into contiguous z-slabs,
@@ -737,12 +773,13 @@ static int multi_run(bjt_ctx *P, const uint8_t *in, const uint8_t *const *in_sli
             k->mg.sqt = sqt;
             if (hy == 0) return BJT_OK;
             const size_t row = (size_t)hy * w * 4;                     // my y range of one plane: contiguous on either side
+            std::vector<Block2D> blk;
             for (int i = 0; i < G; ++i) {
                 const int p = (r + i) % G;                             // every device starts with a different peer
                 int pz0, pz1; zr(p, &pz0, &pz1);
-                CK(cudaMemcpy2DAsync(gyt + (size_t)pz0 * hy * w, row, P->kids[p]->mg.gy + (size_t)y0 * w, wh * 4, row,
-                                     (size_t)(pz1 - pz0), cudaMemcpyDefault, k->stream));
+                blk.push_back(Block2D{gyt + (size_t)pz0 * hy * w, row, P->kids[p]->mg.gy + (size_t)y0 * w, wh * 4, row, (size_t)(pz1 - pz0)});
             }
+            { const int rcb = dev_copy_blocks(k, blk.data(), (int)blk.size()); if (rcb) return rcb; }
             CK(cudaMemsetAsync(scal, 0, 4, k->stream));
             k->launches += launch_edt_z(gyt, w, hy, d, n0, sqt, nullptr, scal, k->stream); CKL();
             CK(peek(k, k->h_scal, scal, 4));
@@ -777,14 +814,14 @@ static int multi_run(bjt_ctx *P, const uint8_t *in, const uint8_t *const *in_sli
                 const int de = e_hi - e_lo;
                 uint32_t *sq_ext, *ridge;
                 WS("mg_sq_ext", (size_t)de * wh * 4, sq_ext); WS("mg_ridge", (size_t)de * wh * 4, ridge);
+                std::vector<Block2D> blk;
                 for (int i = 0; i < G; ++i) {
                     const int p = (r + i) % G;
                     int py0, py1; yr(p, &py0, &py1);
                     const size_t prow = (size_t)(py1 - py0) * w * 4;
-                    if (prow == 0) continue;
-                    CK(cudaMemcpy2DAsync(sq_ext + (size_t)py0 * w, wh * 4, P->kids[p]->mg.sqt + (size_t)e_lo * (py1 - py0) * w, prow,
-                                         prow, (size_t)de, cudaMemcpyDefault, k->stream));
+                    blk.push_back(Block2D{sq_ext + (size_t)py0 * w, wh * 4, P->kids[p]->mg.sqt + (size_t)e_lo * (py1 - py0) * w, prow, prow, (size_t)de});
                 }
+                { const int rcb = dev_copy_blocks(k, blk.data(), (int)blk.size()); if (rcb) return rcb; }
                 int rc2 = dev_ridge(k, sq_ext, w, h, de, gmax, ridge, nullptr);
                 if (rc2) return rc2;
                 // the outermost fetched planes have an incomplete neighbourhood unless they are volume faces; they lie
@@ -1319,6 +1356,64 @@ int bjt_dev_finish_range(bjt_ctx *c, const uint32_t *d_rsq, const uint8_t *d_ori
     int rc = check_dims(c, w, h, d);
     if (rc) return rc;
     return dev_finish_range(c, d_rsq, d_original, w, h, d, z_lo, z_hi, inverse, calibrate, pixel_width, d_out, stats);
+}
+
+// ---- buffers other processes read: CUDA IPC over NVLink (one process per GPU; bonej2_b200/sharded.py) ----------
+// A rank's y-pass and z-pass results stay in buffers of its own context; the other ranks map them once
+// (bjt_ipc_import) and pull their share with strided copies (bjt_dev_copy2d), so the transposes of the z pass and the
+// max-radius halo are device-to-device DMA over NVLink with no pack / unpack kernels and no staging buffers.
+int bjt_dev_alloc(bjt_ctx *c, const char *name, size_t bytes, void **ptr) {
+    ENTER(c);
+    if (!name || !ptr) return fail(c, BJT_E_ARG, "dev_alloc: null argument");
+    void *p;
+    const std::string key = std::string("user:") + name;
+    WS(key.c_str(), bytes, p);
+    *ptr = p;
+    return BJT_OK;
+}
+
+int bjt_ipc_export(bjt_ctx *c, const void *ptr, unsigned char *handle64) {
+    ENTER(c);
+    if (!ptr || !handle64) return fail(c, BJT_E_ARG, "ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, const_cast<void *>(ptr)));
+    memcpy(handle64, &h, 64);
+    return BJT_OK;
+}
+
+int bjt_ipc_import(bjt_ctx *c, const unsigned char *handle64, void **ptr) {
+    ENTER(c);
+    if (!ptr || !handle64) return fail(c, BJT_E_ARG, "ipc_import: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return BJT_OK;
+}
+
+int bjt_ipc_close(bjt_ctx *c, void *ptr) {
+    ENTER(c);
+    if (ptr) CK(cudaIpcCloseMemHandle(ptr));
+    return BJT_OK;
+}
+
+int bjt_dev_copy2d(bjt_ctx *c, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height) {
+    ENTER(c);
+    if (!dst || !src) return fail(c, BJT_E_ARG, "copy2d: null pointer");
+    const Block2D b{dst, dpitch, src, spitch, width, height};
+    return dev_copy_blocks(c, &b, 1);
+}
+
+int bjt_dev_copy2d_batch(bjt_ctx *c, int n, void *const *dst, const size_t *dpitch, const void *const *src, const size_t *spitch,
+                         const size_t *width, const size_t *height) {
+    ENTER(c);
+    if (n < 0 || (n > 0 && (!dst || !dpitch || !src || !spitch || !width || !height))) return fail(c, BJT_E_ARG, "copy2d_batch: null argument");
+    std::vector<Block2D> blk;
+    for (int i = 0; i < n; ++i) {
+        if (!dst[i] || !src[i]) return fail(c, BJT_E_ARG, "copy2d_batch: null pointer in block %d", i);
+        blk.push_back(Block2D{dst[i], dpitch[i], src[i], spitch[i], width[i], height[i]});
+    }
+    return dev_copy_blocks(c, blk.data(), n);
 }
 
 // ---- phantom ---------------------------------------------------------------------------------------

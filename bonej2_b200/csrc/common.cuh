@@ -145,6 +145,12 @@ int launch_ridge_points_collect(const float *ridge, size_t n, float threshold, u
                                 unsigned long long *count, cudaStream_t s);
 int launch_check_binary(const uint8_t *in, size_t n, uint32_t *bad, cudaStream_t s);
 
+// strided copies by the SMs, all blocks of a batch in one launch (peer_copy.cu); units of 16 bytes
+constexpr int COPY_BATCH_MAX = 16;
+struct CopyDesc { const uint4 *src; uint4 *dst; size_t spitch16, dpitch16, width16, height; };
+struct CopyBatch { int n; CopyDesc d[COPY_BATCH_MAX]; };
+int launch_copy2d_batch(const CopyBatch &b, int sm_count, cudaStream_t s);
+
 int launch_phantom(const int32_t *shapes, int nshapes, int w, int h, int d, int z0, int dz, uint8_t *out,
                    cudaStream_t s);
 

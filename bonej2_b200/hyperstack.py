@@ -105,8 +105,16 @@ def thickness_hyperstack_ranks(data, axes, name="image", map_choice="Both", mask
         import os
         ctx = _native.Context(int(os.environ.get("LOCAL_RANK", rank)) if device is None else device)
 
+        cache = {}
+
         def run(vol, inverse):
-            _, st, _ = ctx.thickness(vol, inverse=inverse, mask=mask, pixel_width=pixel_width, want_map=False)
+            # "Both": one call per subspace (one upload); the second run's row comes from the same call
+            key = id(vol)
+            if key not in cache:
+                cache.clear()
+                res = _run_subspace(ctx, vol, map_choice, mask, pixel_width, False)
+                cache[key] = {inv: res[prefix][0] for prefix, inv in runs}
+            st = cache[key][inverse]
             return (st.mean, st.sd, st.max) if st.count else (float("nan"),) * 3
     mine = []
     try:
@@ -133,35 +141,67 @@ def thickness_hyperstack_ranks(data, axes, name="image", map_choice="Both", mask
     return [(label, vals) for _, label, vals in rows]
 
 
+def _run_subspace(ctx, vol, map_choice, mask, pixel_width, want_maps):
+    """one subspace through the C-ABI: {prefix: (stats, map)}; "Both" is one call (one upload, the first map on its way
+    back while the second run computes: bjt_thickness_both_u8), as ThicknessWrapper.run does for one image"""
+    if map_choice == "Both":
+        (m0, s0, _), (m1, s1, _) = ctx.thickness_both(vol, mask=mask, pixel_width=pixel_width, want_maps=want_maps)
+        return {"Tb.Th": (s0, m0), "Tb.Sp": (s1, m1)}
+    prefix, inverse = _runs(map_choice)[0]
+    m, st, _ = ctx.thickness(vol, inverse=inverse, mask=mask, pixel_width=pixel_width, want_map=want_maps)
+    return {prefix: (st, m)}
+
+
 def thickness_hyperstack(data, axes, name="image", map_choice="Both", mask=True, pixel_width=1.0, unit="",
                          devices=(0,), want_maps=False):
     """Thickness on every {X, Y, Z} subspace.  Returns rows [(label, {header: value})] in subspace order
-    (and the maps when want_maps).  Subspaces are dealt round-robin to the given CUDA devices."""
-    if map_choice not in ("Trabecular thickness", "Trabecular separation", "Both"):
-        raise ValueError("Unexpected map choice")
+    (and the maps when want_maps).  Subspaces are dealt round-robin to the given CUDA devices and the devices work
+    at the same time: one host thread per device drives its context (the calls block in native code with the
+    interpreter lock released), so k devices take k subspaces at once.  A failure on any device is raised after the
+    others have finished their current subspace."""
+    import threading
+    runs = _runs(map_choice)
     unit_header = f"({unit or 'pixel'})"
+    subs = list(split_3d_subspaces(np.asarray(data), axes))
+    for sub in subs:
+        if sub.data.dtype != np.uint8:
+            raise ValueError("Need a binary image")
     ctxs = [_native.Context(d) for d in devices]
-    rows, maps = [], []
+    results, errors = [None] * len(subs), []
+
+    def worker(i):
+        try:
+            for k in range(i, len(subs), len(ctxs)):
+                if errors:
+                    return
+                results[k] = _run_subspace(ctxs[i], subs[k].data, map_choice, mask, pixel_width, want_maps)
+        except Exception as e:                                   # re-raised on the calling thread
+            errors.append(e)
+
     try:
-        for k, sub in enumerate(split_3d_subspaces(np.asarray(data), axes)):
-            ctx = ctxs[k % len(ctxs)]
-            vol = sub.data
-            if vol.dtype != np.uint8:
-                raise ValueError("Need a binary image")
-            label = f"{name} {sub.label}".strip()
-            vals, out = {}, {}
-            runs = [("Tb.Th", False)] if map_choice == "Trabecular thickness" else \
-                   [("Tb.Sp", True)] if map_choice == "Trabecular separation" else [("Tb.Th", False), ("Tb.Sp", True)]
-            for prefix, inverse in runs:
-                m, st, _ = ctx.thickness(vol, inverse=inverse, mask=mask, pixel_width=pixel_width, want_map=want_maps)
-                mean, sd, mx = (st.mean, st.sd, st.max) if st.count else (float("nan"),) * 3
-                vals[f"{prefix} Mean {unit_header}"] = mean
-                vals[f"{prefix} Std Dev {unit_header}"] = sd
-                vals[f"{prefix} Max {unit_header}"] = mx
-                out[prefix] = m
-            rows.append((label, vals))
-            maps.append(out)
+        if len(ctxs) == 1:
+            worker(0)
+        else:
+            threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(ctxs))]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
     finally:
         for c in ctxs:
             c.close()
+    if errors:
+        raise errors[0]
+    rows, maps = [], []
+    for sub, res in zip(subs, results):
+        vals, out = {}, {}
+        for prefix, _ in runs:
+            st, m = res[prefix]
+            mean, sd, mx = (st.mean, st.sd, st.max) if st.count else (float("nan"),) * 3
+            vals[f"{prefix} Mean {unit_header}"] = mean
+            vals[f"{prefix} Std Dev {unit_header}"] = sd
+            vals[f"{prefix} Max {unit_header}"] = mx
+            out[prefix] = m
+        rows.append((f"{name} {sub.label}".strip(), vals))
+        maps.append(out)
     return (rows, maps) if want_maps else rows

@@ -7,6 +7,12 @@ The volume [d][h][w] is cut into contiguous z-slabs, one per rank
   r_max             all-reduce of the largest squared distance: no ball reaches further than H = floor(sqrt(max))
   halo              ONE exchange per run: every rank fetches the squared-EDT planes within H + 3 of its slab (the
                     "max-radius halo exchange" of BASELINE.json's north_star)
+                    On GPUs with even splits both layout changes are PULLS out of the peers' HBM (PeerExchange: the
+                    y-pass and z-pass results live in buffers every other rank has mapped through CUDA IPC; a rank
+                    copies its share with one strided device-to-device copy per peer over NVLink, and the transpose
+                    back fetches slab + halo planes in the same copy, straight from the y-slab layout): no pack or
+                    unpack kernels, no staging, no separate halo exchange.  Otherwise (CPU tests over gloo, ragged
+                    splits) the same data moves with point-to-point sends.
   ridge             on slab +- (H + 2) planes (the outermost fetched plane only serves as a neighbour)
   paint             planes slab +- 2 only (bjt_dev_paint_range): the painter's fronts run along z and read the ridge
                     within H of a plane, its discs are plane-local, so nothing else crosses a slab face
@@ -101,6 +107,73 @@ class Comm:
         if self.size > 1:
             dist.barrier(group=self.group)
 
+    def stream_barrier(self, device):
+        """a collective in stream order: when it has run on this rank's stream, every rank's work queued before its own
+        call has finished (what a pull out of a peer's buffer waits for)"""
+        if self.size > 1:
+            t = torch.zeros(1, dtype=torch.int32, device=device)
+            dist.all_reduce(t, group=self.group)
+
+
+class DeviceArray:
+    """a device buffer of the library (bjt_dev_alloc) or of a peer (bjt_ipc_import) as something torch can view"""
+
+    def __init__(self, ptr, shape, typestr):
+        self.ptr = ptr
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class PeerExchange:
+    """The two buffers of this rank that the other ranks read -- gy [dz][h][w] (y-pass result, z-slab layout) and
+    sqt [d][hy][w] (z-pass result, y-slab layout) -- and the mappings of every peer's pair (CUDA IPC: the ranks are
+    processes).  Needs d and h divisible by the number of ranks (every rank's buffers then have the same shape)."""
+
+    def __init__(self, ctx, comm, dims, device):
+        w, h, d = dims
+        G, r = comm.size, comm.rank
+        if d % G or h % G:
+            raise ValueError("PeerExchange needs d and h divisible by the number of ranks")
+        self.ctx, self.dims, self.dz, self.hy = ctx, dims, d // G, h // G
+        self.gy_ptr = ctx.dev_alloc("peer_gy", self.dz * h * w * 4)
+        self.sqt_ptr = ctx.dev_alloc("peer_sqt", d * self.hy * w * 4)
+        self.gy = torch.as_tensor(DeviceArray(self.gy_ptr, (self.dz, h, w), "<i4"), device=device)
+        self.sqt = torch.as_tensor(DeviceArray(self.sqt_ptr, (d, self.hy, w), "<i4"), device=device)
+        mine = (ctx.ipc_export(self.gy_ptr), ctx.ipc_export(self.sqt_ptr))
+        everyone = [mine]
+        if G > 1:
+            everyone = [None] * G
+            dist.all_gather_object(everyone, mine, group=comm.group)
+        self.peer_gy, self.peer_sqt, self._opened = [0] * G, [0] * G, []
+        for p in range(G):
+            if p == r:
+                self.peer_gy[p], self.peer_sqt[p] = self.gy_ptr, self.sqt_ptr
+            else:
+                self.peer_gy[p] = ctx.ipc_import(everyone[p][0])
+                self.peer_sqt[p] = ctx.ipc_import(everyone[p][1])
+                self._opened += [self.peer_gy[p], self.peer_sqt[p]]
+
+    def close(self):
+        for ptr in self._opened:
+            self.ctx.ipc_close(ptr)
+        self._opened = []
+
+    def pull_y_slab(self, comm, out):
+        """out [d][hy][w] <- my y range of every rank's gy (the all-to-all transpose z-slabs -> y-slabs)"""
+        w, h, d = self.dims
+        G, r, dz, hy = comm.size, comm.rank, self.dz, self.hy
+        row = hy * w * 4
+        order = [(r + i) % G for i in range(G)]                        # every rank starts with a different peer
+        self.ctx.dev_copy2d_batch([(out.data_ptr() + p * dz * row, row, self.peer_gy[p] + r * row, h * w * 4, row, dz) for p in order])
+
+    def pull_planes(self, comm, out, lo, hi):
+        """out [hi - lo][h][w] <- planes [lo, hi) of the squared EDT, gathered from every rank's y-slab result (the
+        transpose back and the halo in one copy per peer)"""
+        w, h, d = self.dims
+        G, r, hy = comm.size, comm.rank, self.hy
+        row = hy * w * 4
+        order = [(r + i) % G for i in range(G)]
+        self.ctx.dev_copy2d_batch([(out.data_ptr() + p * row, h * w * 4, self.peer_sqt[p] + lo * row, row, row, hi - lo) for p in order])
+
 
 # ------------------------------------------------------------------------------------------------------
 # layout changes
@@ -187,15 +260,15 @@ class CudaStages:
         self.ctx.dev_edt_x(slab_u8.data_ptr(), w, h, dz, inverse, threshold, gx.data_ptr())
         return gx
 
-    def edt_y(self, gx, n_sentinel):
+    def edt_y(self, gx, n_sentinel, out=None):
         dz, h, w = gx.shape
-        gy = self._i32((dz, h, w))
+        gy = self._i32((dz, h, w)) if out is None else out
         self.ctx.dev_edt_y(gx.data_ptr(), w, h, dz, n_sentinel, gy.data_ptr())
         return gy
 
-    def edt_z(self, gy_t, n_sentinel):
+    def edt_z(self, gy_t, n_sentinel, out=None):
         d, hy, w = gy_t.shape
-        sq = self._i32((d, hy, w))
+        sq = self._i32((d, hy, w)) if out is None else out
         if hy > 0:
             self.ctx.dev_edt_z(gy_t.data_ptr(), w, hy, d, n_sentinel, sq.data_ptr())
         return sq
@@ -260,9 +333,10 @@ class PhaseTimer:
         return self.ms
 
 
-def thickness_slab(stages, comm: Comm, slab_u8, dims, inverse, mask=True, pixel_width=1.0, timer=None):
+def thickness_slab(stages, comm: Comm, slab_u8, dims, inverse, mask=True, pixel_width=1.0, timer=None, peer=None):
     """One pipeline run (LocalThicknessWrapper.processImage + StackStatistics) on this rank's z-slab.
-    slab_u8: [dz][h][w] planes zs[rank] of the volume dims = (w, h, d).  Returns (map slab f32, stats dict)."""
+    slab_u8: [dz][h][w] planes zs[rank] of the volume dims = (w, h, d).  Returns (map slab f32, stats dict).
+    peer: a PeerExchange for these dims -- the layout changes are then pulls out of the peers' memory."""
     w, h, d = dims
     G, r = comm.size, comm.rank
     zs, ys = split_ranges(d, G), split_ranges(h, G)
@@ -273,20 +347,37 @@ def thickness_slab(stages, comm: Comm, slab_u8, dims, inverse, mask=True, pixel_
 
     mark("start")
     gx = stages.edt_x(slab_u8, inverse)
-    gy = stages.edt_y(gx, n)
-    del gx
-    mark("edt_xy")
-    gy_t = transpose_z_to_y(comm, gy, zs, ys)
-    del gy
-    mark("transpose")
-    sq_t = stages.edt_z(gy_t, n)
-    del gy_t
-    mark("edt_z")
-    sq = transpose_y_to_z(comm, sq_t, zs, ys, h)
-    del sq_t
-    mark("transpose")
-    gmax = comm.allreduce_max_int(stages.max_value(sq), slab_u8.device)
-    mark("rmax")
+    if peer is not None:
+        stages.edt_y(gx, n, out=peer.gy)
+        del gx
+        mark("edt_xy")
+        comm.stream_barrier(slab_u8.device)                            # every rank's y pass has finished
+        gy_t = torch.empty((d, ys[r][1] - ys[r][0], w), dtype=torch.int32, device=slab_u8.device)
+        peer.pull_y_slab(comm, gy_t)
+        mark("transpose")
+        stages.edt_z(gy_t, n, out=peer.sqt)
+        del gy_t
+        mark("edt_z")
+        # the collective also orders the pulls: after it every rank's z pass has finished (sqt may be read) and every
+        # pull out of gy has completed (the next run may overwrite it)
+        gmax = comm.allreduce_max_int(stages.max_value(peer.sqt), slab_u8.device)
+        mark("rmax")
+        sq = None
+    else:
+        gy = stages.edt_y(gx, n)
+        del gx
+        mark("edt_xy")
+        gy_t = transpose_z_to_y(comm, gy, zs, ys)
+        del gy
+        mark("transpose")
+        sq_t = stages.edt_z(gy_t, n)
+        del gy_t
+        mark("edt_z")
+        sq = transpose_y_to_z(comm, sq_t, zs, ys, h)
+        del sq_t
+        mark("transpose")
+        gmax = comm.allreduce_max_int(stages.max_value(sq), slab_u8.device)
+        mark("rmax")
 
     # planes of the painted map the cleanup of this slab reads: slab +- 2, clipped to the volume
     s_lo, s_hi = (max(0, z0 - 2), min(d, z1 + 2)) if z1 > z0 else (z0, z0)
@@ -300,7 +391,12 @@ def thickness_slab(stages, comm: Comm, slab_u8, dims, inverse, mask=True, pixel_
         # EDT one plane further out
         needs = [((max(0, a - 2 - H - 1), min(d, b + 2 + H + 1)) if b > a else (a, a)) for (a, b) in zs]
         e_lo, e_hi = needs[r]
-        sq_ext = gather_planes(comm, sq, zs, needs)
+        if peer is not None:
+            sq_ext = torch.empty((e_hi - e_lo, h, w), dtype=torch.int32, device=slab_u8.device)
+            if e_hi > e_lo:
+                peer.pull_planes(comm, sq_ext, e_lo, e_hi)
+        else:
+            sq_ext = gather_planes(comm, sq, zs, needs)
         mark("halo")
         if z1 > z0:
             ridge_ext = stages.ridge(sq_ext)
@@ -319,6 +415,7 @@ def thickness_slab(stages, comm: Comm, slab_u8, dims, inverse, mask=True, pixel_
         del sq_ext
     out, part = stages.finish(rsq_sub, slab_u8, z0 - s_lo, z1 - s_lo, inverse, mask, pixel_width)
     mark("finish")
+    # (with a PeerExchange this collective is also what lets the next run overwrite sqt: every rank's pulls precede it)
     stats = comm.combine_stats(part, slab_u8.device).finalize()
     mark("stats")
     return out, stats
@@ -371,9 +468,13 @@ def bench(args, rank, world, local_rank, dist_mod):
     slab = torch.empty((dz, n, n), dtype=torch.uint8, device=dev)
     ctx.dev_phantom(shapes, n, n, n, z0, dz, slab.data_ptr())
 
+    peer = None
+    if n % world == 0 and __import__("os").environ.get("BJT_NO_PEER", "0") != "1":
+        peer = PeerExchange(ctx, comm, dims, dev)
+
     def step(timer=None):
-        th = thickness_slab(stages, comm, slab, dims, False, True, 1.0, timer)
-        sp = thickness_slab(stages, comm, slab, dims, True, True, 1.0, timer)
+        th = thickness_slab(stages, comm, slab, dims, False, True, 1.0, timer, peer)
+        sp = thickness_slab(stages, comm, slab, dims, True, True, 1.0, timer, peer)
         return th, sp
 
     for _ in range(args.warmup):
@@ -417,12 +518,12 @@ def bench(args, rank, world, local_rank, dist_mod):
         torch.cuda.synchronize(); comm.barrier()
         t0 = time.perf_counter()
         slab2.copy_(h_in, non_blocking=True)
-        th = thickness_slab(stages, comm, slab2, dims, False, True, 1.0)
+        th = thickness_slab(stages, comm, slab2, dims, False, True, 1.0, None, peer)
         copy_stream.wait_stream(stream)
         with torch.cuda.stream(copy_stream):
             h_th.copy_(th[0], non_blocking=True)
         th[0].record_stream(copy_stream)
-        sp = thickness_slab(stages, comm, slab2, dims, True, True, 1.0)
+        sp = thickness_slab(stages, comm, slab2, dims, True, True, 1.0, None, peer)
         h_sp.copy_(sp[0], non_blocking=True)
         torch.cuda.synchronize(); comm.barrier()
         if i >= args.warmup:
@@ -435,6 +536,51 @@ def bench(args, rank, world, local_rank, dist_mod):
     pt = torch.tensor([per[k] for k in names], dtype=torch.float64, device=dev)
     dist_mod.all_reduce(pt, op=dist_mod.ReduceOp.MAX)
     per_max = {k: float(v) for k, v in zip(names, pt.tolist())}
-    return dict(dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), phases_rank0_ms={k: round(v, 3) for k, v in per.items()},
+    if peer is not None:
+        torch.cuda.synchronize(); comm.barrier()
+        peer.close()
+
+    # The same volume through ONE process: bjt_create_multi over all the GPUs of the job and the blocking C-ABI call a
+    # JNI shim binds (bjt_thickness_both_u8, page-locked host buffers) -- how the reference's single-call seam
+    # (ThicknessWrapper.java:127-134, 190-196) reaches N GPUs.  Rank 0 drives it while the other ranks wait on the
+    # host (a gloo barrier: an NCCL barrier would keep their GPUs spinning).
+    multi = None
+    if not getattr(args, "no_multi", False) and n <= 1024:
+        host_group = dist_mod.new_group(backend="gloo")
+        th, sp = (None, th[1]), (None, sp[1])                               # keep the statistics, drop the maps
+        del slab2, h_in, h_th, h_sp
+        torch.cuda.empty_cache()
+        if rank == 0:
+            import ctypes
+            import numpy as np
+            L = _native.lib()
+            N = n ** 3
+            vol = ctx.phantom(shapes, n, n, n)
+            ctx.release_workspace()
+            p_in, p_th, p_sp = L.bjt_host_alloc(N), L.bjt_host_alloc(4 * N), L.bjt_host_alloc(4 * N)
+            ctypes.memmove(p_in, vol.ctypes.data, N)
+            del vol
+            with _native.Context(devices=list(range(world))) as mctx:
+                times = []
+                for i in range(2 + args.steps):
+                    t0 = time.perf_counter()
+                    (s0, _), (s1, _) = mctx.thickness_both_raw(p_in, n, n, n, True, 128, 1.0, p_th, p_sp)
+                    if i >= 2:
+                        times.append(time.perf_counter() - t0)
+                ms_multi = 1e3 * sum(times) / len(times)
+                mm = {}
+                for name, ptr in (("tb_th", p_th), ("tb_sp", p_sp)):
+                    a = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_float)), shape=(n, n, n))
+                    hh = {}
+                    for k, (za, zb) in enumerate(split_ranges(n, 8)):           # the same ranges and checksum as map_hashes
+                        t = torch.from_numpy(a[za:zb]).to(dev)
+                        hh.update(map_hashes(t, za, dims, 8))
+                        del t
+                    mm[name] = [format(hh[k], "016x") for k in range(8)]
+                multi = dict(e2e_ms=ms_multi, hashes=mm, count=[int(s0.count), int(s1.count)], mean=[s0.mean, s1.mean])
+            for ptr in (p_in, p_th, p_sp):
+                L.bjt_host_free(ptr)
+        dist_mod.barrier(group=host_group)
+    return dict(multi=multi, dev_ms=dev_ms, e2e_ms=e2e_ms, launches=int(launches), layout_changes="peer pulls (CUDA IPC)" if peer is not None else "nccl send/recv", phases_rank0_ms={k: round(v, 3) for k, v in per.items()},
                 phases_max_ms={k: round(v, 3) for k, v in per_max.items()}, hashes=hashes,
                 results={"tb_th": th[1], "tb_sp": sp[1]})

@@ -214,6 +214,21 @@ int bjt_dev_finish_range(bjt_ctx *ctx, const uint32_t *d_rsq, const uint8_t *d_o
                          int z_lo, int z_hi, int inverse, int calibrate, double pixel_width, float *d_out,
                          bjt_stats *stats);
 
+/* ---- device buffers that other processes read directly (one process per GPU: bonej2_b200/sharded.py) ---- *
+ * bjt_dev_alloc: a named device buffer owned by the context (kept until bjt_release_workspace / bjt_destroy).
+ * bjt_ipc_export / _import: a 64-byte CUDA IPC handle of such a buffer, and its mapping in another process (peer
+ * access over NVLink is enabled on first use); bjt_ipc_close unmaps.  bjt_dev_copy2d: strided device-to-device copy
+ * on the context's stream (height rows of width bytes), local or out of a mapped peer buffer -- the transposes
+ * of the EDT z pass ("NCCL all-to-all transpose" of the north star) and the max-radius halo are such pulls. */
+int bjt_dev_alloc(bjt_ctx *ctx, const char *name, size_t bytes, void **ptr);
+int bjt_ipc_export(bjt_ctx *ctx, const void *ptr, unsigned char *handle64);
+int bjt_ipc_import(bjt_ctx *ctx, const unsigned char *handle64, void **ptr);
+int bjt_ipc_close(bjt_ctx *ctx, void *ptr);
+int bjt_dev_copy2d(bjt_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height);
+/* n such copies in one kernel launch (the shares of all peers at once; 16-byte aligned blocks are moved by the SMs) */
+int bjt_dev_copy2d_batch(bjt_ctx *ctx, int n, void *const *dst, const size_t *dpitch, const void *const *src,
+                         const size_t *spitch, const size_t *width, const size_t *height);
+
 /* ---- synthetic trabecular phantom (workload of BASELINE.json) ------------------- */
 /* shapes: n records of 16 int32 (bonej2_b200/phantom.py); out: u8 [d][h][w] in {0,255}          */
 int bjt_phantom_u8(bjt_ctx *ctx, const int32_t *shapes, int nshapes, int w, int h, int d, uint8_t *out);

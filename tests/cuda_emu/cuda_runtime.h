@@ -63,6 +63,8 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
     p->multiProcessorCount = 1; p->major = 0; p->minor = 0;
     return cudaSuccess;
 }
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { *v = 1; return cudaSuccess; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated CUDA runtime"; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (cudaStream_t)(uintptr_t)1; return cudaSuccess; }
@@ -88,6 +90,11 @@ inline cudaError_t cudaMemcpy2DAsync(void *dst, size_t dpitch, const void *src, 
     for (size_t i = 0; i < height; ++i) memcpy((char *)dst + i * dpitch, (const char *)src + i * spitch, width);
     return cudaSuccess;
 }
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
+inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
 inline cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 0; return cudaSuccess; }
 inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 

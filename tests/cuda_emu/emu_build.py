@@ -125,7 +125,7 @@ def build(force=False):
 
 API_OUT = os.path.join(_OUTDIR, "libbonejthickness_emu.so")
 API_SOURCES = ["api.cu", "edt.cu", "ridge.cu", "paint_sep.cu", "paint_disc.cu", "paint_scatter.cu", "finish.cu", "phantom.cu", "segstats.cu",
-               "ridgepoints.cu"]
+               "ridgepoints.cu", "peer_copy.cu"]
 
 
 def build_api(force=False):

@@ -24,19 +24,36 @@ def _cmp(got, st, ref):
         assert st["max"] == pytest.approx(ref["stats"].max, rel=1e-6)
 
 
+@pytest.mark.parametrize("use_peer", [False, True], ids=["plain", "peer_buffers"])
 @pytest.mark.parametrize("inverse", [False, True])
-def test_single_rank_matches_oracle(ctx, oracle, inverse):
+def test_single_rank_matches_oracle(ctx, oracle, inverse, use_peer):
+    """one rank: the slab is the volume.  With use_peer the layout changes go through the exchange buffers and the
+    strided device copies of the multi-rank path (bjt_dev_alloc, bjt_dev_copy2d), pulling from itself."""
     from bonej2_b200 import sharded
     vol = shapes.random_blobs((40, 36, 44), 9)
     dev = torch.device("cuda", 0)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     slab = torch.from_numpy(vol).to(dev)
     d, h, w = vol.shape
-    out, st = sharded.thickness_slab(sharded.CudaStages(ctx, dev), sharded.Comm(), slab, (w, h, d), inverse, True, 0.7)
+    comm = sharded.Comm()
+    peer = sharded.PeerExchange(ctx, comm, (w, h, d), dev) if use_peer else None
+    out, st = sharded.thickness_slab(sharded.CudaStages(ctx, dev), comm, slab, (w, h, d), inverse, True, 0.7, None, peer)
     _cmp(out.cpu().numpy(), st, oracle.process_image(vol, inverse=inverse, mask=True, pixel_width=0.7))
 
 
-def _worker(rank, world, port, vol_path, out_dir, inverse):
+def test_ipc_handle_round_trip_in_process(ctx):
+    """bjt_ipc_export gives a 64-byte handle of a library buffer; importing it in the exporting process is refused by
+    CUDA (a handle is for another process) and reported as an error, never ignored"""
+    from bonej2_b200 import _native
+    p = ctx.dev_alloc("ipc_test", 4096)
+    h = ctx.ipc_export(p)
+    assert len(h) == 64 and any(h)
+    assert ctx.dev_alloc("ipc_test", 1024) == p                      # named buffers persist and only grow
+    with pytest.raises(_native.ThicknessError):
+        ctx.ipc_import(h)
+
+
+def _worker(rank, world, port, vol_path, out_dir, inverse, use_peer):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     from bonej2_b200 import _native, sharded
@@ -50,16 +67,26 @@ def _worker(rank, world, port, vol_path, out_dir, inverse):
     c = _native.Context(rank)
     c.set_stream(torch.cuda.current_stream().cuda_stream)
     slab = torch.from_numpy(vol[zs[rank][0]:zs[rank][1]].copy()).to(dev)
-    out, st = sharded.thickness_slab(sharded.CudaStages(c, dev), sharded.Comm(), slab, (w, h, d), inverse, True, 1.0)
+    comm = sharded.Comm()
+    peer = sharded.PeerExchange(c, comm, (w, h, d), dev) if use_peer else None
+    stages = sharded.CudaStages(c, dev)
+    if use_peer:    # the other run first: the exchange buffers are reused from run to run, as in a "Both" call
+        sharded.thickness_slab(stages, comm, slab, (w, h, d), not inverse, True, 1.0, None, peer)
+    out, st = sharded.thickness_slab(stages, comm, slab, (w, h, d), inverse, True, 1.0, None, peer)
     np.save(os.path.join(out_dir, f"map_{rank}.npy"), out.cpu().numpy())
+    if peer is not None:
+        torch.cuda.synchronize(); comm.barrier()
+        peer.close()
     if rank == 0:
         np.save(os.path.join(out_dir, "stats.npy"), np.array([st["count"], st["mean"], st["sd"], st["min"], st["max"]]))
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("use_peer", [False, True], ids=["nccl_p2p", "peer_pulls"])
 @pytest.mark.parametrize("inverse", [False, True])
-def test_two_ranks_nccl_bitwise(oracle, tmp_path, inverse):
+def test_two_ranks_nccl_bitwise(oracle, tmp_path, inverse, use_peer):
+    """two ranks, two GPUs: layout changes by NCCL send / recv, and by pulls out of the peer's memory (CUDA IPC)"""
     import torch.multiprocessing as mp
     from bonej2_b200 import _native
     from bonej2_b200.phantom import phantom_shapes
@@ -68,7 +95,7 @@ def test_two_ranks_nccl_bitwise(oracle, tmp_path, inverse):
     vol_path = os.path.join(tmp_path, "vol.npy")
     np.save(vol_path, vol)
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_worker, args=(2, port, vol_path, str(tmp_path), inverse), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, vol_path, str(tmp_path), inverse, use_peer), nprocs=2, join=True)
     got = np.concatenate([np.load(os.path.join(tmp_path, f"map_{r}.npy")) for r in range(2)], axis=0)
     with _native.Context(0) as c:
         one, st1, _ = c.thickness(vol, inverse=inverse, mask=True)

@@ -115,3 +115,33 @@ def test_ranks_single_process_cuda(oracle):
     for (label, vals), vol in zip(rows, vols):
         st = oracle.process_image(vol, inverse=True, mask=True)["stats"]
         assert math.isclose(vals["Tb.Sp Mean (pixel)"], st.mean, rel_tol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("map_choice", ["Both", "Trabecular separation"])
+def test_devices_work_concurrently_and_agree(map_choice):
+    """three contexts (here on the GPUs of the box, sharing one if there is only one), one host thread each: rows and
+    maps are those of the single-context batch, in subspace order"""
+    import torch
+    vols = [shapes.random_blobs((16, 18, 20), s) for s in (1, 2, 3, 4, 5)] + [np.zeros((16, 18, 20), np.uint8),
+                                                                           np.full((16, 18, 20), 255, np.uint8)]
+    data = np.stack(vols)                                          # T = 7, Z, Y, X
+    ndev = torch.cuda.device_count()
+    one, maps1 = hs.thickness_hyperstack(data, [X, Y, Z, TIME], name="h", map_choice=map_choice, want_maps=True)
+    many, maps3 = hs.thickness_hyperstack(data, [X, Y, Z, TIME], name="h", map_choice=map_choice, want_maps=True,
+                                          devices=[i % ndev for i in range(3)])
+    assert [r[0] for r in one] == [r[0] for r in many] == [f"h Time: {t}" for t in range(1, 8)]
+    for (_, a), (_, b), ma, mb in zip(one, many, maps1, maps3):
+        assert a.keys() == b.keys()
+        for k in a:
+            assert (math.isnan(a[k]) and math.isnan(b[k])) or a[k] == b[k], k
+        for prefix in ma:
+            assert np.array_equal(ma[prefix].view(np.uint32), mb[prefix].view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_failure_on_one_device_is_raised():
+    from bonej2_b200._native import ThicknessError
+    vols = [shapes.random_blobs((8, 9, 10), 1), np.full((8, 9, 10), 7, np.uint8)]      # the second is not binary
+    with pytest.raises(ThicknessError):
+        hs.thickness_hyperstack(np.stack(vols), [X, Y, Z, TIME], devices=[0, 0])

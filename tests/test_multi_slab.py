@@ -29,10 +29,11 @@ def one(lib_kind):
     c.close()
 
 
-def _multi(nslabs):
+def _multi(nslabs, kind):
+    """slabs dealt round-robin over the GPUs of the box (one GPU: they share it); the emulation has one device"""
     from bonej2_b200 import _native
     import torch
-    ndev = torch.cuda.device_count() if torch.cuda.is_available() else 1
+    ndev = torch.cuda.device_count() if (kind == "gpu" and torch.cuda.is_available()) else 1
     return _native.Context(devices=[i % max(ndev, 1) for i in range(nslabs)])
 
 
@@ -44,7 +45,7 @@ def _bits(a):
 @pytest.mark.parametrize("shape,seed", [((24, 20, 28), 3), ((9, 33, 17), 8)])
 def test_both_equals_single_device(lib_kind, one, oracle, nslabs, shape, seed):
     vol = shapes.random_blobs(shape, seed)
-    with _multi(nslabs) as m:
+    with _multi(nslabs, lib_kind) as m:
         assert m.device_count() == nslabs
         (a_th, sa_th, t_th), (a_sp, sa_sp, _) = m.thickness_both(vol, mask=True, pixel_width=0.5)
     (b_th, sb_th, _), (b_sp, sb_sp, _) = one.thickness_both(vol, mask=True, pixel_width=0.5)
@@ -62,7 +63,7 @@ def test_both_equals_single_device(lib_kind, one, oracle, nslabs, shape, seed):
 @pytest.mark.parametrize("mask", [False, True])
 def test_single_run_and_slices(lib_kind, one, inverse, mask):
     vol = shapes.random_blobs((17, 22, 26), 11)
-    with _multi(4) as m:
+    with _multi(4, lib_kind) as m:
         a, sa, _ = m.thickness(vol, inverse=inverse, mask=mask)
         outs, ss, _ = m.thickness_slices([vol[z] for z in range(vol.shape[0])], inverse=inverse, mask=mask)
         _, s_only, _ = m.thickness(vol, inverse=inverse, mask=mask, want_map=False)
@@ -76,7 +77,7 @@ def test_single_run_and_slices(lib_kind, one, inverse, mask):
 def test_edge_volumes(lib_kind, one, oracle, name):
     """empty and full volumes (constant fast paths), fewer planes than devices, one plane"""
     vol = G.CASES[name]
-    with _multi(3) as m:
+    with _multi(3, lib_kind) as m:
         for inverse in (False, True):
             a, sa, _ = m.thickness(vol, inverse=inverse, mask=True)
             b, sb, _ = one.thickness(vol, inverse=inverse, mask=True)
@@ -92,7 +93,7 @@ def test_not_binary_and_bad_arguments(lib_kind):
     from bonej2_b200 import _native
     vol = np.zeros((6, 5, 4), np.uint8)
     vol[5, 4, 3] = 9                                    # in the last slab only
-    with _multi(3) as m:
+    with _multi(3, lib_kind) as m:
         with pytest.raises(_native.ThicknessError) as e:
             m.thickness(vol)
         assert e.value.code == _native.BJT_E_NOT_BINARY
@@ -110,7 +111,7 @@ def test_thin_slabs_far_reach(lib_kind, one):
     vol = np.full((30, 26, 26), 255, np.uint8)
     vol[0, 0, 0] = 0
     vol[29, 25, 25] = 0
-    with _multi(6) as m:
+    with _multi(6, lib_kind) as m:
         a, sa, tm = m.thickness(vol, inverse=False, mask=True)
     b, sb, _ = one.thickness(vol, inverse=False, mask=True)
     assert tm.rsq_max > 5 * 5 * 3
