@@ -90,6 +90,21 @@ def test_painter_kernels(oracle, guard_behind, shape, inverse):
     assert flags == 0 and np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("shape", PAINT_SHAPES + [(24, 40, 70), (40, 7, 33)])
+def test_disc_painter_kernels(oracle, guard_behind, shape, inverse):
+    """paint path 4: fronts along z, sparse-table discs in the plane (tiles of 64 x 32 with partial tiles, buckets of 32
+    columns) -- the painted r^2 is the brute force's, bit for bit"""
+    vol = shapes.random_blobs(shape, 5)
+    rg, ridge, _ = _ridge_of(oracle, vol, inverse)
+    _, want = oracle.paint(rg)
+    got, flags = emu.paint_disc(ridge)
+    assert flags == 0 and np.array_equal(got, want)
+    if shape[0] > 8:                                   # a plane range, in chunks
+        got, flags = emu.paint_disc(ridge, z_lo=3, z_hi=shape[0] - 2, chunk_planes=32)
+        assert flags == 0 and np.array_equal(got, want[3:shape[0] - 2])
+
+
 @pytest.mark.parametrize("variant", [1, 2, 3])
 def test_painter_kernels_wide_items_and_doubled_pools(oracle, guard_behind, variant):
     vol = shapes.random_blobs((12, 14, 18), 9)
