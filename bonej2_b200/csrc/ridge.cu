@@ -8,6 +8,18 @@
 // float sqrt map via (int)(v*v+0.5f)).
 #include "common.cuh"
 
+// the halo tile comes in by one TMA bulk-tensor copy when the toolchain is nvcc (device code only exists there)
+#ifndef BJT_USE_TMA
+#ifdef __CUDACC__
+#define BJT_USE_TMA 1
+#else
+#define BJT_USE_TMA 0
+#endif
+#endif
+#if BJT_USE_TMA
+#include "tma.cuh"
+#endif
+
 namespace bjt {
 
 // ---- distinct r^2 values ----------------------------------------------------------------------
@@ -111,6 +123,54 @@ int launch_ridge_template_compact(const uint32_t *values, uint32_t nvalues, uint
 constexpr int RTX = 32, RTY = 8, RTZ = 8;
 constexpr int RHX = RTX + 2, RHY = RTY + 2, RHZ = RTZ + 2;
 
+// the test itself on a staged halo tile [RHZ][RHY][PITCH] (cell (0, 0, 0) = voxel (bx - XO, by - 1, bz - 1), out-of-image cells 0)
+template <int PITCH, int XO>
+__device__ __forceinline__ void ridge_tile_test(const uint32_t *__restrict__ tile, int bx, int by, int bz, int w, int h, int d,
+                                                const uint32_t *__restrict__ t1, const uint32_t *__restrict__ t2,
+                                                const uint32_t *__restrict__ t3, uint32_t *__restrict__ ridge,
+                                                unsigned long long *__restrict__ count) {
+    const int tid = threadIdx.x + RTX * threadIdx.y;
+    const int lane = tid & 31;
+    const size_t wh = (size_t)w * h;
+    const int x = bx + threadIdx.x, y = by + threadIdx.y;
+    const int lx = threadIdx.x + XO, ly = threadIdx.y + 1;
+    unsigned nridge = 0;
+    uint32_t A0, B0, C0, A1, B1, C1, A2, B2, C2;
+    auto plane = [&](int lz, uint32_t &A, uint32_t &B, uint32_t &C) {
+        const uint32_t *p = tile + (lz * RHY + ly) * PITCH + lx;
+        A = p[0];
+        B = max(max(p[-1], p[1]), max(p[-PITCH], p[PITCH]));
+        C = max(max(p[-PITCH - 1], p[-PITCH + 1]), max(p[PITCH - 1], p[PITCH + 1]));
+    };
+    plane(0, A0, B0, C0);
+    plane(1, A1, B1, C1);
+#pragma unroll
+    for (int tz = 0; tz < RTZ; ++tz) {
+        plane(tz + 2, A2, B2, C2);
+        const int z = bz + tz;
+        if (x < w && y < h && z < d) {
+            const uint32_t v = A1;
+            bool is_ridge = false;
+            if (v > 0) {
+                const uint32_t face = max(B1, max(A0, A2)), edge = max(C1, max(B0, B2)), corner = max(C0, C2);
+                is_ridge = !(face >= __ldg(t1 + v) || edge >= __ldg(t2 + v) || corner >= __ldg(t3 + v));
+            }
+            ridge[z * wh + (size_t)y * w + x] = is_ridge ? v : 0u;
+            nridge += is_ridge ? 1u : 0u;
+        }
+        A0 = A1; B0 = B1; C0 = C1;
+        A1 = A2; B1 = B2; C1 = C2;
+    }
+    // block count of ridge points: one atomic per block (a per-warp atomic on one address serialises in L2)
+    __shared__ unsigned int block_count;
+    if (tid == 0) block_count = 0;
+    __syncthreads();
+    nridge = __reduce_add_sync(0xFFFFFFFFu, nridge);
+    if (lane == 0 && nridge) atomicAdd(&block_count, nridge);
+    __syncthreads();
+    if (tid == 0 && block_count) atomicAdd(count, (unsigned long long)block_count);
+}
+
 __global__ void __launch_bounds__(RTX *RTY, 8) ridge_kernel(const uint32_t *__restrict__ sq, int w, int h, int d,
                                                          const uint32_t *__restrict__ t1,
                                                          const uint32_t *__restrict__ t2,
@@ -151,48 +211,48 @@ __global__ void __launch_bounds__(RTX *RTY, 8) ridge_kernel(const uint32_t *__re
         }
     }
     __syncthreads();
-    const int x = bx + threadIdx.x, y = by + threadIdx.y;
-    const int lx = threadIdx.x + 1, ly = threadIdx.y + 1;
-    unsigned nridge = 0;
-    uint32_t A0, B0, C0, A1, B1, C1, A2, B2, C2;
-    auto plane = [&](int lz, uint32_t &A, uint32_t &B, uint32_t &C) {
-        A = tile[lz][ly][lx];
-        B = max(max(tile[lz][ly][lx - 1], tile[lz][ly][lx + 1]), max(tile[lz][ly - 1][lx], tile[lz][ly + 1][lx]));
-        C = max(max(tile[lz][ly - 1][lx - 1], tile[lz][ly - 1][lx + 1]), max(tile[lz][ly + 1][lx - 1], tile[lz][ly + 1][lx + 1]));
-    };
-    plane(0, A0, B0, C0);
-    plane(1, A1, B1, C1);
-#pragma unroll
-    for (int tz = 0; tz < RTZ; ++tz) {
-        plane(tz + 2, A2, B2, C2);
-        const int z = bz + tz;
-        if (x < w && y < h && z < d) {
-            const uint32_t v = A1;
-            bool is_ridge = false;
-            if (v > 0) {
-                const uint32_t face = max(B1, max(A0, A2)), edge = max(C1, max(B0, B2)), corner = max(C0, C2);
-                is_ridge = !(face >= __ldg(t1 + v) || edge >= __ldg(t2 + v) || corner >= __ldg(t3 + v));
-            }
-            ridge[z * wh + (size_t)y * w + x] = is_ridge ? v : 0u;
-            nridge += is_ridge ? 1u : 0u;
-        }
-        A0 = A1; B0 = B1; C0 = C1;
-        A1 = A2; B1 = B2; C1 = C2;
-    }
-    // block count of ridge points: one atomic per block (a per-warp atomic on one address serialises in L2)
-    __shared__ unsigned int block_count;
-    if (tid == 0) block_count = 0;
-    __syncthreads();
-    nridge = __reduce_add_sync(0xFFFFFFFFu, nridge);
-    if (lane == 0 && nridge) atomicAdd(&block_count, nridge);
-    __syncthreads();
-    if (tid == 0 && block_count) atomicAdd(count, (unsigned long long)block_count);
+    ridge_tile_test<RHX, 1>(&tile[0][0][0], bx, by, bz, w, h, d, t1, t2, t3, ridge, count);
 }
+
+#if BJT_USE_TMA
+// The same with the halo tile brought in by the TMA: the (34 x 10 x 10) neighbourhood of the block is inside one box
+// of the [d][h][w] volume at coordinates (bx - 4, by - 1, bz - 1), 40 wide: a box has to START on a 16-byte boundary
+// of its row (x = bx - 1 raises "illegal instruction": tools/study/tma_box_test.cu) and be a multiple of 16 bytes
+// wide.  Cells outside the volume arrive as zeros, which is the reference's rule for neighbours outside the image.
+// One cp.async.bulk.tensor instruction replaces the staging loop (row index arithmetic, bounds predicates, 2 loads
+// and 2 shared-memory stores per row and warp); eight blocks per SM keep eight tiles in flight.
+constexpr int RHXT = 40, RXOT = 4;
+__global__ void __launch_bounds__(RTX *RTY, 8) ridge_tma_kernel(const __grid_constant__ CUtensorMap map, int w, int h, int d,
+                                                             const uint32_t *__restrict__ t1, const uint32_t *__restrict__ t2,
+                                                             const uint32_t *__restrict__ t3, uint32_t *__restrict__ ridge,
+                                                             unsigned long long *__restrict__ count) {
+    __shared__ __align__(128) uint32_t tile[RHZ * RHY * RHXT];
+    __shared__ uint64_t bar;
+    const int bx = blockIdx.x * RTX, by = blockIdx.y * RTY, bz = blockIdx.z * RTZ;
+    const int tid = threadIdx.x + RTX * threadIdx.y;
+    if (tid == 0) {
+        tma::mbar_init(&bar, 1);
+        tma::mbar_expect_tx(&bar, (uint32_t)sizeof(tile));
+        tma::load_3d(tile, &map, bx - RXOT, by - 1, bz - 1, &bar);
+    }
+    __syncthreads();                                     // the barrier is initialised before anybody polls it
+    if (tid < 32) tma::mbar_wait(&bar, 0);               // one warp polls, the others sleep in the block barrier
+    __syncthreads();
+    ridge_tile_test<RHXT, RXOT>(tile, bx, by, bz, w, h, d, t1, t2, t3, ridge, count);
+}
+#endif
 
 int launch_ridge(const uint32_t *sq, int w, int h, int d, const uint32_t *t1, const uint32_t *t2, const uint32_t *t3,
                  uint32_t *ridge, unsigned long long *count, cudaStream_t s) {
     dim3 grid((w + RTX - 1) / RTX, (h + RTY - 1) / RTY, (d + RTZ - 1) / RTZ);
     dim3 block(RTX, RTY, 1);
+#if BJT_USE_TMA
+    CUtensorMap map;
+    if (tma::make_map_3d_u32(&map, sq, w, h, d, RHXT, RHY, RHZ)) {
+        ridge_tma_kernel<<<grid, block, 0, s>>>(map, w, h, d, t1, t2, t3, ridge, count);
+        return 1;
+    }
+#endif
     ridge_kernel<<<grid, block, 0, s>>>(sq, w, h, d, t1, t2, t3, ridge, count);
     return 1;
 }
