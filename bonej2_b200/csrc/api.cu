@@ -561,8 +561,14 @@ static int dev_finish_range(bjt_ctx *c, const uint32_t *rsq, const uint8_t *d_or
     const int np = finish_partials(w, h, z_hi - z_lo);
     WS("partials", (size_t)np * sizeof(StatsPartial), partials);
     WS("stats_result", sizeof(StatsPartial), result);
+    float *ttab;
+    {   // the 2*sqrt table lives as long as the context's workspace and is filled once
+        const bool fresh = c->bufs.find("thick_tab") == c->bufs.end();
+        WS("thick_tab", thickness_table_bytes(), ttab);
+        if (fresh) { c->launches += launch_thickness_table(ttab, c->stream); CKL(); }
+    }
     c->launches += launch_finish(rsq, d_original, w, h, d, z_lo, z_hi, inverse, calibrate, (float)pixel_width, d_out,
-                                 partials, np, result, c->stream); CKL();
+                                 partials, np, result, ttab, c->stream); CKL();
     if (stats) {
         CK(peek(c, c->h_stats, result, sizeof(StatsPartial)));
         CK(cudaStreamSynchronize(c->stream));

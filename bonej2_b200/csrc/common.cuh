@@ -127,9 +127,12 @@ int paint_sep_stage3(int w, int h, int d, int variant, void *workspace, int xs, 
 
 // 2*sqrt + cleanup + mask + NaN/calibrate + stats
 // output / statistics restricted to planes [z_lo, z_hi) of the local volume; `out` starts at plane z_lo
+// thick_tab: table of 2*sqrt(r^2) filled by launch_thickness_table (thickness_table_bytes() bytes), or null
 int launch_finish(const uint32_t *rsq, const uint8_t *original, int w, int h, int d, int z_lo, int z_hi, int inverse,
                   int calibrate, float pixel_width, float *out, StatsPartial *partials, int npartials,
-                  StatsPartial *result, cudaStream_t s);
+                  StatsPartial *result, const float *thick_tab, cudaStream_t s);
+int launch_thickness_table(float *tab, cudaStream_t s);
+size_t thickness_table_bytes();
 int finish_partials(int w, int h, int nz);
 int launch_stats(const float *map, size_t n, StatsPartial *partials, int npartials, StatsPartial *result,
                  cudaStream_t s);

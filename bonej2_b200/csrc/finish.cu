@@ -19,6 +19,18 @@
 #include "common.cuh"
 #include <math.h>
 
+// the halo tile comes in by one TMA bulk-tensor copy when the toolchain is nvcc (device code only exists there)
+#ifndef BJT_USE_TMA
+#ifdef __CUDACC__
+#define BJT_USE_TMA 1
+#else
+#define BJT_USE_TMA 0
+#endif
+#endif
+#if BJT_USE_TMA
+#include "tma.cuh"
+#endif
+
 namespace bjt {
 
 constexpr int FTX = 32, FTY = 8, FTZ = 16;
@@ -29,6 +41,17 @@ constexpr uint32_t OUTSIDE = 0xFFFFFFFFu;
 // neighbour visiting order of the cleanup average (A.4): 6 faces, 12 edges, 8 corners -- see BJT_NBR below
 
 __device__ __forceinline__ float thickness_of(uint32_t R) { return 2.0f * sqrtf((float)R); }   // == (float)(2*sqrt((double)R)), R < 2^24
+// The same through a table of the first THICK_TAB values (filled by thickness_table_kernel with thickness_of itself,
+// so the bits are identical): the correctly rounded square root is a dozen instructions, the kernels below are bound by
+// instruction issue, and the few thousand distinct r^2 of a volume keep their entries in L1.
+constexpr uint32_t THICK_TAB = 65536;
+__device__ __forceinline__ float thickness_lut(uint32_t R, const float *__restrict__ tab) {
+    return (tab && R < THICK_TAB) ? __ldg(tab + R) : thickness_of(R);
+}
+__global__ void thickness_table_kernel(float *__restrict__ tab) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < THICK_TAB) tab[i] = thickness_of(i);
+}
 
 __device__ __forceinline__ void block_reduce_stats(double sum, double sum2, double mn, double mx, long long cnt,
                                                    StatsPartial *__restrict__ out) {
@@ -56,24 +79,151 @@ __device__ __forceinline__ void block_reduce_stats(double sum, double sum2, doub
     }
 }
 
+// Shared state of a block: the tile of 2*sqrt(r^2) values (PITCH cells per row; cell (0, 0, 0) is voxel (bx - XO, by - 2,
+// bz - 2)) and, one 64-bit word per tile row (z, y) with bit j = tile column j: cell is not zero (outside the image
+// counts as not zero) / cell is interior ("inside the image" follows from the coordinates).
+template <int PITCH>
+struct FinishTile {
+    float S[HZ * HY * PITCH];
+    unsigned long long nzrow[HZ][HY], itrow[HZ][HY];
+    uint32_t keptrow[FTZ][FTY];                 // bit x: the mask keeps the voxel (or there is no mask)
+    uint16_t surf[(FTZ / 2) * FTY * FTX];       // surface voxels of half the block: tz << 8 | ty << 5 | tx
+    int nsurf[2];
+};
+
+// everything after the tile has been staged (S, nzrow, inrow filled; a block barrier follows the mask rows here)
+template <int PITCH, int XO>
+__device__ __forceinline__ void finish_tile_rest(FinishTile<PITCH> &T, const uint8_t *__restrict__ original, int bx, int by, int bz,
+                                                 int w, int h, int d, int z_lo, int z_hi, int fgval, int calibrate, float pw,
+                                                 float *__restrict__ out, StatsPartial *__restrict__ partials) {
+    const int tid = threadIdx.x + FTX * threadIdx.y;
+    const int lane = tid & 31;
+    const size_t wh = (size_t)w * h;
+    auto S = [&](int z, int y, int x) -> float & { return T.S[(z * HY + y) * PITCH + x]; };
+    // which of the block's voxels the mask keeps
+    {
+        const int x = bx + threadIdx.x, y = by + threadIdx.y;
+        uint8_t o[FTZ];
+#pragma unroll
+        for (int tz = 0; tz < FTZ; ++tz) {
+            const int z = bz + tz;
+            o[tz] = (uint8_t)fgval;
+            if (original && x < w && y < h && z < z_hi && z < d) o[tz] = __ldg(original + z * wh + (size_t)y * w + x);
+        }
+#pragma unroll
+        for (int tz = 0; tz < FTZ; ++tz) {
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, (int)o[tz] == fgval);
+            if (lane == 0) T.keptrow[tz][threadIdx.y] = m;
+        }
+    }
+    __syncthreads();
+    // interior(x) = inside && not zero && all 27 cells around it not zero: AND of the 9 neighbouring rows,
+    // each already ANDed with its two x-shifts
+    if (tid < IZ * IY) {
+        const int iz = 1 + tid / IY, iy = 1 + tid % IY;
+        unsigned long long all = ~0ull;
+#pragma unroll
+        for (int dz = -1; dz <= 1; ++dz)
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                const unsigned long long m = T.nzrow[iz + dz][iy + dy];
+                all &= m & (m >> 1) & (m << 1);
+            }
+        // cells of the row that lie inside the image: tile columns [XO - bx, w - bx + XO) of rows with y, z in range
+        const int gy = by + iy - 2, gz = bz + iz - 2;
+        const int lo = max(0, XO - bx), hi = min(64, w - bx + XO);
+        unsigned long long inside = 0ull;
+        if (gy >= 0 && gy < h && gz >= 0 && gz < d && hi > lo)
+            inside = (hi >= 64 ? ~0ull : ((1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull);
+        T.itrow[iz][iy] = all & inside;
+    }
+    __syncthreads();
+    // surface voxels the mask keeps (a voxel the mask removes needs no value: the mask is applied after the cleanup,
+    // so skipping its average changes nothing; its painted value still counts as "not zero" for its neighbours above)
+    const int x = bx + threadIdx.x, y = by + threadIdx.y;
+    const int cx = threadIdx.x + XO, cy = threadIdx.y + 2;
+    const bool col_in = x < w && y < h;
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll 4
+        for (int tz = half * (FTZ / 2); tz < (half + 1) * (FTZ / 2); ++tz) {
+            const int z = bz + tz;
+            const bool is_surf = col_in && z < z_hi && z < d && ((T.keptrow[tz][threadIdx.y] >> threadIdx.x) & 1u) &&
+                                 S(tz + 2, cy, cx) != 0.0f && !((T.itrow[tz + 2][cy] >> cx) & 1ull);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, is_surf);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&T.nsurf[half], __popc(m));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (is_surf) T.surf[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(tz << 8 | threadIdx.y << 5 | threadIdx.x);
+            }
+        }
+        __syncthreads();
+        // their values: float32 mean of the interior neighbours, faces, edges, corners in turn.  The 9 flag rows sit
+        // in registers; adding 0.0f for the other neighbours is exact.  The cell is overwritten in place.
+        const int ns = T.nsurf[half];
+        for (int i = tid; i < ns; i += FTX * FTY) {
+            const int code = T.surf[i];
+            const int sx = (code & 31) + XO, sy = ((code >> 5) & 7) + 2, sz = (code >> 8) + 2;
+            unsigned long long rows[3][3];
+#pragma unroll
+            for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) rows[dz][dy] = T.itrow[sz + dz - 1][sy + dy - 1] >> (sx - 1);
+            float s = 0.0f;
+            int n = 0;
+#define BJT_NBR(dx, dy, dz)                                                         \
+    {                                                                              \
+        const bool in_ = (rows[(dz) + 1][(dy) + 1] >> ((dx) + 1)) & 1ull;          \
+        s += in_ ? S(sz + (dz), sy + (dy), sx + (dx)) : 0.0f;                      \
+        n += in_ ? 1 : 0;                                                          \
+    }
+            BJT_NBR(0, 0, -1) BJT_NBR(0, 0, 1) BJT_NBR(0, -1, 0) BJT_NBR(0, 1, 0) BJT_NBR(-1, 0, 0) BJT_NBR(1, 0, 0)
+            BJT_NBR(0, 1, -1) BJT_NBR(0, 1, 1) BJT_NBR(1, -1, 0) BJT_NBR(1, 1, 0) BJT_NBR(-1, 0, 1) BJT_NBR(1, 0, 1)
+            BJT_NBR(0, -1, -1) BJT_NBR(0, -1, 1) BJT_NBR(-1, -1, 0) BJT_NBR(-1, 1, 0) BJT_NBR(-1, 0, -1) BJT_NBR(1, 0, -1)
+            BJT_NBR(1, 1, 1) BJT_NBR(1, -1, 1) BJT_NBR(-1, 1, 1) BJT_NBR(-1, -1, 1)
+            BJT_NBR(1, 1, -1) BJT_NBR(1, -1, -1) BJT_NBR(-1, 1, -1) BJT_NBR(-1, -1, -1)
+#undef BJT_NBR
+            if (n > 0) S(sz, sy, sx) = s / (float)n;
+        }
+        __syncthreads();
+    }
+    double sum = 0, sum2 = 0, mn = INFINITY, mx = -INFINITY;
+    long long cnt = 0;
+    if (col_in) {
+#pragma unroll 4
+        for (int tz = 0; tz < FTZ; ++tz) {
+            const int z = bz + tz;
+            if (z >= z_hi || z >= d) break;
+            float v = S(tz + 2, cy, cx);
+            if (!((T.keptrow[tz][threadIdx.y] >> threadIdx.x) & 1u)) v = 0.0f;
+            if (calibrate) {
+                if (v == 0.0f) v = __int_as_float(0x7FC00000);
+                v = v * pw;
+            }
+            if (out) out[(size_t)(z - z_lo) * wh + (size_t)y * w + x] = v;
+            if (v == v) {   // not NaN
+                const double dv = (double)v;
+                sum += dv; sum2 += dv * dv; mn = fmin(mn, dv); mx = fmax(mx, dv); ++cnt;
+            }
+        }
+    }
+    const int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    block_reduce_stats(sum, sum2, mn, mx, cnt, partials + bid);
+}
+
 // Output and statistics cover z in [z_lo, z_hi) of the local volume; `out` and nothing else is indexed
 // relative to z_lo (a sharded caller passes its slab plus halo planes and keeps the core).
 __global__ void __launch_bounds__(FTX *FTY, 4) finish_kernel(const uint32_t *__restrict__ rsq,
                                                           const uint8_t *__restrict__ original, int w, int h, int d,
                                                           int z_lo, int z_hi, int fgval, int calibrate, float pw,
-                                                          float *__restrict__ out, StatsPartial *__restrict__ partials) {
-    __shared__ float S[HZ][HY][HX];            // 2*sqrt(r^2) of every tile cell (0 for empty and outside cells)
-    // one 64-bit word per tile row (z, y): bit x set = cell is not zero (outside the image counts as not
-    // zero) / cell is inside the image / cell is interior
-    __shared__ unsigned long long nzrow[HZ][HY], inrow[HZ][HY], itrow[HZ][HY];
-    __shared__ uint32_t keptrow[FTZ][FTY];      // bit x: the mask keeps the voxel (or there is no mask)
-    __shared__ uint16_t surf[(FTZ / 2) * FTY * FTX];   // surface voxels of half the block: tz << 8 | ty << 5 | tx
-    __shared__ int nsurf[2];
+                                                          float *__restrict__ out, StatsPartial *__restrict__ partials,
+                                                          const float *__restrict__ ttab) {
+    __shared__ FinishTile<HX> T;
     const int bx = blockIdx.x * FTX, by = blockIdx.y * FTY, bz = z_lo + blockIdx.z * FTZ;
     const int tid = threadIdx.x + FTX * threadIdx.y;
     const int lane = tid & 31, warp = tid >> 5;
     const size_t wh = (size_t)w * h;
-    if (tid < 2) nsurf[tid] = 0;
+    if (tid < 2) T.nsurf[tid] = 0;
     // a warp loads whole tile rows (36 cells: lanes 0..31, then lanes 0..3) and ballots the masks; row r = warp +
     // NWARP * j of the HZ * HY rows, (lz, ly) carried along instead of divided out
     constexpr int NWARP = (FTX * FTY) / 32, RPW = (HZ * HY) / NWARP;      // 30 rows per warp
@@ -101,122 +251,65 @@ __global__ void __launch_bounds__(FTX *FTY, 4) finish_kernel(const uint32_t *__r
 #pragma unroll
         for (int k = 0; k < BATCH; ++k) {
             // outside cells: value 0, flagged "not zero"
-            S[lz][ly][lane] = thickness_of(v0[k] == OUTSIDE ? 0u : v0[k]);
-            if (lane < 4) S[lz][ly][32 + lane] = thickness_of(v1[k] == OUTSIDE ? 0u : v1[k]);
+            T.S[(lz * HY + ly) * HX + lane] = thickness_lut(v0[k] == OUTSIDE ? 0u : v0[k], ttab);
+            if (lane < 4) T.S[(lz * HY + ly) * HX + 32 + lane] = thickness_lut(v1[k] == OUTSIDE ? 0u : v1[k], ttab);
             const unsigned nz0 = __ballot_sync(0xFFFFFFFFu, v0[k] != 0u), nz1 = __ballot_sync(0xFFFFFFFFu, lane < 4 && v1[k] != 0u);
-            const unsigned i0 = __ballot_sync(0xFFFFFFFFu, v0[k] != OUTSIDE), i1 = __ballot_sync(0xFFFFFFFFu, lane < 4 && v1[k] != OUTSIDE);
-            if (lane == 0) {
-                nzrow[lz][ly] = (unsigned long long)nz0 | ((unsigned long long)nz1 << 32);
-                inrow[lz][ly] = (unsigned long long)i0 | ((unsigned long long)i1 << 32);
-            }
+            if (lane == 0) T.nzrow[lz][ly] = (unsigned long long)nz0 | ((unsigned long long)nz1 << 32);
             ly += NWARP;
             if (ly >= HY) { ly -= HY; ++lz; }
         }
     }
-    // which of the block's voxels the mask keeps
-    {
-        const int x = bx + threadIdx.x, y = by + threadIdx.y;
-        uint8_t o[FTZ];
-#pragma unroll
-        for (int tz = 0; tz < FTZ; ++tz) {
-            const int z = bz + tz;
-            o[tz] = (uint8_t)fgval;
-            if (original && x < w && y < h && z < z_hi && z < d) o[tz] = __ldg(original + z * wh + (size_t)y * w + x);
-        }
-#pragma unroll
-        for (int tz = 0; tz < FTZ; ++tz) {
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, (int)o[tz] == fgval);
-            if (lane == 0) keptrow[tz][threadIdx.y] = m;
-        }
-    }
-    __syncthreads();
-    // interior(x) = inside && not zero && all 27 cells around it not zero: AND of the 9 neighbouring rows,
-    // each already ANDed with its two x-shifts
-    if (tid < IZ * IY) {
-        const int iz = 1 + tid / IY, iy = 1 + tid % IY;
-        unsigned long long all = ~0ull;
-#pragma unroll
-        for (int dz = -1; dz <= 1; ++dz)
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy) {
-                const unsigned long long m = nzrow[iz + dz][iy + dy];
-                all &= m & (m >> 1) & (m << 1);
-            }
-        itrow[iz][iy] = all & inrow[iz][iy];
-    }
-    __syncthreads();
-    // surface voxels the mask keeps (a voxel the mask removes needs no value: the mask is applied after the cleanup,
-    // so skipping its average changes nothing; its painted value still counts as "not zero" for its neighbours above)
-    const int x = bx + threadIdx.x, y = by + threadIdx.y;
-    const int cx = threadIdx.x + 2, cy = threadIdx.y + 2;
-    const bool col_in = x < w && y < h;
-    for (int half = 0; half < 2; ++half) {
-#pragma unroll 4
-        for (int tz = half * (FTZ / 2); tz < (half + 1) * (FTZ / 2); ++tz) {
-            const int z = bz + tz;
-            const bool is_surf = col_in && z < z_hi && z < d && ((keptrow[tz][threadIdx.y] >> threadIdx.x) & 1u) &&
-                                 S[tz + 2][cy][cx] != 0.0f && !((itrow[tz + 2][cy] >> cx) & 1ull);
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, is_surf);
-            if (m) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&nsurf[half], __popc(m));
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                if (is_surf) surf[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(tz << 8 | threadIdx.y << 5 | threadIdx.x);
-            }
-        }
-        __syncthreads();
-        // their values: float32 mean of the interior neighbours, faces, edges, corners in turn.  The 9 flag rows sit
-        // in registers; adding 0.0f for the other neighbours is exact.  The cell is overwritten in place.
-        const int ns = nsurf[half];
-        for (int i = tid; i < ns; i += FTX * FTY) {
-            const int code = surf[i];
-            const int sx = (code & 31) + 2, sy = ((code >> 5) & 7) + 2, sz = (code >> 8) + 2;
-            unsigned long long rows[3][3];
-#pragma unroll
-            for (int dz = 0; dz < 3; ++dz)
-#pragma unroll
-                for (int dy = 0; dy < 3; ++dy) rows[dz][dy] = itrow[sz + dz - 1][sy + dy - 1] >> (sx - 1);
-            float s = 0.0f;
-            int n = 0;
-#define BJT_NBR(dx, dy, dz)                                                         \
-    {                                                                              \
-        const bool in_ = (rows[(dz) + 1][(dy) + 1] >> ((dx) + 1)) & 1ull;          \
-        s += in_ ? S[sz + (dz)][sy + (dy)][sx + (dx)] : 0.0f;                      \
-        n += in_ ? 1 : 0;                                                          \
-    }
-            BJT_NBR(0, 0, -1) BJT_NBR(0, 0, 1) BJT_NBR(0, -1, 0) BJT_NBR(0, 1, 0) BJT_NBR(-1, 0, 0) BJT_NBR(1, 0, 0)
-            BJT_NBR(0, 1, -1) BJT_NBR(0, 1, 1) BJT_NBR(1, -1, 0) BJT_NBR(1, 1, 0) BJT_NBR(-1, 0, 1) BJT_NBR(1, 0, 1)
-            BJT_NBR(0, -1, -1) BJT_NBR(0, -1, 1) BJT_NBR(-1, -1, 0) BJT_NBR(-1, 1, 0) BJT_NBR(-1, 0, -1) BJT_NBR(1, 0, -1)
-            BJT_NBR(1, 1, 1) BJT_NBR(1, -1, 1) BJT_NBR(-1, 1, 1) BJT_NBR(-1, -1, 1)
-            BJT_NBR(1, 1, -1) BJT_NBR(1, -1, -1) BJT_NBR(-1, 1, -1) BJT_NBR(-1, -1, -1)
-#undef BJT_NBR
-            if (n > 0) S[sz][sy][sx] = s / (float)n;
-        }
-        __syncthreads();
-    }
-    double sum = 0, sum2 = 0, mn = INFINITY, mx = -INFINITY;
-    long long cnt = 0;
-    if (col_in) {
-#pragma unroll 4
-        for (int tz = 0; tz < FTZ; ++tz) {
-            const int z = bz + tz;
-            if (z >= z_hi || z >= d) break;
-            float v = S[tz + 2][cy][cx];
-            if (!((keptrow[tz][threadIdx.y] >> threadIdx.x) & 1u)) v = 0.0f;
-            if (calibrate) {
-                if (v == 0.0f) v = __int_as_float(0x7FC00000);
-                v = v * pw;
-            }
-            if (out) out[(size_t)(z - z_lo) * wh + (size_t)y * w + x] = v;
-            if (v == v) {   // not NaN
-                const double dv = (double)v;
-                sum += dv; sum2 += dv * dv; mn = fmin(mn, dv); mx = fmax(mx, dv); ++cnt;
-            }
-        }
-    }
-    const int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    block_reduce_stats(sum, sum2, mn, mx, cnt, partials + bid);
+    finish_tile_rest<HX, 2>(T, original, bx, by, bz, w, h, d, z_lo, z_hi, fgval, calibrate, pw, out, partials);
 }
+
+#if BJT_USE_TMA
+// The same with the r^2 halo tile brought in by the TMA: one (40 x 12 x 20) box at (bx - 4, by - 2, bz - 2) -- a box
+// starts on a 16-byte boundary of its row, so the 2-voxel halo in x sits inside a 4-voxel one --, cells outside the
+// volume arriving as zeros.  A warp then turns the rows into 2*sqrt(r^2) in place (the float takes the place of the
+// integer) and ballots the flag words, with "inside the image" from the coordinates instead of a marker value.
+// No global address, bounds predicate or load instruction per cell: the staging loop was half of the kernel's
+// instructions, and the kernel is bound by instruction issue.
+constexpr int HXT = 40, FXO = 4;
+__global__ void __launch_bounds__(FTX *FTY, 4) finish_tma_kernel(const __grid_constant__ CUtensorMap map,
+                                                              const uint8_t *__restrict__ original, int w, int h, int d,
+                                                              int z_lo, int z_hi, int fgval, int calibrate, float pw,
+                                                              float *__restrict__ out, StatsPartial *__restrict__ partials,
+                                                              const float *__restrict__ ttab) {
+    __shared__ __align__(128) FinishTile<HXT> T;         // S first: the copy lands on a 128-byte boundary
+    __shared__ uint64_t bar;
+    const int bx = blockIdx.x * FTX, by = blockIdx.y * FTY, bz = z_lo + blockIdx.z * FTZ;
+    const int tid = threadIdx.x + FTX * threadIdx.y;
+    const int lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        tma::mbar_init(&bar, 1);
+        tma::mbar_expect_tx(&bar, (uint32_t)sizeof(T.S));
+        tma::load_3d(T.S, &map, bx - FXO, by - 2, bz - 2, &bar);
+    }
+    if (tid < 2) T.nsurf[tid] = 0;
+    __syncthreads();                                     // the barrier is initialised before anybody polls it
+    if (tid < 32) tma::mbar_wait(&bar, 0);               // one warp polls, the others sleep in the block barrier
+    __syncthreads();
+    constexpr int NWARP = (FTX * FTY) / 32;
+    const int gx0 = bx - FXO + lane, gx1 = gx0 + 32;
+    const bool x0_in = gx0 >= 0 && gx0 < w, x1_in = lane < HXT - 32 && gx1 < w;
+    uint32_t *raw = reinterpret_cast<uint32_t *>(T.S);
+    for (int r = warp; r < HZ * HY; r += NWARP) {
+        const int lz = r / HY, ly = r % HY;
+        const int gy = by + ly - 2, gz = bz + lz - 2;
+        const bool row_in = gy >= 0 && gy < h && gz >= 0 && gz < d;
+        const uint32_t v0 = raw[r * HXT + lane];
+        const uint32_t v1 = lane < HXT - 32 ? raw[r * HXT + 32 + lane] : 0u;
+        const bool in0 = row_in && x0_in, in1 = row_in && x1_in;
+        T.S[r * HXT + lane] = thickness_lut(v0, ttab);
+        if (lane < HXT - 32) T.S[r * HXT + 32 + lane] = thickness_lut(v1, ttab);
+        // outside cells (zeros from the copy) are flagged "not zero", as the reference's look() returns -1 there
+        const unsigned nz0 = __ballot_sync(0xFFFFFFFFu, v0 != 0u || !in0);
+        const unsigned nz1 = __ballot_sync(0xFFFFFFFFu, lane < HXT - 32 && (v1 != 0u || !in1));
+        if (lane == 0) T.nzrow[lz][ly] = (unsigned long long)nz0 | ((unsigned long long)nz1 << 32);
+    }
+    finish_tile_rest<HXT, FXO>(T, original, bx, by, bz, w, h, d, z_lo, z_hi, fgval, calibrate, pw, out, partials);
+}
+#endif
 
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(const StatsPartial *__restrict__ partials, int n,
                                                                StatsPartial *__restrict__ result) {
@@ -233,13 +326,29 @@ int finish_partials(int w, int h, int nz) {
     return ((w + FTX - 1) / FTX) * ((h + FTY - 1) / FTY) * ((nz + FTZ - 1) / FTZ);
 }
 
+int launch_thickness_table(float *tab, cudaStream_t s) {
+    thickness_table_kernel<<<THICK_TAB / 256, 256, 0, s>>>(tab);
+    return 1;
+}
+size_t thickness_table_bytes() { return (size_t)THICK_TAB * sizeof(float); }
+
 int launch_finish(const uint32_t *rsq, const uint8_t *original, int w, int h, int d, int z_lo, int z_hi, int inverse,
                   int calibrate, float pixel_width, float *out, StatsPartial *partials, int npartials,
-                  StatsPartial *result, cudaStream_t s) {
+                  StatsPartial *result, const float *thick_tab, cudaStream_t s) {
     dim3 grid((w + FTX - 1) / FTX, (h + FTY - 1) / FTY, (z_hi - z_lo + FTZ - 1) / FTZ);
     dim3 block(FTX, FTY, 1);
-    finish_kernel<<<grid, block, 0, s>>>(rsq, original, w, h, d, z_lo, z_hi, inverse ? 0 : 255, calibrate, pixel_width, out,
-                                         partials);
+    bool done = false;
+#if BJT_USE_TMA
+    CUtensorMap map;
+    if (tma::make_map_3d_u32(&map, rsq, w, h, d, HXT, HY, HZ)) {
+        cudaFuncSetAttribute(finish_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        finish_tma_kernel<<<grid, block, 0, s>>>(map, original, w, h, d, z_lo, z_hi, inverse ? 0 : 255, calibrate, pixel_width, out, partials, thick_tab);
+        done = true;
+    }
+#endif
+    if (!done)
+        finish_kernel<<<grid, block, 0, s>>>(rsq, original, w, h, d, z_lo, z_hi, inverse ? 0 : 255, calibrate, pixel_width, out,
+                                             partials, thick_tab);
     reduce_partials_kernel<<<1, 1024, 0, s>>>(partials, npartials, result);
     return 2;
 }

@@ -107,7 +107,7 @@ int emu_finish(const uint32_t *rsq, const uint8_t *original, int w, int h, int d
     memset(g_out.p, 0xAB, M * 4);
     const int launches = launch_finish(g_rsq.as<uint32_t>(), original ? g_org.as<uint8_t>() : nullptr, w, h, d, z_lo, z_hi, inverse,
                                        calibrate, pixel_width, g_out.as<float>(), g_part.as<StatsPartial>(), np,
-                                       g_res.as<StatsPartial>(), nullptr);
+                                       g_res.as<StatsPartial>(), nullptr, nullptr);
     memcpy(out, g_out.p, M * 4);
     const StatsPartial r = *g_res.as<StatsPartial>();
     res[0] = r.sum; res[1] = r.sum2; res[2] = r.mn; res[3] = r.mx; res[4] = (double)r.count;
@@ -296,7 +296,7 @@ int emu_dev_finish_range(const uint32_t *rsq, const uint8_t *original, int w, in
     const int np = finish_partials(w, h, z_hi - z_lo);
     std::vector<StatsPartial> part((size_t)np);
     StatsPartial r;
-    const int launches = launch_finish(rsq, original, w, h, d, z_lo, z_hi, inverse, calibrate, pixel_width, out, part.data(), np, &r, nullptr);
+    const int launches = launch_finish(rsq, original, w, h, d, z_lo, z_hi, inverse, calibrate, pixel_width, out, part.data(), np, &r, nullptr, nullptr);
     res[0] = r.sum; res[1] = r.sum2; res[2] = r.mn; res[3] = r.mx; res[4] = (double)r.count;
     return launches;
 }
