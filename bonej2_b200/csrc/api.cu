@@ -1424,9 +1424,8 @@ int bjt_dev_copy2d_batch(bjt_ctx *c, int n, void *const *dst, const size_t *dpit
 
 // ---- phantom ---------------------------------------------------------------------------------------
 
-int bjt_dev_phantom_u8(bjt_ctx *c, const int32_t *shapes_host, int nshapes, int w, int h, int d, int z0, int dz,
-                       uint8_t *d_out) {
-    ENTER(c);
+// rasterise slices [z0, z0 + dz) into d_out; the caller holds the context's lock
+static int dev_phantom(bjt_ctx *c, const int32_t *shapes_host, int nshapes, int w, int h, int d, int z0, int dz, uint8_t *d_out) {
     int rc = check_dims(c, w, h, d);
     if (rc) return rc;
     if (nshapes < 0 || (nshapes > 0 && !shapes_host) || !d_out || z0 < 0 || dz <= 0 || z0 + dz > d)
@@ -1439,21 +1438,21 @@ int bjt_dev_phantom_u8(bjt_ctx *c, const int32_t *shapes_host, int nshapes, int 
     return BJT_OK;
 }
 
+int bjt_dev_phantom_u8(bjt_ctx *c, const int32_t *shapes_host, int nshapes, int w, int h, int d, int z0, int dz,
+                       uint8_t *d_out) {
+    ENTER(c);
+    return dev_phantom(c, shapes_host, nshapes, w, h, d, z0, dz, d_out);
+}
+
 int bjt_phantom_u8(bjt_ctx *c, const int32_t *shapes, int nshapes, int w, int h, int d, uint8_t *out) {
-    if (!c) return fail(nullptr, BJT_E_ARG, "null context");
+    ENTER(c);                                            // one lock for the whole call: the context's input buffer is in use throughout
     if (!out) return fail(c, BJT_E_ARG, "null output");
-    uint8_t *d_in;
-    {
-        std::lock_guard<std::mutex> lk(c->mu);
-        DeviceGuard dg(c->device);
-        int rc = check_dims(c, w, h, d);
-        if (rc) return rc;
-        WS("in", (size_t)w * h * d, d_in);
-    }
-    int rc = bjt_dev_phantom_u8(c, shapes, nshapes, w, h, d, 0, d, d_in);
+    int rc = check_dims(c, w, h, d);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
-    DeviceGuard dg(c->device);
+    uint8_t *d_in;
+    WS("in", (size_t)w * h * d, d_in);
+    rc = dev_phantom(c, shapes, nshapes, w, h, d, 0, d, d_in);
+    if (rc) return rc;
     CK(cudaMemcpyAsync(out, d_in, (size_t)w * h * d, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return BJT_OK;

@@ -442,11 +442,10 @@ __global__ void __launch_bounds__(1024, 2) edt_tile_kernel(const TIn *__restrict
 // always in flight: 3.2 / 3.2 ms against 2.7 / 3.1 -- the copies, not the walk, then bound the kernel: 64-byte rows
 // are 1024 requests per tile, and with 8-column tiles (32-byte rows, room for a ring in each of two blocks) the time
 // doubles to 6.2 ms: the TMA's rate here is per row, not per byte.  L2 promotion off costs the same factor.
-template <bool WANT_MAX>
+template <bool WANT_MAX, int TX>
 __global__ void __launch_bounds__(1024, 2) edt_tile_z_tma_kernel(const __grid_constant__ CUtensorMap map, uint32_t *__restrict__ out,
                                                                int groups, int w, long long plane, int L, int BZ, uint32_t n0,
                                                                uint32_t *__restrict__ maxval) {
-    constexpr int TX = 16;
     extern __shared__ __align__(128) uint32_t sm_raw[];
     __shared__ uint64_t bar;
     const int y = blockIdx.x / groups, x0 = (blockIdx.x % groups) * TX;
@@ -508,15 +507,22 @@ int launch_edt_y(const uint16_t *gx, int w, int h, int d, uint32_t n0, uint32_t 
 
 #if BJT_USE_TMA
 // false: this shape or driver cannot take the TMA kernel
-static bool launch_edt_z_tma(const uint32_t *gy, int w, int h, int d, uint32_t n0, uint32_t *sq, uint32_t *maxval, cudaStream_t s) {
-    const size_t smem = (size_t)(d + 2 * EDT_PAD) * 16 * 4;
-    if (w % 16 != 0 || d % 64 != 0 || smem > 100 * 1024 || !maxval) return false;
+template <int TX>
+static bool launch_edt_z_tma_tx(const uint32_t *gy, int w, int h, int d, uint32_t n0, uint32_t *sq, uint32_t *maxval, cudaStream_t s) {
+    const size_t smem = (size_t)(d + 2 * EDT_PAD) * TX * 4;
+    if (w % TX != 0 || d % 64 != 0 || smem > 100 * 1024 || !maxval) return false;
     const int bz = d % 256 == 0 ? 256 : (d % 128 == 0 ? 128 : 64);         // whole boxes only: nothing may land in the pad rows
     CUtensorMap map;
-    if (!tma::make_map_3d_u32(&map, gy, w, h, d, 16, 1, bz)) return false;
-    cudaFuncSetAttribute(edt_tile_z_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    edt_tile_z_tma_kernel<true><<<(unsigned)((long long)h * (w / 16)), 1024, smem, s>>>(map, sq, w / 16, w, (long long)w * h, d, bz, n0, maxval);
+    if (!tma::make_map_3d_u32(&map, gy, w, h, d, TX, 1, bz)) return false;
+    cudaFuncSetAttribute(edt_tile_z_tma_kernel<true, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    edt_tile_z_tma_kernel<true, TX><<<(unsigned)((long long)h * (w / TX)), 1024, smem, s>>>(map, sq, w / TX, w, (long long)w * h, d, bz, n0,
+                                                                                          maxval);
     return true;
+}
+// 32 lines per tile (128-byte rows: half the row requests per byte) where the lines are short enough for two such
+// tiles per SM, else 16
+static bool launch_edt_z_tma(const uint32_t *gy, int w, int h, int d, uint32_t n0, uint32_t *sq, uint32_t *maxval, cudaStream_t s) {
+    return launch_edt_z_tma_tx<32>(gy, w, h, d, n0, sq, maxval, s) || launch_edt_z_tma_tx<16>(gy, w, h, d, n0, sq, maxval, s);
 }
 #endif
 

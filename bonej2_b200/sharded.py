@@ -93,15 +93,17 @@ class Comm:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return int(t.item())
 
-    def combine_stats(self, st: PartialStats, device) -> PartialStats:
+    def combine_stats(self, st: PartialStats, device, failed=False):
+        """(statistics over all ranks, number of ranks that report a failure)"""
         if self.size == 1:
-            return st
-        t = torch.tensor([float(st.count), st.sum, st.sum2, st.min, st.max], dtype=torch.float64, device=device)
+            return st, int(failed)
+        t = torch.tensor([float(st.count), st.sum, st.sum2, st.min, st.max, 1.0 if failed else 0.0], dtype=torch.float64,
+                         device=device)
         all_t = [torch.empty_like(t) for _ in range(self.size)]
         dist.all_gather(all_t, t, group=self.group)
         rows = [x.cpu().tolist() for x in all_t]                      # rank order: the same sum on every rank
-        return PartialStats(int(sum(r[0] for r in rows)), sum(r[1] for r in rows), sum(r[2] for r in rows),
-                            min(r[3] for r in rows), max(r[4] for r in rows))
+        return (PartialStats(int(sum(r[0] for r in rows)), sum(r[1] for r in rows), sum(r[2] for r in rows),
+                             min(r[3] for r in rows), max(r[4] for r in rows)), int(sum(r[5] for r in rows)))
 
     def barrier(self):
         if self.size > 1:
@@ -379,44 +381,58 @@ def thickness_slab(stages, comm: Comm, slab_u8, dims, inverse, mask=True, pixel_
         gmax = comm.allreduce_max_int(stages.max_value(sq), slab_u8.device)
         mark("rmax")
 
-    # planes of the painted map the cleanup of this slab reads: slab +- 2, clipped to the volume
-    s_lo, s_hi = (max(0, z0 - 2), min(d, z1 + 2)) if z1 > z0 else (z0, z0)
-    if gmax == 0:
-        rsq_sub = stages.full((s_hi - s_lo, h, w), 0)
-    elif gmax >= n0:
-        rsq_sub = stages.full((s_hi - s_lo, h, w), n0)                 # no background anywhere (sentinel)
-    else:
-        H = math.isqrt(gmax)                                           # no ball reaches further
-        # painting [s_lo, s_hi) reads the ridge of [s_lo - H, s_hi + H); the ridge of a plane needs the squared
-        # EDT one plane further out
-        needs = [((max(0, a - 2 - H - 1), min(d, b + 2 + H + 1)) if b > a else (a, a)) for (a, b) in zs]
-        e_lo, e_hi = needs[r]
-        if peer is not None:
-            sq_ext = torch.empty((e_hi - e_lo, h, w), dtype=torch.int32, device=slab_u8.device)
-            if e_hi > e_lo:
-                peer.pull_planes(comm, sq_ext, e_lo, e_hi)
+    # An error on one rank in the ridge / paint / finish stages (out of memory in the painter, a library failure) must
+    # not leave the others waiting in the next collective: it is caught, travels with the statistics, and every rank
+    # raises.  (With a PeerExchange nothing in this section waits for another rank; without one the halo exchange does,
+    # so there the guarantee covers the stages behind it.)
+    failure = None
+    try:
+        # planes of the painted map the cleanup of this slab reads: slab +- 2, clipped to the volume
+        s_lo, s_hi = (max(0, z0 - 2), min(d, z1 + 2)) if z1 > z0 else (z0, z0)
+        if gmax == 0:
+            rsq_sub = stages.full((s_hi - s_lo, h, w), 0)
+        elif gmax >= n0:
+            rsq_sub = stages.full((s_hi - s_lo, h, w), n0)                 # no background anywhere (sentinel)
         else:
-            sq_ext = gather_planes(comm, sq, zs, needs)
-        mark("halo")
-        if z1 > z0:
-            ridge_ext = stages.ridge(sq_ext)
-            # the outermost fetched planes have an incomplete neighbourhood unless they are volume faces; they lie
-            # beyond reach of [s_lo, s_hi) and must not paint
-            if e_lo > 0:
-                ridge_ext[0] = 0
-            if e_hi < d:
-                ridge_ext[-1] = 0
-            mark("ridge")
-            rsq_sub = stages.paint_range(ridge_ext, s_lo - e_lo, s_hi - e_lo, gmax)
-            del ridge_ext
-            mark("paint")
-        else:
-            rsq_sub = stages.full((0, h, w), 0)
-        del sq_ext
-    out, part = stages.finish(rsq_sub, slab_u8, z0 - s_lo, z1 - s_lo, inverse, mask, pixel_width)
-    mark("finish")
+            H = math.isqrt(gmax)                                           # no ball reaches further
+            # painting [s_lo, s_hi) reads the ridge of [s_lo - H, s_hi + H); the ridge of a plane needs the squared
+            # EDT one plane further out
+            needs = [((max(0, a - 2 - H - 1), min(d, b + 2 + H + 1)) if b > a else (a, a)) for (a, b) in zs]
+            e_lo, e_hi = needs[r]
+            if peer is not None:
+                sq_ext = torch.empty((e_hi - e_lo, h, w), dtype=torch.int32, device=slab_u8.device)
+                if e_hi > e_lo:
+                    peer.pull_planes(comm, sq_ext, e_lo, e_hi)
+            else:
+                sq_ext = gather_planes(comm, sq, zs, needs)
+            mark("halo")
+            if z1 > z0:
+                ridge_ext = stages.ridge(sq_ext)
+                # the outermost fetched planes have an incomplete neighbourhood unless they are volume faces; they lie
+                # beyond reach of [s_lo, s_hi) and must not paint
+                if e_lo > 0:
+                    ridge_ext[0] = 0
+                if e_hi < d:
+                    ridge_ext[-1] = 0
+                mark("ridge")
+                rsq_sub = stages.paint_range(ridge_ext, s_lo - e_lo, s_hi - e_lo, gmax)
+                del ridge_ext
+                mark("paint")
+            else:
+                rsq_sub = stages.full((0, h, w), 0)
+            del sq_ext
+        out, part = stages.finish(rsq_sub, slab_u8, z0 - s_lo, z1 - s_lo, inverse, mask, pixel_width)
+        mark("finish")
+    except Exception as e:                                             # noqa: BLE001 -- re-raised on every rank below
+        failure = e
+        out, part = None, PartialStats(0, 0.0, 0.0, float("inf"), float("-inf"))
     # (with a PeerExchange this collective is also what lets the next run overwrite sqt: every rank's pulls precede it)
-    stats = comm.combine_stats(part, slab_u8.device).finalize()
+    combined, nfailed = comm.combine_stats(part, slab_u8.device, failed=failure is not None)
+    if failure is not None:
+        raise failure
+    if nfailed:
+        raise RuntimeError(f"thickness_slab: {nfailed} other rank(s) failed in the ridge / paint / finish stages of this run")
+    stats = combined.finalize()
     mark("stats")
     return out, stats
 

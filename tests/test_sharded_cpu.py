@@ -125,3 +125,38 @@ def test_split_ranges():
     from bonej2_b200.sharded import split_ranges
     assert split_ranges(10, 3) == [(0, 4), (4, 7), (7, 10)]
     assert split_ranges(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+
+
+def _failing_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    from bonej2_b200 import sharded
+    from tests.sharded_cpu_backend import OracleStages
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+
+    class Stages(OracleStages):
+        def paint_range(self, ridge_ext, z_lo, z_hi, max_rsq):
+            if rank == 1:
+                raise MemoryError("no room for the painter's items on this rank")
+            return super().paint_range(ridge_ext, z_lo, z_hi, max_rsq)
+
+    from tests import shapes
+    vol = shapes.random_blobs((12, 10, 14), 3)
+    zs = sharded.split_ranges(12, world)
+    slab = torch.from_numpy(vol[zs[rank][0]:zs[rank][1]].copy())
+    try:
+        sharded.thickness_slab(Stages(), sharded.Comm(), slab, (14, 10, 12), True, True, 1.0)
+        msg = "no error"
+    except Exception as e:                                           # noqa: BLE001
+        msg = f"{type(e).__name__}: {e}"
+    with open(os.path.join(out_dir, f"err_{rank}.txt"), "w") as f:
+        f.write(msg)
+    dist.destroy_process_group()
+
+
+def test_failure_on_one_rank_is_raised_on_every_rank(tmp_path):
+    """a rank that fails in its paint stage must not leave the others waiting in the statistics collective: it raises its
+    own error, the others are told that a rank failed"""
+    mp.spawn(_failing_worker, args=(3, _free_port(), str(tmp_path)), nprocs=3, join=True)
+    errs = [open(os.path.join(tmp_path, f"err_{r}.txt")).read() for r in range(3)]
+    assert errs[1].startswith("MemoryError: no room")
+    assert errs[0].startswith("RuntimeError: thickness_slab: 1 other rank(s) failed") and errs[2] == errs[0]
