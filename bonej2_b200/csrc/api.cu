@@ -41,6 +41,7 @@ struct bjt_ctx {
     int sm_count = 0;
     // per-stage device time of the last separable paint (events around the x stage and every column block's y / z stage)
     std::vector<cudaEvent_t> pev;
+    std::vector<cudaEvent_t> sev;        // events of the streamed paint / finish / download path
     float paint_ms[3] = {0, 0, 0};
     int paint_launches[3] = {0, 0, 0};
     // stepwise painter of a z-slab (bjt_dev_paint_open .. _close)
@@ -207,6 +208,7 @@ void bjt_destroy(bjt_ctx *c) {
     DeviceGuard dg(c->device);
     for (auto &ev : c->ev) cudaEventDestroy(ev);
     for (auto &ev : c->pev) cudaEventDestroy(ev);
+    for (auto &ev : c->sev) cudaEventDestroy(ev);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -582,9 +584,92 @@ static int dev_finish(bjt_ctx *c, const uint32_t *rsq, const uint8_t *d_original
     return dev_finish_range(c, rsq, d_original, w, h, d, 0, d, inverse, calibrate, pixel_width, d_out, stats);
 }
 
+// Where a host entry point wants its map: with it, the pipeline paints and finishes the volume in chunks of planes and
+// sends every finished chunk home on the copy stream while the next chunk is painted -- the download of a 1024^3 map
+// (4 GiB over PCIe, ~75 ms) then hides behind the painter instead of following it.
+struct StreamOut {
+    float *host = nullptr;                  // contiguous map, or
+    float *const *host_slices = nullptr;    // one array per slice
+    cudaStream_t copy = nullptr;
+    cudaEvent_t first = nullptr, last = nullptr;   // recorded on the copy stream around the copies (timing)
+    bool used = false;                      // set when the map went out this way
+};
+
+// paint (fronts + discs) and finish in chunks of planes, each finished chunk copied out asynchronously.
+// *done = 0: the disc painter could not take a chunk (nothing usable in d_out; the caller runs the plain path).
+static int dev_paint_finish_streamed(bjt_ctx *c, const uint32_t *ridge, const uint8_t *d_orig, int w, int h, int d, int inverse,
+                                     double pixel_width, uint32_t maxval, uint32_t *rsq, float *d_out, StreamOut *so, bjt_stats *stats,
+                                     float *ms_paint, float *ms_finish, int *done) {
+    const size_t wh = (size_t)w * h;
+    *done = 0;
+    int zc = 0;
+    size_t wb = 0;
+    paint_disc_plan(w, h, d, 3, (size_t)6 << 30, &zc, &wb);
+    const int nchunks = (d + zc - 1) / zc;
+    while (c->sev.size() < (size_t)(2 * nchunks + 2)) { cudaEvent_t e; CK(cudaEventCreate(&e)); c->sev.push_back(e); }
+    StatsPartial tot{0.0, 0.0, 0.0, 0.0, 0};
+    bool any = false;
+    float px = 0.f, py = 0.f, pf = 0.f;
+    int nlaunch_disc = 0, finished = 0, nev = 0;
+    bool first_copy = true;
+    auto finish_to = [&](int upto) -> int {              // finish and send planes [finished, upto)
+        if (upto <= finished) return BJT_OK;
+        bjt_stats st;
+        cudaEvent_t e0 = c->sev[nev++], e1 = c->sev[nev++];
+        CK(cudaEventRecord(e0, c->stream));
+        const int rc = dev_finish_range(c, rsq, d_orig, w, h, d, finished, upto, inverse, 1, pixel_width, d_out + (size_t)finished * wh, &st);
+        if (rc) return rc;                               // (returns with the compute stream idle)
+        CK(cudaEventRecord(e1, c->stream));
+        if (st.count > 0) {
+            tot.sum += st.sum; tot.sum2 += st.sum2; tot.count += st.count;
+            tot.mn = any ? std::min(tot.mn, st.min) : st.min;
+            tot.mx = any ? std::max(tot.mx, st.max) : st.max;
+            any = true;
+        }
+        CK(cudaStreamWaitEvent(so->copy, e1, 0));
+        if (first_copy && so->first) { CK(cudaEventRecord(so->first, so->copy)); first_copy = false; }
+        if (so->host) {
+            CK(cudaMemcpyAsync(so->host + (size_t)finished * wh, d_out + (size_t)finished * wh, (size_t)(upto - finished) * wh * sizeof(float),
+                               cudaMemcpyDeviceToHost, so->copy));
+        } else {
+            for (int z = finished; z < upto; ++z)
+                CK(cudaMemcpyAsync(so->host_slices[z], d_out + (size_t)z * wh, wh * sizeof(float), cudaMemcpyDeviceToHost, so->copy));
+        }
+        float ms = 0.f;
+        CK(cudaEventSynchronize(e1));
+        cudaEventElapsedTime(&ms, e0, e1);
+        pf += ms;
+        finished = upto;
+        return BJT_OK;
+    };
+    for (int z0 = 0; z0 < d; z0 += zc) {
+        const int z1 = std::min(d, z0 + zc);
+        int ok = 0;
+        int rc = dev_paint_disc(c, ridge, w, h, d, z0, z1, maxval, rsq + (size_t)z0 * wh, &ok);
+        if (rc) return rc;
+        if (!ok) {                                       // not with this painter: let the copies already queued finish, then the plain path
+            CK(cudaStreamSynchronize(so->copy));
+            return BJT_OK;
+        }
+        px += c->paint_ms[0]; py += c->paint_ms[1]; nlaunch_disc += c->paint_launches[1];
+        // the cleanup of a plane reads two painted planes either side
+        rc = finish_to(z1 == d ? d : z1 - 2);
+        if (rc) return rc;
+    }
+    if (so->last) CK(cudaEventRecord(so->last, so->copy));
+    c->paint_ms[0] = px; c->paint_ms[1] = py; c->paint_ms[2] = 0.f;
+    c->paint_launches[0] = nlaunch_disc; c->paint_launches[1] = nlaunch_disc; c->paint_launches[2] = 0;
+    if (!any) { tot.mn = INFINITY; tot.mx = -INFINITY; }
+    stats_out(tot, stats);
+    *ms_paint = px + py; *ms_finish = pf;
+    so->used = true;
+    *done = 1;
+    return BJT_OK;
+}
+
 // the whole chain on device buffers
 static int dev_pipeline(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, int inverse, int mask, int thresh,
-                        double pixel_width, float *d_out, bjt_stats *stats, bjt_timing *tm) {
+                        double pixel_width, float *d_out, bjt_stats *stats, bjt_timing *tm, StreamOut *so = nullptr) {
     const size_t N = (size_t)w * h * d;
     const int n = w > h ? (w > d ? w : d) : (h > d ? h : d);
     const uint32_t n0 = no_result(n);
@@ -608,6 +693,8 @@ static int dev_pipeline(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, in
     int64_t n_ridge = 0;
     int path_used = 3;
     uint32_t *rsq = bufB;
+    bool streamed = false;
+    float streamed_paint_ms = 0.f, streamed_finish_ms = 0.f;
     if (maxval == 0) {
         // no foreground for this run: sq (bufB) is all zero and doubles as the painted map
         CK(cudaEventRecord(c->ev[4], c->stream));
@@ -622,12 +709,24 @@ static int dev_pipeline(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, in
         rc = dev_ridge(c, bufB, w, h, d, maxval, bufA, &n_ridge);
         if (rc) return rc;
         CK(cudaEventRecord(c->ev[4], c->stream));
-        rc = dev_paint(c, bufA, w, h, d, -1, n_ridge, (int64_t)maxval, bufB, &path_used);
-        if (rc) return rc;
+        if (so && d_out && c->paint_path < 0 && paint_disc_supports(maxval)) {
+            // paint, finish and download chunk by chunk
+            int done = 0;
+            rc = dev_paint_finish_streamed(c, bufA, mask ? d_in : nullptr, w, h, d, inverse, pixel_width, maxval, bufB, d_out, so, stats,
+                                           &streamed_paint_ms, &streamed_finish_ms, &done);
+            if (rc) return rc;
+            if (done) { streamed = true; path_used = 4; }
+        }
+        if (!streamed) {
+            rc = dev_paint(c, bufA, w, h, d, -1, n_ridge, (int64_t)maxval, bufB, &path_used);
+            if (rc) return rc;
+        }
         CK(cudaEventRecord(c->ev[5], c->stream));
     }
-    rc = dev_finish(c, rsq, mask ? d_in : nullptr, w, h, d, inverse, 1, pixel_width, d_out, stats);
-    if (rc) return rc;
+    if (!streamed) {
+        rc = dev_finish(c, rsq, mask ? d_in : nullptr, w, h, d, inverse, 1, pixel_width, d_out, stats);
+        if (rc) return rc;
+    }
     CK(cudaEventRecord(c->ev[6], c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (tm) {
@@ -637,6 +736,7 @@ static int dev_pipeline(bjt_ctx *c, const uint8_t *d_in, int w, int h, int d, in
         cudaEventElapsedTime(&tm->ms_ridge, c->ev[3], c->ev[4]);
         cudaEventElapsedTime(&tm->ms_paint, c->ev[4], c->ev[5]);
         cudaEventElapsedTime(&tm->ms_finish, c->ev[5], c->ev[6]);
+        if (streamed) { tm->ms_paint = streamed_paint_ms; tm->ms_finish = streamed_finish_ms; }   // interleaved: the sums of their pieces
         tm->ms_cleanup = tm->ms_finish;
         cudaEventElapsedTime(&tm->ms_total, c->ev[0], c->ev[6]);
         tm->n_ridge = n_ridge;
@@ -923,6 +1023,7 @@ static int host_run(bjt_ctx *c, const uint8_t *in, const uint8_t *const *in_slic
     // "Both": the download of the first map runs on the copy stream while the second run computes into
     // a second device buffer
     const bool overlap = both && out0 && c->copy_stream;
+    bool streamed_any = false;
     for (int run = 0; run < (both ? 2 : 1); ++run) {
         const int inv = both ? run : inverse;
         float *out = run == 0 ? out0 : out1;
@@ -930,9 +1031,16 @@ static int host_run(bjt_ctx *c, const uint8_t *in, const uint8_t *const *in_slic
         const bool want_map = out || (run == 0 && out_slices);
         float *d_dst = d_out;
         if (run == 1 && overlap) WS("out2", N * sizeof(float), d_dst);
+        // the map goes home chunk by chunk behind the painter where that is possible (its own copy stream), else in one
+        // piece afterwards
+        StreamOut so;
+        so.host = out; so.host_slices = (run == 0 && !out) ? out_slices : nullptr; so.copy = c->copy_stream;
+        so.first = c->ev[10 + 2 * run]; so.last = c->ev[11 + 2 * run];
+        const bool can_stream = want_map && c->copy_stream && (so.host || so.host_slices);
         rc = dev_pipeline(c, d_in, w, h, d, inv, mask, threshold, pixel_width, want_map ? d_dst : nullptr,
-                          run == 0 ? st0 : st1, tm);      // returns with the compute stream idle
+                          run == 0 ? st0 : st1, tm, can_stream ? &so : nullptr);      // returns with the compute stream idle
         if (rc) return rc;
+        if (so.used) { streamed_any = true; continue; }
         cudaStream_t cs = (run == 0 && overlap) ? c->copy_stream : c->stream;
         CK(cudaEventRecord(c->ev[10 + 2 * run], cs));
         if (out) CK(cudaMemcpyAsync(out, d_dst, N * sizeof(float), cudaMemcpyDeviceToHost, cs));
@@ -941,7 +1049,7 @@ static int host_run(bjt_ctx *c, const uint8_t *in, const uint8_t *const *in_slic
         CK(cudaEventRecord(c->ev[11 + 2 * run], cs));
         if (!(run == 0 && overlap)) CK(cudaStreamSynchronize(cs));
     }
-    if (overlap) CK(cudaStreamSynchronize(c->copy_stream));
+    if (overlap || streamed_any) CK(cudaStreamSynchronize(c->copy_stream));
     for (int run = 0; run < (both ? 2 : 1); ++run) {
         bjt_timing *tm = run == 0 ? tm0 : tm1;
         if (!tm) continue;

@@ -77,6 +77,8 @@ inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
     e->ms = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
     return cudaSuccess;
 }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->ms - a->ms); return cudaSuccess; }
 template <class T> inline cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)aligned_alloc(256, (n + 255) / 256 * 256); return *p ? cudaSuccess : 2; }
 inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
