@@ -934,8 +934,38 @@ static int multi_run(bjt_ctx *P, const uint8_t *in, const uint8_t *const *in_sli
                 // beyond reach of [s_lo, s_hi) and must not paint
                 if (e_lo > 0) CK(cudaMemsetAsync(ridge, 0, wh * 4, k->stream));
                 if (e_hi < d) CK(cudaMemsetAsync(ridge + (size_t)(de - 1) * wh, 0, wh * 4, k->stream));
-                rc2 = dev_paint_range(k, ridge, w, h, de, s_lo - e_lo, s_hi - e_lo, (int64_t)gmax, rsq);
-                if (rc2) return rc2;
+                // paint in chunks of planes, finish the chunk before (the cleanup reads two painted planes either side) and
+                // send it home on the copy stream while the next chunk is painted
+                const uint8_t *orig = mask ? d_in - (size_t)(z0 - s_lo) * wh : nullptr;
+                cudaStream_t cs = k->copy_stream ? k->copy_stream : k->stream;
+                const int quarter = (ds + 3) / 4, chunk = std::max(32, (quarter + 31) / 32 * 32);
+                StatsPartial acc{0.0, 0.0, 0.0, 0.0, 0};
+                bool any = false;
+                int fin = z0;
+                for (int c0 = s_lo; c0 < s_hi; c0 += chunk) {
+                    const int c1 = std::min(s_hi, c0 + chunk);
+                    rc2 = dev_paint_range(k, ridge, w, h, de, c0 - e_lo, c1 - e_lo, (int64_t)gmax, rsq + (size_t)(c0 - s_lo) * wh);
+                    if (rc2) return rc2;
+                    const int upto = c1 == s_hi ? z1 : std::min(z1, c1 - 2);
+                    if (upto <= fin) continue;
+                    bjt_stats st;
+                    rc2 = dev_finish_range(k, rsq, orig, w, h, ds, fin - s_lo, upto - s_lo, inv, 1, pixel_width,
+                                           want_map ? d_out + (size_t)(fin - z0) * wh : nullptr, &st);
+                    if (rc2) return rc2;                           // returns with the compute stream idle: the planes are final
+                    if (st.count > 0) {
+                        acc.sum += st.sum; acc.sum2 += st.sum2; acc.count += st.count;
+                        acc.mn = any ? std::min(acc.mn, st.min) : st.min;
+                        acc.mx = any ? std::max(acc.mx, st.max) : st.max;
+                        any = true;
+                    }
+                    if (out) CK(cudaMemcpyAsync(out + (size_t)fin * wh, d_out + (size_t)(fin - z0) * wh, (size_t)(upto - fin) * wh * 4, cudaMemcpyDeviceToHost, cs));
+                    else if (outs) for (int z = fin; z < upto; ++z)
+                        CK(cudaMemcpyAsync(outs[z], d_out + (size_t)(z - z0) * wh, wh * 4, cudaMemcpyDeviceToHost, cs));
+                    fin = upto;
+                }
+                if (!any) { acc.mn = INFINITY; acc.mx = -INFINITY; }
+                k->mg.part = acc;
+                return BJT_OK;                                     // the copies are joined after the last run
             }
             bjt_stats st;
             // the kernel indexes the original with the coordinates of rsq: shift the slab's pointer

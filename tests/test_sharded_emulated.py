@@ -100,3 +100,28 @@ def test_four_ranks_thin_slabs_product_stages(tmp_path):
     vol[1:15, 1:13, 1:31] = 255                                         # r_max = 6 > slab thickness 4
     vol[7, 6, 6] = 0
     _check(vol, False, True, str(tmp_path), world=4)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_chunked_run_with_a_sink_equals_the_plain_run(inverse):
+    """thickness_slab(..., sink=...) paints and finishes the slab in chunks of planes and hands every finished chunk to
+    the sink in order (what the bench's end-to-end loop uses to send planes home behind the painter): the map, the
+    statistics and the pieces the sink saw are those of the plain run"""
+    from bonej2_b200 import sharded
+    from tests import shapes
+    from tests.kernels_emu import EmuContext
+    vol = shapes.random_blobs((75, 9, 32), 4)                              # 75 planes: chunks of 32, 32, 11
+    d, h, w = vol.shape
+    stages = sharded.CudaStages(EmuContext(), torch.device("cpu"))
+    slab = torch.from_numpy(vol.copy())
+    plain, st0 = sharded.thickness_slab(stages, sharded.Comm(), slab, (w, h, d), inverse, True, 0.5)
+    seen, pieces = [], torch.full((d, h, w), -7.0)
+    def sink(a, b, view):
+        seen.append((a, b))
+        pieces[a:b] = view
+    out, st1 = sharded.thickness_slab(stages, sharded.Comm(), slab, (w, h, d), inverse, True, 0.5, None, None, sink)
+    assert len(seen) >= 2 and seen[0][0] == 0 and seen[-1][1] == d and all(x[1] == y[0] for x, y in zip(seen, seen[1:]))
+    for t in (out, pieces):
+        assert np.array_equal(np.nan_to_num(t.numpy(), nan=-1.0), np.nan_to_num(plain.numpy(), nan=-1.0))
+    assert st1["count"] == st0["count"] and st1["max"] == st0["max"] and st1["min"] == st0["min"]
+    assert st1["mean"] == pytest.approx(st0["mean"], rel=1e-12) and st1["sd"] == pytest.approx(st0["sd"], rel=1e-9)
