@@ -32,6 +32,9 @@ constexpr int ZF_ZB = 32;              // planes per front block = lanes of a wa
 constexpr int ZF_THREADS = 128;
 constexpr int ZF_WARPS = ZF_THREADS / 32;
 constexpr int ZF_KEY_Z_BITS = 10;      // key = R << 10 | window position
+#ifndef BJT_ZF_ALIAS
+#define BJT_ZF_ALIAS 1
+#endif
 
 constexpr int DTW = 64, DTH = 32;      // disc tile: 64 columns x 32 rows
 constexpr int DT_STRIDE = DTW + 3;     // row stride of a table level: rows of a disc land in different banks
@@ -128,12 +131,24 @@ __global__ void __launch_bounds__(ZF_THREADS) zfront_kernel(const uint32_t *__re
                                                              unsigned long long pool_cap, unsigned long long *cursor,
                                                              uint32_t *flags) {
     extern __shared__ uint32_t zf_smem[];
-    const int ZW = ZF_ZB + 2 * emax, ZWP = ZW | 1;
+    const int ZW = ZF_ZB + 2 * emax;
     int P = 32;
     while (P < ZW) P <<= 1;
+#if BJT_ZF_ALIAS
+    // one array for both: a column's candidates are compacted in place (entry n + rank <= the position it was read
+    // from, all reads of a group of 32 precede its writes), so the window and the sorted keys share a row of P + 1
+    // words (odd: the transposed staging stores of a warp land in 32 banks).  Half the shared memory of separate
+    // arrays: the kernel's occupancy is bounded by it (6 blocks of 4 warps per SM before).
+    const int ZWP = P + 1, KP = P + 1;
+    uint32_t *lines = zf_smem;                              // [32][P + 1] column x of the block: window, then sorted candidates
+    uint32_t *skeys = lines;
+    int *ncand = (int *)(lines + 32 * KP);                  // [32]
+#else
+    const int ZWP = ZW | 1, KP = P;
     uint32_t *lines = zf_smem;                              // [32][ZWP]   column x of the block, window position
     uint32_t *skeys = lines + 32 * ZWP;                     // [32][P]     sorted candidates of every column
     int *ncand = (int *)(skeys + 32 * P);                   // [32]
+#endif
     uint32_t *cntz = (uint32_t *)(ncand + 32);              // [ZF_ZB] items of the plane's bucket
     uint32_t *mez = cntz + ZF_ZB;                           // [ZF_ZB] largest slack + 1
     uint32_t *exz = mez + ZF_ZB;                            // [ZF_ZB] exclusive prefix of cntz
@@ -163,7 +178,7 @@ __global__ void __launch_bounds__(ZF_THREADS) zfront_kernel(const uint32_t *__re
     // per column: candidates sorted by tag (descending), then the front of every plane counted (lane = plane)
     const int zwin = emax + lane;
     for (int line = warp; line < 32; line += ZF_WARPS) {
-        uint32_t *mys = skeys + line * P;
+        uint32_t *mys = skeys + line * KP;
         int n = 0;
         for (int base = 0; base < ZW; base += 32) {
             const int zi = base + lane;
@@ -239,7 +254,7 @@ __global__ void __launch_bounds__(ZF_THREADS) zfront_kernel(const uint32_t *__re
     if (lane < nz) {
         for (int line = warp; line < 32; line += ZF_WARPS) {
             int best;
-            front_walk<true>(skeys + line * P, ncand[line], zwin, line, pool + base + exz[lane] + pc[lane * 32 + line], &best);
+            front_walk<true>(skeys + line * KP, ncand[line], zwin, line, pool + base + exz[lane] + pc[lane * 32 + line], &best);
         }
     }
 }
@@ -425,10 +440,15 @@ __global__ void isqrt_small_check_kernel(uint32_t *mismatches) {
 }
 
 size_t zfront_smem_bytes(int emax) {
-    const int ZW = ZF_ZB + 2 * emax, ZWP = ZW | 1;
+    const int ZW = ZF_ZB + 2 * emax;
     int P = 32;
     while (P < ZW) P <<= 1;
-    return (size_t)(32 * ZWP + 32 * P + 32 + 3 * ZF_ZB) * 4 + 8 + (size_t)ZF_ZB * 32 * 2 + 16;
+#if BJT_ZF_ALIAS
+    const size_t rows = (size_t)32 * (P + 1);
+#else
+    const size_t rows = (size_t)32 * (ZW | 1) + (size_t)32 * P;
+#endif
+    return (rows + 32 + 3 * ZF_ZB) * 4 + 8 + (size_t)ZF_ZB * 32 * 2 + 16;
 }
 constexpr size_t DISC_SMEM = (size_t)(DT_LEVELS * DTH * DT_STRIDE + DTH) * 4 + (size_t)DISC_BL * 12 +
                              (size_t)DISC_WARPS * DISC_NCLS * DISC_QCAP * 16 + 16;
