@@ -481,6 +481,29 @@ __device__ __forceinline__ void edt_publish_max(uint32_t tmax, uint32_t *__restr
     if ((threadIdx.x & 31) == 0 && tmax) atomicMax(maxval, tmax);
 }
 
+// staging of a tile of TX adjacent lines as u32: LOADS_IN_FLIGHT independent loads per thread before the first is used
+// -- with one load per trip a thread waits a full memory latency for every 2-4 bytes (the profile of that form showed
+// 37 % of the kernel's samples on the store to shared memory waiting for its load).  Pad rows: BIG (beyond the line).
+template <typename TIn, int TX>
+__device__ __forceinline__ void edt_stage_tile(const TIn *__restrict__ in, long long base, long long stride, int L, uint32_t n0,
+                                               uint32_t *sm) {
+    constexpr int RPW = 32 / TX;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int xx = lane % TX, rsub = lane / TX;
+    const int rstep = nwarps * RPW;
+    const long long pstep = (long long)rstep * stride;
+    const TIn *p = in + base + (long long)(warp * RPW + rsub) * stride + xx;
+    uint32_t *q = sm + (warp * RPW + rsub) * TX + xx;
+    for (int t0 = warp * RPW + rsub; t0 < L; t0 += LOADS_IN_FLIGHT * rstep, p += LOADS_IN_FLIGHT * pstep, q += LOADS_IN_FLIGHT * rstep * TX) {
+        TIn v[LOADS_IN_FLIGHT];
+#pragma unroll
+        for (int u = 0; u < LOADS_IN_FLIGHT; ++u) v[u] = t0 + u * rstep < L ? __ldg(p + u * pstep) : TIn(0);
+#pragma unroll
+        for (int u = 0; u < LOADS_IN_FLIGHT; ++u)
+            if (t0 + u * rstep < L) q[u * rstep * TX] = f_of(v[u], n0);
+    }
+}
+
 template <typename TIn, int TX, bool WANT_MAX>
 __global__ void __launch_bounds__(1024, 2) edt_tile_kernel(const TIn *__restrict__ in, uint32_t *__restrict__ out, int groups,
                                                          long long outer, long long stride, int L, uint32_t n0,
@@ -493,26 +516,173 @@ __global__ void __launch_bounds__(1024, 2) edt_tile_kernel(const TIn *__restrict
     const uint32_t BIG = 0x3FFFFFFFu;
     uint32_t *sm = sm_raw + EDT_PAD * TX;                // sm[t * TX + xx], t in [-EDT_PAD, L + EDT_PAD)
     for (int i = threadIdx.x; i < EDT_PAD * TX; i += blockDim.x) { sm[-EDT_PAD * TX + i] = BIG; sm[L * TX + i] = BIG; }
-    // staging: LOADS_IN_FLIGHT independent loads per thread before the first is used -- with one load per trip a
-    // thread waits a full memory latency for every 2-4 bytes (the profile of that form showed 37 % of the kernel's
-    // samples on the store to shared memory waiting for its load)
-    {
-        const int rstep = nwarps * RPW;
-        const long long pstep = (long long)rstep * stride;
-        const TIn *p = in + base + (long long)(warp * RPW + rsub) * stride + xx;
-        uint32_t *q = sm + (warp * RPW + rsub) * TX + xx;
-        for (int t0 = warp * RPW + rsub; t0 < L; t0 += LOADS_IN_FLIGHT * rstep, p += LOADS_IN_FLIGHT * pstep, q += LOADS_IN_FLIGHT * rstep * TX) {
-            TIn v[LOADS_IN_FLIGHT];
-#pragma unroll
-            for (int u = 0; u < LOADS_IN_FLIGHT; ++u) v[u] = t0 + u * rstep < L ? __ldg(p + u * pstep) : TIn(0);
-#pragma unroll
-            for (int u = 0; u < LOADS_IN_FLIGHT; ++u)
-                if (t0 + u * rstep < L) q[u * rstep * TX] = f_of(v[u], n0);
-        }
-    }
+    edt_stage_tile<TIn, TX>(in, base, stride, L, n0, sm);
     __syncthreads();
     const uint32_t tmax = edt_tile_walk<TX, WANT_MAX>(sm, out, base, stride, L, n0);
     if (WANT_MAX) edt_publish_max(tmax, maxval);
+}
+
+// ---- two columns per lane, 16 bits each (DPX) -----------------------------------------------------------
+// The walk above is bound by the ALU pipe (one add-then-min per candidate and position, half rate) and the
+// shared-memory loads.  Distances on real data are far below 256 voxels, so the squared values that can win fit 16
+// bits: this kernel keeps the tile as pairs of 16-bit values (two adjacent columns per 32-bit word, values clamped
+// to EDT16_CLAMP, pad rows = the clamp), a lane owns one word-column and K consecutive line positions, and every
+// VIADDMNMX.U16x2 (__viaddmin_u16x2) serves two (candidate, position) pairs; a row read from shared memory serves
+// 2 K.  A clamped candidate can only win where the result itself is >= the clamp, and the walk only ends where
+// d^2 has reached the running minimum, so a walk that ends within the pad rows is exact.  Where one does not (a
+// voxel more than ~90 line positions from every feature, or a line without features) the block redoes its tile
+// with the 32-bit walk, 16 columns at a time in the same shared memory.
+constexpr int EDT16_PAD = 96;
+constexpr uint32_t EDT16_CLAMP = 55000u;                 // + (EDT16_PAD)^2 stays below 2^16
+constexpr uint32_t EDT16_CLAMP2 = EDT16_CLAMP | (EDT16_CLAMP << 16);
+
+#ifndef BJT_EDT16_K
+#define BJT_EDT16_K 3                                    // odd: the two half-warps of a step then read different banks
+#endif
+
+__device__ __forceinline__ uint32_t edt16_pack(uint32_t a, uint32_t b) { return min(a, EDT16_CLAMP) | (min(b, EDT16_CLAMP) << 16); }
+// y pass: two in-row distances (u16, GX_INF = none: 0xFFFF^2 still fits 32 bits and clamps)
+__device__ __forceinline__ uint32_t edt16_load_pair(const uint16_t *p) {
+    const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(p));
+    const uint32_t a = v & 0xFFFFu, b = v >> 16;
+    return edt16_pack(a * a, b * b);
+}
+// z pass: two squared distances
+__device__ __forceinline__ uint32_t edt16_load_pair(const uint32_t *p) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+    return edt16_pack(v.x, v.y);
+}
+
+// TW words (2 TW columns) per tile row: sm[t * TW + xw], t in [-EDT16_PAD, L + EDT16_PAD).  *sat: some walk of this warp did not end inside the pad rows.
+template <bool WANT_MAX, int K, int TW>
+__device__ __forceinline__ uint32_t edt16_walk(const uint32_t *sm, uint32_t *__restrict__ out, long long base, long long stride, int L,
+                                               uint32_t n0, bool *sat) {
+    static_assert(K >= 3 && (K & 1), "K: odd (bank parity of the half-warps) and at least 3 (D[4] is carried)");
+    constexpr int GPW = 32 / TW;                         // groups of K positions per warp step
+    constexpr int FAST = EDT16_PAD - (K - 1);
+    constexpr uint32_t ONE2 = 0x00010001u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int xw = lane & (TW - 1), gsub = lane / TW;
+    uint32_t tmax = 0;
+    for (int r0 = warp * GPW * K; r0 < L; r0 += nwarps * GPW * K) {
+        const int t0 = r0 + gsub * K;
+        const int tc = t0 < L ? t0 : 0;                  // a group beyond the line walks nothing and writes nothing
+        const uint32_t *pc = sm + tc * TW + xw;
+        uint32_t f[K], m[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) f[k] = pc[k * TW];   // rows at or beyond L are pad rows (the clamp)
+#pragma unroll
+        for (int k = 0; k < K; ++k) {                    // the positions of the group are candidates of one another
+            m[k] = f[k];
+#pragma unroll
+            for (int q = 0; q < K; ++q)
+                if (q != k) m[k] = __viaddmin_u16x2(f[q], (uint32_t)((k - q) * (k - q)) * ONE2, m[k]);
+            if (t0 + k >= L) m[k] = 0u;
+        }
+        int j = 1;
+        uint32_t D0 = ONE2, e = 2u * ONE2;               // j^2 and 2 j in both halves, carried from ring to ring
+        const uint32_t *lo = pc - TW, *hi = pc + K * TW;
+        for (;; j += 4, e += 8u * ONE2, lo -= 4 * TW, hi += 4 * TW) {
+            uint32_t mx = m[0];
+#pragma unroll
+            for (int k = 1; k < K; ++k) mx = __vmaxu2(mx, m[k]);
+            // some half of some position still above j^2?  (positions in the middle of the group have seen candidates
+            // one or two further out; testing them against j^2 too costs nothing: the walk advances four rings a time)
+            if (!__any_sync(0xFFFFFFFFu, __vmaxu2(mx, D0) != D0)) break;
+            if (j + 3 > FAST) { *sat = true; break; }
+            uint32_t D[K + 3];                           // D[i] = (j + i)^2 = D[i - 1] + 2 j + (2 i - 1)
+            D[0] = D0;
+#pragma unroll
+            for (int i = 1; i < K + 3; ++i) D[i] = D[i - 1] + e + (uint32_t)(2 * i - 1) * ONE2;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t a = lo[-u * TW], b = hi[u * TW];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    m[k] = __viaddmin_u16x2(a, D[u + k], m[k]);
+                    m[k] = __viaddmin_u16x2(b, D[u + K - 1 - k], m[k]);
+                }
+            }
+            D0 = D[4];
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (t0 + k < L) {
+                uint2 res;
+                res.x = min(m[k] & 0xFFFFu, n0);
+                res.y = min(m[k] >> 16, n0);
+                *reinterpret_cast<uint2 *>(out + base + (long long)(t0 + k) * stride + 2 * xw) = res;
+                if (WANT_MAX) tmax = max(tmax, max(res.x, res.y));
+            }
+        }
+    }
+    return tmax;
+}
+
+template <typename TIn, bool WANT_MAX, int K, int TW>
+__global__ void __launch_bounds__(1024, 2) edt_tile16_kernel(const TIn *__restrict__ in, uint32_t *__restrict__ out, int groups,
+                                                           long long outer, long long stride, int L, uint32_t n0,
+                                                           uint32_t *__restrict__ maxval) {
+    extern __shared__ uint32_t sm_raw[];                 // [EDT16_PAD + L + EDT16_PAD][TW] pairs; the redo: [EDT_PAD + L + EDT_PAD][16] u32
+    __shared__ int s_sat;
+    constexpr int GPW = 32 / TW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const long long base = (long long)(blockIdx.x / groups) * outer + (long long)(blockIdx.x % groups) * (2 * TW);
+    uint32_t *sm = sm_raw + EDT16_PAD * TW;
+    if (threadIdx.x == 0) s_sat = 0;
+    for (int i = threadIdx.x; i < EDT16_PAD * TW; i += blockDim.x) { sm[-EDT16_PAD * TW + i] = EDT16_CLAMP2; sm[L * TW + i] = EDT16_CLAMP2; }
+    {
+        const int xw = lane & (TW - 1), rsub = lane / TW;
+        const int rstep = nwarps * GPW;
+        const long long pstep = (long long)rstep * stride;
+        const TIn *p = in + base + (long long)(warp * GPW + rsub) * stride + 2 * xw;
+        uint32_t *q = sm + (warp * GPW + rsub) * TW + xw;
+        for (int t0 = warp * GPW + rsub; t0 < L; t0 += LOADS_IN_FLIGHT * rstep, p += LOADS_IN_FLIGHT * pstep, q += LOADS_IN_FLIGHT * rstep * TW) {
+            uint32_t v[LOADS_IN_FLIGHT];
+#pragma unroll
+            for (int u = 0; u < LOADS_IN_FLIGHT; ++u) v[u] = t0 + u * rstep < L ? edt16_load_pair(p + u * pstep) : 0u;
+#pragma unroll
+            for (int u = 0; u < LOADS_IN_FLIGHT; ++u)
+                if (t0 + u * rstep < L) q[u * rstep * TW] = v[u];
+        }
+    }
+    __syncthreads();
+    bool sat = false;
+    uint32_t tmax = edt16_walk<WANT_MAX, K, TW>(sm, out, base, stride, L, n0, &sat);
+    if (sat) s_sat = 1;
+    __syncthreads();
+    if (s_sat) {                                         // rare: the whole tile again, exact in 32 bits, 16 columns at a time
+        tmax = 0;
+        uint32_t *sm32 = sm_raw + EDT_PAD * 16;
+        for (int half = 0; half < TW / 8; ++half) {
+            for (int i = threadIdx.x; i < EDT_PAD * 16; i += blockDim.x) { sm32[-EDT_PAD * 16 + i] = 0x3FFFFFFFu; sm32[L * 16 + i] = 0x3FFFFFFFu; }
+            edt_stage_tile<TIn, 16>(in, base + half * 16, stride, L, n0, sm32);
+            __syncthreads();
+            tmax = max(tmax, edt_tile_walk<16, WANT_MAX>(sm32, out, base + half * 16, stride, L, n0));
+            __syncthreads();
+        }
+    }
+    if (WANT_MAX) edt_publish_max(tmax, maxval);
+}
+
+// false: the shape does not fit (lines too long for two tiles per SM, width not a multiple of the tile's)
+template <typename TIn, bool WANT_MAX, int TW>
+static bool launch_edt_tile16_tw(const TIn *in, uint32_t *out, int w, long long nouter, long long outer, long long stride, int L,
+                                 uint32_t n0, uint32_t *maxval, cudaStream_t s) {
+    const size_t smem = std::max((size_t)(L + 2 * EDT16_PAD) * TW * 4, (size_t)(L + 2 * EDT_PAD) * 16 * 4);   // pairs; the redo's u32 tile
+    if (w % (2 * TW) != 0 || smem > 100 * 1024 || (uintptr_t)in % 8 != 0 || (uintptr_t)out % 8 != 0) return false;
+    const int groups = w / (2 * TW);
+    cudaFuncSetAttribute(edt_tile16_kernel<TIn, WANT_MAX, BJT_EDT16_K, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    edt_tile16_kernel<TIn, WANT_MAX, BJT_EDT16_K, TW><<<(unsigned)(nouter * groups), 1024, smem, s>>>(in, out, groups, outer, stride, L, n0,
+                                                                                                  maxval);
+    return true;
+}
+// 32 columns per tile (64- / 128-byte row pieces), 16 where the lines are too long for two such tiles per SM
+template <typename TIn, bool WANT_MAX>
+static bool launch_edt_tile16(const TIn *in, uint32_t *out, int w, long long nouter, long long outer, long long stride, int L,
+                              uint32_t n0, uint32_t *maxval, cudaStream_t s) {
+    return launch_edt_tile16_tw<TIn, WANT_MAX, 16>(in, out, w, nouter, outer, stride, L, n0, maxval, s) ||
+           launch_edt_tile16_tw<TIn, WANT_MAX, 8>(in, out, w, nouter, outer, stride, L, n0, maxval, s);
 }
 
 #if BJT_USE_TMA
@@ -575,7 +745,12 @@ static bool launch_edt_tile(const TIn *in, uint32_t *out, int w, long long noute
     return true;
 }
 
+#ifndef BJT_EDT16
+#define BJT_EDT16 3             // bit 0: y pass, bit 1: z pass through the 16-bit pair kernel
+#endif
+
 int launch_edt_y(const uint16_t *gx, int w, int h, int d, uint32_t n0, uint32_t *gy, cudaStream_t s) {
+    if ((BJT_EDT16 & 1) && launch_edt_tile16<uint16_t, false>(gx, gy, w, d, (long long)w * h, (long long)w, h, n0, nullptr, s)) return 1;
     if (launch_edt_tile<uint16_t, false>(gx, gy, w, d, (long long)w * h, (long long)w, h, n0, nullptr, s)) return 1;
     if (w % 4 == 0 && (uintptr_t)gx % 8 == 0 && (uintptr_t)gy % 16 == 0) {
         const long long ng = (long long)(w / 4) * d;
@@ -613,6 +788,8 @@ static bool launch_edt_z_tma(const uint32_t *gy, int w, int h, int d, uint32_t n
 
 int launch_edt_z(const uint32_t *gy, int w, int h, int d, uint32_t n0, uint32_t *sq, uint8_t *present,
                  uint32_t *maxval, cudaStream_t s) {
+    if ((BJT_EDT16 & 2) && !present && maxval &&
+        launch_edt_tile16<uint32_t, true>(gy, sq, w, h, (long long)w, (long long)w * h, d, n0, maxval, s)) return 1;
 #if BJT_USE_TMA
     if (!present && launch_edt_z_tma(gy, w, h, d, n0, sq, maxval, s)) return 1;
 #endif

@@ -29,7 +29,10 @@ namespace bjt {
 namespace disc_detail {
 
 constexpr int ZF_ZB = 32;              // planes per front block = lanes of a warp
-constexpr int ZF_THREADS = 128;
+#ifndef BJT_ZF_THREADS
+#define BJT_ZF_THREADS 128
+#endif
+constexpr int ZF_THREADS = BJT_ZF_THREADS;
 constexpr int ZF_WARPS = ZF_THREADS / 32;
 constexpr int ZF_KEY_Z_BITS = 10;      // key = R << 10 | window position
 #ifndef BJT_ZF_ALIAS

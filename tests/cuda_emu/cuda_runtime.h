@@ -335,6 +335,16 @@ inline unsigned __vcmpltu4(unsigned a, unsigned b) {         // per byte: 0xff w
     for (int i = 0; i < 4; ++i) if (((a >> (8 * i)) & 0xffu) < ((b >> (8 * i)) & 0xffu)) r |= 0xffu << (8 * i);
     return r;
 }
+// per 16-bit half (DPX): max(a, b); min(a + b, c) with the sum wrapping in 16 bits, as the hardware does
+inline unsigned __vmaxu2(unsigned a, unsigned b) {
+    const unsigned lo = (a & 0xffffu) > (b & 0xffffu) ? (a & 0xffffu) : (b & 0xffffu), hi = (a >> 16) > (b >> 16) ? (a >> 16) : (b >> 16);
+    return lo | (hi << 16);
+}
+inline unsigned __viaddmin_u16x2(unsigned a, unsigned b, unsigned c) {
+    const unsigned slo = ((a & 0xffffu) + (b & 0xffffu)) & 0xffffu, shi = ((a >> 16) + (b >> 16)) & 0xffffu;
+    const unsigned lo = slo < (c & 0xffffu) ? slo : (c & 0xffffu), hi = shi < (c >> 16) ? shi : (c >> 16);
+    return lo | (hi << 16);
+}
 inline size_t __cvta_generic_to_global(const void *p) { return (size_t)p; }
 // "shared window" addresses: 32-bit offsets from an anchor inside this library; the function-local statics that
 // stand in for __shared__ arrays lie within 2 GB of it, so the offset survives the round trip through 32 bits

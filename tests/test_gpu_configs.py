@@ -138,6 +138,27 @@ def test_squared_edt_bit_exact_at_bench_sizes(ctx, oracle, n, inverse):
         ctx.release_workspace()
 
 
+@pytest.mark.parametrize("shape", [(2048, 32, 64), (32, 2048, 64), (300, 700, 96), (64, 64, 1344)])
+def test_squared_edt_pair_kernel_long_lines_and_redo(ctx, oracle, shape):
+    """edt_tile16_kernel off the beaten track: lines of 2048 (16-column tiles, the shape of the 2048^3 slabs), widths
+    that are multiples of 16 or 32 only, and -- on a volume with a handful of background voxels -- walks that leave the
+    pad rows everywhere and squared distances far above the 16-bit clamp (the in-kernel 32-bit redo), next to a dense
+    volume on which nothing saturates"""
+    rng = np.random.default_rng(5)
+    dense = (rng.random(shape) < 0.7).astype(np.uint8) * 255
+    sparse = np.full(shape, 255, np.uint8)
+    idx = tuple(rng.integers(0, s, 3) for s in shape)
+    sparse[idx] = 0
+    half = sparse.copy()                                              # one half dense, the other nearly empty: both paths in one launch
+    half[:, :, : shape[2] // 2] = dense[:, :, : shape[2] // 2]
+    for vol in (dense, sparse, half):
+        for inverse in (False, True):
+            got = ctx.edt_sq(vol, inverse=inverse)
+            want = oracle.edt_exact_sq(vol, inverse=inverse)
+            assert np.array_equal(got, want), (shape, inverse)
+    assert oracle.edt_exact_sq(sparse).max() > 55000
+
+
 def test_1024_disc_painter_equals_sweep_painter_on_the_device(ctx):
     """BASELINE.json configs[2], background run (the large balls): the default painter (path 4, fronts along z + discs
     in the plane) against the separable sweeps (path 0, a different algorithm, oracle-checked on small volumes), bit

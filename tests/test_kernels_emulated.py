@@ -56,6 +56,32 @@ def test_edt_kernels_far_from_the_background(oracle, guard, shape):
     assert np.array_equal(got, want) and mx == int(want.max())
 
 
+@pytest.mark.parametrize("shape", [(1, 1500, 32), (3, 40, 48), (2, 37, 96)])
+def test_edt_pair_kernel_tile_widths(oracle, guard_behind, shape):
+    """the 16-bit pair kernel (edt_tile16_kernel): 16 columns per tile where the lines are too long for 32 (1500) or the
+    width is a multiple of 16 only (48), groups of three positions that run past the end of a line (37, 40)"""
+    for inverse in (False, True):
+        vol = shapes.random_blobs(shape, 11)
+        _, want = oracle.edt(vol, inverse=inverse)
+        got, mx = emu.edt_sq(vol, inverse=inverse)
+        assert np.array_equal(got, want) and mx == int(want.max())
+
+
+def test_edt_pair_kernel_redoes_only_what_saturates(oracle, guard_behind):
+    """tiles of short walks beside tiles whose walks leave the pad rows (the block redoes the tile in 32 bits), values
+    above the 16-bit clamp (55000) included; and a tile in which only a few columns saturate"""
+    vol = np.full((1, 40, 288), 255, np.uint8)
+    vol[0, ::3, :2] = 0                                                  # background in the first two columns only
+    _, want = oracle.edt(vol)                                            # x distance up to 286: y walks beyond column ~96 run through the pad
+    got, mx = emu.edt_sq(vol)
+    assert want.max() > 55000 and np.array_equal(got, want) and mx == int(want.max())
+    vol = np.full((30, 1, 128), 255, np.uint8)                           # the same along z
+    vol[::2, 0, :1] = 0
+    _, want = oracle.edt(vol)
+    got, mx = emu.edt_sq(vol)
+    assert want.max() > 96 * 96 and np.array_equal(got, want) and mx == int(want.max())
+
+
 def test_edt_kernels_no_background_and_no_foreground(oracle, guard):
     full = np.full((4, 6, 32), 255, np.uint8)
     got, mx = emu.edt_sq(full)
