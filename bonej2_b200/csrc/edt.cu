@@ -509,9 +509,6 @@ __global__ void __launch_bounds__(1024, 2) edt_tile_kernel(const TIn *__restrict
                                                          long long outer, long long stride, int L, uint32_t n0,
                                                          uint32_t *__restrict__ maxval) {
     extern __shared__ uint32_t sm_raw[];                 // [EDT_PAD + L + EDT_PAD][TX]: the pad rows hold BIG (beyond the line)
-    constexpr int RPW = 32 / TX;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int xx = lane % TX, rsub = lane / TX;
     const long long base = (long long)(blockIdx.x / groups) * outer + (long long)(blockIdx.x % groups) * TX;
     const uint32_t BIG = 0x3FFFFFFFu;
     uint32_t *sm = sm_raw + EDT_PAD * TX;                // sm[t * TX + xx], t in [-EDT_PAD, L + EDT_PAD)
@@ -530,10 +527,21 @@ __global__ void __launch_bounds__(1024, 2) edt_tile_kernel(const TIn *__restrict
 // VIADDMNMX.U16x2 (__viaddmin_u16x2) serves two (candidate, position) pairs; a row read from shared memory serves
 // 2 K.  A clamped candidate can only win where the result itself is >= the clamp, and the walk only ends where
 // d^2 has reached the running minimum, so a walk that ends within the pad rows is exact.  Where one does not (a
-// voxel more than ~90 line positions from every feature, or a line without features) the block redoes its tile
+// voxel more than ~60 line positions from every feature, or a line without features) the block redoes its tile
 // with the 32-bit walk, 16 columns at a time in the same shared memory.
-constexpr int EDT16_PAD = 96;
+// Pad rows and block shape, measured at 1024^3 (profiles/r02_stage_edt_pair_kernel_variants.log): 64 pad rows and
+// three blocks of 512 threads per SM (73.7 KB each) -- three tiles in flight per SM hide the strided staging loads of
+// the z pass better than two blocks of 1024 with 96 pad rows (y 1.70 / 2.22 -> 1.51 / 2.08 ms, z 2.27 -> 2.08 ms).
+#ifndef BJT_EDT16_PAD
+#define BJT_EDT16_PAD 64
+#endif
+#ifndef BJT_EDT16_THREADS
+#define BJT_EDT16_THREADS 512
+#define BJT_EDT16_BLOCKS 3
+#endif
+constexpr int EDT16_PAD = BJT_EDT16_PAD;
 constexpr uint32_t EDT16_CLAMP = 55000u;                 // + (EDT16_PAD)^2 stays below 2^16
+static_assert(EDT16_CLAMP + (uint32_t)(EDT16_PAD + 3) * (EDT16_PAD + 3) < 65536u, "16-bit sums must not wrap");
 constexpr uint32_t EDT16_CLAMP2 = EDT16_CLAMP | (EDT16_CLAMP << 16);
 
 #ifndef BJT_EDT16_K
@@ -620,7 +628,7 @@ __device__ __forceinline__ uint32_t edt16_walk(const uint32_t *sm, uint32_t *__r
 }
 
 template <typename TIn, bool WANT_MAX, int K, int TW>
-__global__ void __launch_bounds__(1024, 2) edt_tile16_kernel(const TIn *__restrict__ in, uint32_t *__restrict__ out, int groups,
+__global__ void __launch_bounds__(BJT_EDT16_THREADS, BJT_EDT16_BLOCKS) edt_tile16_kernel(const TIn *__restrict__ in, uint32_t *__restrict__ out, int groups,
                                                            long long outer, long long stride, int L, uint32_t n0,
                                                            uint32_t *__restrict__ maxval) {
     extern __shared__ uint32_t sm_raw[];                 // [EDT16_PAD + L + EDT16_PAD][TW] pairs; the redo: [EDT_PAD + L + EDT_PAD][16] u32
@@ -670,10 +678,10 @@ template <typename TIn, bool WANT_MAX, int TW>
 static bool launch_edt_tile16_tw(const TIn *in, uint32_t *out, int w, long long nouter, long long outer, long long stride, int L,
                                  uint32_t n0, uint32_t *maxval, cudaStream_t s) {
     const size_t smem = std::max((size_t)(L + 2 * EDT16_PAD) * TW * 4, (size_t)(L + 2 * EDT_PAD) * 16 * 4);   // pairs; the redo's u32 tile
-    if (w % (2 * TW) != 0 || smem > 100 * 1024 || (uintptr_t)in % 8 != 0 || (uintptr_t)out % 8 != 0) return false;
+    if (w % (2 * TW) != 0 || smem > (size_t)(227 * 1024 / BJT_EDT16_BLOCKS - 1024) || (uintptr_t)in % 8 != 0 || (uintptr_t)out % 8 != 0) return false;
     const int groups = w / (2 * TW);
     cudaFuncSetAttribute(edt_tile16_kernel<TIn, WANT_MAX, BJT_EDT16_K, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    edt_tile16_kernel<TIn, WANT_MAX, BJT_EDT16_K, TW><<<(unsigned)(nouter * groups), 1024, smem, s>>>(in, out, groups, outer, stride, L, n0,
+    edt_tile16_kernel<TIn, WANT_MAX, BJT_EDT16_K, TW><<<(unsigned)(nouter * groups), BJT_EDT16_THREADS, smem, s>>>(in, out, groups, outer, stride, L, n0,
                                                                                                   maxval);
     return true;
 }
