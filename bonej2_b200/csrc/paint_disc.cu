@@ -24,6 +24,10 @@
 // plane (the north star's max-radius halo exchange), discs are plane-local.
 #include "common.cuh"
 
+#ifndef BJT_ZF_STAGE_UNROLL
+#define BJT_ZF_STAGE_UNROLL 4          // loads in flight per warp while the ridge window is staged
+#endif
+
 namespace bjt {
 
 namespace disc_detail {
@@ -34,9 +38,16 @@ constexpr int ZF_ZB = 32;              // planes per front block = lanes of a wa
 #endif
 constexpr int ZF_THREADS = BJT_ZF_THREADS;
 constexpr int ZF_WARPS = ZF_THREADS / 32;
+constexpr int ZF_STAGE_UNROLL = BJT_ZF_STAGE_UNROLL;
 constexpr int ZF_KEY_Z_BITS = 10;      // key = R << 10 | window position
 #ifndef BJT_ZF_ALIAS
 #define BJT_ZF_ALIAS 1
+#endif
+#ifndef BJT_DISC_PREFETCH
+#define BJT_DISC_PREFETCH 1            // 1: the next 32 items of a bucket are loaded before the current 32 are painted
+#endif
+#ifndef BJT_DISC_LPT
+#define BJT_DISC_LPT 1
 #endif
 
 constexpr int DTW = 64, DTH = 32;      // disc tile: 64 columns x 32 rows
@@ -169,7 +180,7 @@ __global__ void __launch_bounds__(ZF_THREADS) zfront_kernel(const uint32_t *__re
 
     if (threadIdx.x < ZF_ZB) mez[threadIdx.x] = 0u;
     // stage the window: planes z0 - emax .. z0 + ZF_ZB - 1 + emax of 32 columns, transposed to [column][plane]
-#pragma unroll 4
+#pragma unroll ZF_STAGE_UNROLL
     for (int zi = warp; zi < ZW; zi += ZF_WARPS) {
         const int gz = z0 - emax + zi;
         uint32_t v = 0u;
@@ -347,7 +358,7 @@ __global__ void __launch_bounds__(DISC_THREADS, 2) disc_kernel(const unsigned lo
     const int ndesc = (yb - ya + 1) * nb;
     const unsigned long long *dplane = desc + (size_t)zl * h * nxt;
     for (int d0 = 0; d0 < ndesc; d0 += DISC_BL) {
-        if (threadIdx.x == 0) { ctl[0] = 0; ctl[1] = 0; }
+        if (threadIdx.x == 0) { ctl[0] = 0; ctl[1] = 0; ctl[2] = 0; }
         __syncthreads();
         for (int i = d0 + threadIdx.x; i < min(ndesc, d0 + DISC_BL); i += DISC_THREADS) {
             const int yy = ya + i / nb, bx = ba + i % nb;
@@ -358,32 +369,60 @@ __global__ void __launch_bounds__(DISC_THREADS, 2) disc_kernel(const unsigned lo
                 const int bx0 = bx * 32, bx1 = bx0 + 31;
                 const int dx = bx1 < x0 ? x0 - bx1 : (bx0 > x1 ? bx0 - x1 : 0);
                 if (dx * dx + dy * dy < (me + 1) * (me + 1)) {
+#if BJT_DISC_LPT
+                    // buckets with more than a warp of items are listed from the front, the others from the back: the
+                    // warps take the long ones first and the round ends on short ones
+                    const bool heavy = ((dsc >> 36) & 0xFFFFu) > 32u;
+                    const int pos = heavy ? atomicAdd(ctl, 1) : DISC_BL - 1 - atomicAdd(ctl + 2, 1);
+#else
                     const int pos = atomicAdd(ctl, 1);
+#endif
                     bl_desc[pos] = dsc;
                     bl_aux[pos] = (uint32_t)yy | ((uint32_t)bx << 16);
                 }
             }
         }
         __syncthreads();
+#if BJT_DISC_LPT
+        const int nheavy = ctl[0], nlist = ctl[0] + ctl[2];
+#define BJT_DISC_SLOT(i) ((i) < nheavy ? (i) : DISC_BL - 1 - ((i) - nheavy))
+#else
         const int nlist = ctl[0];
+#define BJT_DISC_SLOT(i) (i)
+#endif
+        // Measured (1024^3 background run, profiles/r02_stage_painter_variants.log): taking the long buckets first saves
+        // 1.9 .. 3.6 ms of 84.8, loading the next 32 items of a bucket before the current 32 are painted 1.9 more.
+        // Claiming the NEXT BUCKET ahead and loading its first items early (10 % of the kernel's stall samples sat on
+        // the first use of an item) costs 3.3 ms instead: a warp that sits on a claimed bucket while it paints
+        // lengthens the tail of the round.  Dropping discs that lie inside a disc a few lanes away (same row, larger
+        // tag): +8.6 ms for a window of 2 lanes either side -- every bucket is examined by ~9 tiles, and such a window
+        // finds only 5 % of the disc rows (tools/study/lane_prune_study.py; 29 % with the whole bucket as window).
         while (true) {
             int bi = 0;
             if (lane == 0) bi = atomicAdd(ctl + 1, 1);
             bi = __shfl_sync(0xFFFFFFFFu, bi, 0);
             if (bi >= nlist) break;
-            const unsigned long long bd = bl_desc[bi];
-            const uint32_t aux = bl_aux[bi];
+            const unsigned long long bd = bl_desc[BJT_DISC_SLOT(bi)];
+            const uint32_t aux = bl_aux[BJT_DISC_SLOT(bi)];
             const int byy = (int)(aux & 0xFFFFu), bxx = (int)(aux >> 16) * 32;
             const unsigned long long off = bd & ((1ull << 36) - 1ull);
             const int cnt = (int)((bd >> 36) & 0xFFFFu);
             const int dyl = byy < y0 ? y0 - byy : (byy > y1 ? byy - y1 : 0);
             const int yyr = byy - y0;
+#if BJT_DISC_PREFETCH
+            unsigned long long it = lane < cnt ? __ldg(pool + off + lane) : 0ull;
+#endif
             for (int b0 = 0; b0 < cnt; b0 += 32) {
+#if BJT_DISC_PREFETCH
+                unsigned long long itn = 0ull;                  // the next 32 items of the bucket, before these are painted
+                if (b0 + 32 + lane < cnt) itn = __ldg(pool + off + b0 + 32 + lane);
+#else
+                const unsigned long long it = b0 + lane < cnt ? __ldg(pool + off + b0 + lane) : 0ull;
+#endif
                 // lane = item: does its disc touch the tile, and over how many values of |dy|
                 int cls = -1;
                 uint4 rec = make_uint4(0u, 0u, 0u, 0u);
                 if (b0 + lane < cnt) {
-                    const unsigned long long it = __ldg(pool + off + b0 + lane);
                     const uint32_t rho = (uint32_t)(it & 0xFFFFFFFu), R = (uint32_t)((it >> 28) & 0xFFFFFFFu);
                     const int xcr = bxx + (int)(it >> 56) - x0;
                     const int dxl = xcr < 0 ? -xcr : (xcr > W - 1 ? xcr - (W - 1) : 0);
@@ -399,6 +438,9 @@ __global__ void __launch_bounds__(DISC_THREADS, 2) disc_kernel(const unsigned lo
                 enqueue<1>(T, T6, myq, qn1, cls, rec, lane, W, H);
                 enqueue<2>(T, T6, myq, qn2, cls, rec, lane, W, H);
                 enqueue<3>(T, T6, myq, qn3, cls, rec, lane, W, H);
+#if BJT_DISC_PREFETCH
+                it = itn;
+#endif
             }
         }
         __syncthreads();                                    // the list is rewritten by the next round

@@ -11,7 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     env BJT_BENCH_SHORT_WARMUP=1 python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/${R}_bench_ncu.log 2>&1
 python tools/one_run.py 512 1 1 > gpurun_out/${R}_one_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on \
-    -k regex:"disc_kernel|zfront_kernel|edt_tile|edt_x_kernel|finish_kernel|ridge_tma_kernel|ridge_kernel" -c 12 \
+    -k regex:"disc_kernel|zfront_kernel|edt_tile|edt_x_kernel|finish_tma_kernel|finish_kernel|ridge_tma_kernel|ridge_kernel" -c 14 \
     -o gpurun_out/${R}_full_512sp python tools/one_run.py 512 1 1 > gpurun_out/${R}_full.log 2>&1
 for INV in 0 1; do
   python tools/one_run.py 1024 $INV 1 > gpurun_out/${R}_traffic_plain_$INV.log 2>&1 &&
