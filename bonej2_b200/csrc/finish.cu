@@ -290,22 +290,33 @@ __global__ void __launch_bounds__(FTX *FTY, 4) finish_tma_kernel(const __grid_co
     if (tid < 32) tma::mbar_wait(&bar, 0);               // one warp polls, the others sleep in the block barrier
     __syncthreads();
     constexpr int NWARP = (FTX * FTY) / 32;
-    const int gx0 = bx - FXO + lane, gx1 = gx0 + 32;
-    const bool x0_in = gx0 >= 0 && gx0 < w, x1_in = lane < HXT - 32 && gx1 < w;
     uint32_t *raw = reinterpret_cast<uint32_t *>(T.S);
-    for (int r = warp; r < HZ * HY; r += NWARP) {
-        const int lz = r / HY, ly = r % HY;
+    uint32_t *nzw = reinterpret_cast<uint32_t *>(&T.nzrow[0][0]);      // row r = lz * HY + ly: low word nzw[2 r], high word nzw[2 r + 1]
+    // The 40 cells of a tile row are 32 + 8.  The 8 beyond column 32 are taken four rows per warp step (with a row per
+    // step they kept 8 of 32 lanes busy through a second table lookup, store and ballot: 11 % of the kernel's
+    // instructions); their flags are the upper word of the row's 64-bit mask.
+    for (int i = tid; i < HZ * HY * (HXT - 32); i += FTX * FTY) {      // whole warps: 8 cells x 4 rows per warp
+        const int r = i >> 3, j = i & 7;
+        const int lz = r / HY, ly = r - lz * HY;
         const int gy = by + ly - 2, gz = bz + lz - 2;
-        const bool row_in = gy >= 0 && gy < h && gz >= 0 && gz < d;
-        const uint32_t v0 = raw[r * HXT + lane];
-        const uint32_t v1 = lane < HXT - 32 ? raw[r * HXT + 32 + lane] : 0u;
-        const bool in0 = row_in && x0_in, in1 = row_in && x1_in;
-        T.S[r * HXT + lane] = thickness_lut(v0, ttab);
-        if (lane < HXT - 32) T.S[r * HXT + 32 + lane] = thickness_lut(v1, ttab);
+        const bool in1 = gy >= 0 && gy < h && gz >= 0 && gz < d && bx - FXO + 32 + j < w;
+        const uint32_t v1 = raw[r * HXT + 32 + j];
+        T.S[r * HXT + 32 + j] = thickness_lut(v1, ttab);
         // outside cells (zeros from the copy) are flagged "not zero", as the reference's look() returns -1 there
+        const unsigned b = __ballot_sync(0xFFFFFFFFu, v1 != 0u || !in1);
+        if (j == 0) nzw[2 * r + 1] = (b >> (lane & 24)) & 0xFFu;
+    }
+    const int gx0 = bx - FXO + lane;
+    const bool x0_in = gx0 >= 0 && gx0 < w;
+    for (int r = warp, lz = 0, ly = warp; r < HZ * HY; r += NWARP) {   // NWARP <= HY: (lz, ly) advance without a division
+        const int gy = by + ly - 2, gz = bz + lz - 2;
+        const bool in0 = x0_in && gy >= 0 && gy < h && gz >= 0 && gz < d;
+        const uint32_t v0 = raw[r * HXT + lane];
+        T.S[r * HXT + lane] = thickness_lut(v0, ttab);
         const unsigned nz0 = __ballot_sync(0xFFFFFFFFu, v0 != 0u || !in0);
-        const unsigned nz1 = __ballot_sync(0xFFFFFFFFu, lane < HXT - 32 && (v1 != 0u || !in1));
-        if (lane == 0) T.nzrow[lz][ly] = (unsigned long long)nz0 | ((unsigned long long)nz1 << 32);
+        if (lane == 0) nzw[2 * r] = nz0;
+        ly += NWARP;
+        if (ly >= HY) { ly -= HY; ++lz; }
     }
     finish_tile_rest<HXT, FXO>(T, original, bx, by, bz, w, h, d, z_lo, z_hi, fgval, calibrate, pw, out, partials);
 }
