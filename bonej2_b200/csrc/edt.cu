@@ -347,94 +347,11 @@ constexpr int LOADS_IN_FLIGHT = 8;
 constexpr int EDT_PAD = 64;     // sentinel rows on either side of the staged lines: walks up to this distance need no clamping
 
 // the walk over a staged tile: sm[t * TX + xx], t in [-EDT_PAD, L + EDT_PAD), pad rows = BIG
-#ifndef BJT_EDT_K
-#define BJT_EDT_K 1             // line positions per lane in the walk; K > 1 measured slower (ALU-pipe bound)
-#endif
-
-// The walk with K consecutive line positions t0 .. t0+K-1 per lane.  A candidate row read from shared memory serves
-// all K positions (at K different distances), and every (candidate, position) pair is one add-then-min
-// (VIADDMNMX): ring j reads the rows t0 - j and t0 + K-1 + j, which lie j + k and j + K-1-k away from position k.
-// Per 8 rows read that is 8 LDS + 8 K pair instructions + the squares and the vote, against 22 instructions for 8
-// pairs with one position per lane.  Position k has seen every candidate closer than j + min(k, K-1-k) when ring j
-// starts: the walk ends when that distance squared has reached the running minimum of every position of every lane.
-template <int TX, bool WANT_MAX, int K>
-__device__ __forceinline__ uint32_t edt_tile_walk_k(const uint32_t *sm, uint32_t *__restrict__ out, long long base, long long stride,
-                                                    int L, uint32_t n0) {
-    constexpr int GPW = 32 / TX;                         // groups of K positions per warp step
-    constexpr int FAST = EDT_PAD - (K - 1);              // rings up to here stay inside the pad rows without clamping
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int xx = lane % TX, gsub = lane / TX;
-    uint32_t tmax = 0;
-    for (int r0 = warp * GPW * K; r0 < L; r0 += nwarps * GPW * K) {
-        const int t0 = r0 + gsub * K;
-        const int tc = t0 < L ? t0 : 0;                  // a group beyond the line walks nothing and writes nothing
-        const uint32_t *pc = sm + tc * TX + xx;
-        uint32_t f[K], m[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) f[k] = t0 + k < L ? pc[k * TX] : 0u;
-        // the positions of the group are candidates of one another
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            m[k] = f[k];
-#pragma unroll
-            for (int q = 0; q < K; ++q)
-                if (q != k && (t0 + k < L)) m[k] = min(m[k], (t0 + q < L ? f[q] : 0x3FFFFFFFu) + (uint32_t)((k - q) * (k - q)));
-            if (t0 >= L) m[k] = 0u;
-        }
-        int j = 1;
-        uint32_t D0 = 1u, e = 2u;                        // j^2 and 2 j, carried from ring to ring
-        const uint32_t *lo = pc - TX, *hi = pc + K * TX;
-        for (; j + 3 <= FAST; j += 4, e += 8u, lo -= 4 * TX, hi += 4 * TX) {
-            // D[i] = (j + i)^2 = D[i - 1] + 2 j + (2 i - 1), i = 0 .. K + 2: one three-input add each
-            uint32_t D[K + 3];
-            D[0] = D0;
-#pragma unroll
-            for (int i = 1; i < K + 3; ++i) D[i] = D[i - 1] + e + (uint32_t)(2 * i - 1);
-            bool more = false;
-#pragma unroll
-            for (int k = 0; k < K; ++k) more |= D[k < K - 1 - k ? k : K - 1 - k] < m[k];
-            if (!__any_sync(0xFFFFFFFFu, more)) break;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t a = lo[-u * TX], b = hi[u * TX];
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    m[k] = min(m[k], a + D[u + k]);
-                    m[k] = min(m[k], b + D[u + K - 1 - k]);
-                }
-            }
-            D0 = D[4];
-        }
-        if (j + 3 > FAST) {                              // long walks: rows beyond the pad clamp onto its outermost rows
-            for (;; ++j) {
-                uint32_t D[K];
-#pragma unroll
-                for (int i = 0; i < K; ++i) D[i] = (uint32_t)((j + i) * (j + i));
-                bool more = false;
-#pragma unroll
-                for (int k = 0; k < K; ++k) more |= D[k < K - 1 - k ? k : K - 1 - k] < m[k];
-                if (!__any_sync(0xFFFFFFFFu, more)) break;
-                const uint32_t a = sm[max(tc - j, -1) * TX + xx], b = sm[min(tc + K - 1 + j, L) * TX + xx];
-#pragma unroll
-                for (int k = 0; k < K; ++k) m[k] = min(m[k], min(a + D[k], b + D[K - 1 - k]));
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            if (t0 + k < L) {
-                const uint32_t res = m[k] < n0 ? m[k] : n0;
-                out[base + (long long)(t0 + k) * stride + xx] = res;
-                if (WANT_MAX) tmax = max(tmax, res);
-            }
-        }
-    }
-    return tmax;
-}
-
+// (K line positions per lane in this 32-bit form -- a candidate row serving K positions -- measured slower: the loads fall
+// by K but not the add-then-min per pair, and the ALU pipe becomes the limit: profiles/r02_stage_edt_walk_variants.log.)
 template <int TX, bool WANT_MAX>
 __device__ __forceinline__ uint32_t edt_tile_walk(const uint32_t *sm, uint32_t *__restrict__ out, long long base, long long stride, int L,
                                                   uint32_t n0) {
-    if (BJT_EDT_K > 1) return edt_tile_walk_k<TX, WANT_MAX, BJT_EDT_K>(sm, out, base, stride, L, n0);
     constexpr int RPW = 32 / TX;                         // line positions per warp step
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int xx = lane % TX, rsub = lane / TX;

@@ -106,7 +106,26 @@ def translate(name):
 # -fno-gnu-unique / -Bsymbolic: the two emulated libraries define the same symbols (kernels, the emulation's inline
 # statics); each must bind to its own copies when both are loaded into one test process
 
+class _BuildLock:
+    """one builder at a time (pytest-xdist workers all find the library stale after a source change); the others wait
+    and then find it fresh"""
+
+    def __enter__(self):
+        import fcntl
+        os.makedirs(_OUTDIR, exist_ok=True)
+        self.f = open(os.path.join(_OUTDIR, ".build.lock"), "w")
+        fcntl.flock(self.f, fcntl.LOCK_EX)
+
+    def __exit__(self, *a):
+        self.f.close()
+
+
 def build(force=False):
+    with _BuildLock():
+        return _build(force)
+
+
+def _build(force):
     stale = (not os.path.exists(OUT)) or any(os.path.getmtime(p) > os.path.getmtime(OUT) for p in _DEPS)
     if not (force or stale):
         return OUT
@@ -119,7 +138,8 @@ def build(force=False):
         objs.append(cpp)
     cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w", "-fno-gnu-unique", "-Wl,-Bsymbolic", "-I", _HERE, "-I", _CSRC, "-I", os.path.join(_ROOT, "include"),
            "-o", OUT] + objs + [os.path.join(_HERE, "harness.cpp")]
-    subprocess.check_call(cmd)
+    subprocess.check_call(cmd[:cmd.index("-o") + 1] + [OUT + ".tmp"] + cmd[cmd.index("-o") + 2:])
+    os.replace(OUT + ".tmp", OUT)
     return OUT
 
 
@@ -131,6 +151,11 @@ API_SOURCES = ["api.cu", "edt.cu", "ridge.cu", "paint_sep.cu", "paint_disc.cu", 
 def build_api(force=False):
     """the whole C-ABI (include/bonej_thickness.h, api.cu + thickness_wrapper.cpp) on the emulation, for tests that
     drive the library's entry points without a GPU"""
+    with _BuildLock():
+        return _build_api(force)
+
+
+def _build_api(force):
     deps = [os.path.join(_CSRC, f) for f in API_SOURCES + ["common.cuh", "paint_sep_core.cuh", "thickness_wrapper.cpp"]] + \
            [os.path.join(_HERE, f) for f in ("cuda_runtime.h", "api_stubs.cpp", "emu_build.py")] + \
            [os.path.join(_ROOT, "include", f) for f in ("bonej_thickness.h", "thickness_wrapper.hpp")]
@@ -146,7 +171,8 @@ def build_api(force=False):
         srcs.append(cpp)
     cmd = ["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w", "-fno-gnu-unique", "-Wl,-Bsymbolic", "-I", _HERE, "-I", _CSRC, "-I", os.path.join(_ROOT, "include"),
            "-o", API_OUT] + srcs + [os.path.join(_CSRC, "thickness_wrapper.cpp"), os.path.join(_HERE, "api_stubs.cpp"), "-lpthread"]
-    subprocess.check_call(cmd)
+    subprocess.check_call(cmd[:cmd.index("-o") + 1] + [API_OUT + ".tmp"] + cmd[cmd.index("-o") + 2:])
+    os.replace(API_OUT + ".tmp", API_OUT)
     return API_OUT
 
 
