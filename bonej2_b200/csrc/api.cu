@@ -605,7 +605,7 @@ static int dev_paint_finish_streamed(bjt_ctx *c, const uint32_t *ridge, const ui
     int zc = 0;
     size_t wb = 0;
     paint_disc_plan(w, h, d, 3, (size_t)6 << 30, &zc, &wb);
-    const int nchunks = (d + zc - 1) / zc;
+    const int nchunks = (d + zc - 1) / zc + 8;           // + the halved chunks at the end
     while (c->sev.size() < (size_t)(2 * nchunks + 2)) { cudaEvent_t e; CK(cudaEventCreate(&e)); c->sev.push_back(e); }
     StatsPartial tot{0.0, 0.0, 0.0, 0.0, 0};
     bool any = false;
@@ -642,8 +642,13 @@ static int dev_paint_finish_streamed(bjt_ctx *c, const uint32_t *ridge, const ui
         finished = upto;
         return BJT_OK;
     };
-    for (int z0 = 0; z0 < d; z0 += zc) {
-        const int z1 = std::min(d, z0 + zc);
+    // Chunks of zc planes, halving towards the end (.., zc, zc/2, .., 32, 32): what is left when the last chunk has been
+    // painted is its finish pass and its download, and the download of a full chunk (0.5 GiB at 1024^3) is 10 ms.
+    for (int z0 = 0, z1; z0 < d; z0 = z1) {
+        const int left = d - z0;
+        int step = zc;
+        if (left < 2 * zc) step = std::max(32, (left / 2 + 31) / 32 * 32);
+        z1 = std::min(d, z0 + std::min(step, zc));
         int ok = 0;
         int rc = dev_paint_disc(c, ridge, w, h, d, z0, z1, maxval, rsq + (size_t)z0 * wh, &ok);
         if (rc) return rc;
