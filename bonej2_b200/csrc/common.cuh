@@ -54,6 +54,25 @@ __device__ __forceinline__ int isqrt_small(uint32_t v) {
 #endif
 }
 
+// A shared-memory cell by its address in the shared window, and a max-reduction on it.  Through generic pointers every
+// atomicMax of the disc painter recomputed the window base (S2UR / UMOV / ULEA + LEA) and sat in its own branch region;
+// with the 32-bit address kept in a register it is one address add and one RED (callers that want the reduction off
+// for a lane hand in the address of a scratch word instead: a select, where ptxas makes a predicated RED a branch).
+#ifdef __CUDACC__
+typedef uint32_t smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void smem_red_max(smem_addr_t a, uint32_t v) {
+    asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+#else   // a host compiler reading this header (the CPU emulation of the kernels): plain pointers
+typedef uintptr_t smem_addr_t;
+inline smem_addr_t smem_addr(const void *p) { return (uintptr_t)p; }
+inline void smem_red_max(smem_addr_t a, uint32_t v) {
+    uint32_t *q = (uint32_t *)a;
+    if (*q < v) *q = v;
+}
+#endif
+
 __device__ __forceinline__ uint32_t isqrt_ceil(uint32_t v) {
     uint32_t r = isqrt_floor(v);
     return r * r < v ? r + 1u : r;

@@ -122,6 +122,8 @@ __device__ __forceinline__ int front_walk(const uint32_t *__restrict__ keys, int
                                           unsigned long long *__restrict__ out, int *best_out) {
     int best = -1, cnt = 0;
     uint32_t lastR = 0u;
+    unsigned long long *o = out - 1;                                // EMIT: the slot of the last item written
+    const unsigned long long xhi = (unsigned long long)xl << 56;
 #pragma unroll 4
     for (int c = 0; c < n; ++c) {
         const uint32_t key = keys[c];                               // the same address in every lane
@@ -130,8 +132,8 @@ __device__ __forceinline__ int front_walk(const uint32_t *__restrict__ keys, int
         const int s = (int)R - dz * dz;
         if (s > best) {
             best = s;
-            if (R != lastR) { ++cnt; lastR = R; }                   // same tag, more slack: replaces the previous item
-            if (EMIT) out[cnt - 1] = make_item((uint32_t)s, R, xl);
+            if (R != lastR) { ++cnt; ++o; lastR = R; }              // same tag, more slack: replaces the previous item
+            if (EMIT) *o = (unsigned long long)(uint32_t)s | ((unsigned long long)R << 28) | xhi;      // make_item(s, R, xl)
         }
     }
     *best_out = best;
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(ZF_THREADS) zfront_kernel(const uint32_t *__re
 // of an entry takes |dy| = dlo + sub (+ G, ... in the last class) and paints the rows yc + dy and yc - dy that lie
 // inside the tile.  Entry: rho, R, xc | yc << 16 (signed, relative to the tile), dlo | n << 16.
 template <int CLS>
-__device__ __forceinline__ void drain_pass(uint32_t *T, uint32_t *T6, const uint4 *q, int first, int nent, int lane, int W, int H) {
+__device__ __forceinline__ void drain_pass(smem_addr_t Tsh, smem_addr_t T6sh, const uint4 *q, int first, int nent, int lane, int W, int H) {
     constexpr int G = 4 << CLS;
     const int ent = lane >> (2 + CLS), sub = lane & (G - 1);
     if (ent >= nent) return;
@@ -292,28 +294,32 @@ __device__ __forceinline__ void drain_pass(uint32_t *T, uint32_t *T6, const uint
         const int dy = dlo + q1;
         const int a = isqrt_small(rho - (uint32_t)(dy * dy));
         const int lo = max(0, xcr - a), hi = min(W - 1, xcr + a);
-        if (lo <= hi) {
-            const int r1 = yyr + dy, r2 = yyr - dy;
-            const bool in1 = (unsigned)r1 < (unsigned)H, in2 = dy != 0 && (unsigned)r2 < (unsigned)H;
-            const int len = hi - lo + 1;
-            const int k = 31 - __clz(len);
-            if (k >= DT_LEVELS) {
-                if (in1) atomicMax(T6 + r1, R);
-                if (in2) atomicMax(T6 + r2, R);
-            } else {
-                uint32_t *L = T + k * (DTH * DT_STRIDE) + lo;
-                const int o2 = len - (1 << k);                      // second entry: hi + 1 - 2^k, relative to lo
-                if (in1) { uint32_t *p = L + r1 * DT_STRIDE; atomicMax(p, R); if (o2) atomicMax(p + o2, R); }
-                if (in2) { uint32_t *p = L + r2 * DT_STRIDE; atomicMax(p, R); if (o2) atomicMax(p + o2, R); }
-            }
-        }
+        const int len = hi - lo + 1;                                // <= 0: the rows miss the tile's columns
+        const int r1 = yyr + dy, r2 = yyr - dy;
+        const bool in1 = len > 0 && (unsigned)r1 < (unsigned)H, in2 = len > 0 && dy != 0 && (unsigned)r2 < (unsigned)H;
+        const int k = 31 - __clz(len | 1);
+        // no branches: level >= DT_LEVELS is the whole-row table (one entry per row, no second entry); a reduction
+        // that is off for this lane goes to the lane's scratch word instead
+        const bool whole = k >= DT_LEVELS;
+        const int o2 = whole ? 0 : len - (1 << k);                  // second entry: hi + 1 - 2^k, relative to lo
+        const smem_addr_t b = whole ? T6sh : Tsh + (smem_addr_t)((k * (DTH * DT_STRIDE) + lo) * 4);
+        const int rs = whole ? 4 : DT_STRIDE * 4;
+        const smem_addr_t a1 = b + (smem_addr_t)(r1 * rs), a2 = b + (smem_addr_t)(r2 * rs);
+        // scratch: 64 words behind the whole-row table (lane + o2 <= 62).  Where there is no second entry (o2 == 0) the
+        // second reduction repeats the first: max is idempotent, and a select and a compare are saved
+        const smem_addr_t off = T6sh + (smem_addr_t)((DTH + lane) * 4);
+        const smem_addr_t t1 = in1 ? a1 : off, t2 = in2 ? a2 : off;
+        smem_red_max(t1, R);
+        smem_red_max(t1 + (smem_addr_t)(o2 * 4), R);
+        smem_red_max(t2, R);
+        smem_red_max(t2 + (smem_addr_t)(o2 * 4), R);
         if (CLS < DISC_NCLS - 1) break;                             // n <= G in every class but the last
     }
 }
 
 // the lanes whose item falls in class C append it to the warp's queue of that class; full passes are painted at once
 template <int C>
-__device__ __forceinline__ void enqueue(uint32_t *T, uint32_t *T6, uint4 *myq, int &qn, int cls, const uint4 &rec, int lane,
+__device__ __forceinline__ void enqueue(smem_addr_t T, smem_addr_t T6, uint4 *myq, int &qn, int cls, const uint4 &rec, int lane,
                                         int W, int H) {
     const unsigned m = __ballot_sync(0xFFFFFFFFu, cls == C);
     if (!m) return;
@@ -335,7 +341,7 @@ __global__ void __launch_bounds__(DISC_THREADS, 2) disc_kernel(const unsigned lo
     extern __shared__ uint32_t dk_smem[];
     uint32_t *T = dk_smem;                                  // [DT_LEVELS][DTH][DT_STRIDE]
     uint32_t *T6 = T + DT_LEVELS * DTH * DT_STRIDE;         // [DTH]
-    unsigned long long *bl_desc = (unsigned long long *)(T6 + DTH);     // [DISC_BL]  (offset is a multiple of 8 bytes)
+    unsigned long long *bl_desc = (unsigned long long *)(T6 + DTH + 64);        // [DISC_BL]  (T6: [DTH] + 64 scratch words; offset is a multiple of 8 bytes)
     uint32_t *bl_aux = (uint32_t *)(bl_desc + DISC_BL);     // [DISC_BL] row | column bucket << 16
     uint4 *queues = (uint4 *)(bl_aux + DISC_BL);            // [DISC_WARPS][DISC_NCLS][DISC_QCAP]  (16-byte aligned)
     int *ctl = (int *)(queues + DISC_WARPS * DISC_NCLS * DISC_QCAP);       // [0] listed buckets, [1] next bucket
@@ -349,6 +355,7 @@ __global__ void __launch_bounds__(DISC_THREADS, 2) disc_kernel(const unsigned lo
     for (int i = threadIdx.x; i < DT_LEVELS * DTH * DT_STRIDE + DTH; i += DISC_THREADS) T[i] = 0u;
 
     uint4 *myq = queues + warp * (DISC_NCLS * DISC_QCAP);
+    const smem_addr_t Tsh = smem_addr(T), T6sh = smem_addr(T6);
     int qn0 = 0, qn1 = 0, qn2 = 0, qn3 = 0;                 // entries waiting per class (the same in every lane)
 
     // buckets of the extended tile: rows ya..yb, column buckets ba..bb, listed DISC_BL descriptors at a time
@@ -434,10 +441,10 @@ __global__ void __launch_bounds__(DISC_THREADS, 2) disc_kernel(const unsigned lo
                         rec = make_uint4(rho, R, ((uint32_t)xcr & 0xFFFFu) | ((uint32_t)yyr << 16), (uint32_t)dyl | ((uint32_t)n << 16));
                     }
                 }
-                enqueue<0>(T, T6, myq, qn0, cls, rec, lane, W, H);
-                enqueue<1>(T, T6, myq, qn1, cls, rec, lane, W, H);
-                enqueue<2>(T, T6, myq, qn2, cls, rec, lane, W, H);
-                enqueue<3>(T, T6, myq, qn3, cls, rec, lane, W, H);
+                enqueue<0>(Tsh, T6sh, myq, qn0, cls, rec, lane, W, H);
+                enqueue<1>(Tsh, T6sh, myq, qn1, cls, rec, lane, W, H);
+                enqueue<2>(Tsh, T6sh, myq, qn2, cls, rec, lane, W, H);
+                enqueue<3>(Tsh, T6sh, myq, qn3, cls, rec, lane, W, H);
 #if BJT_DISC_PREFETCH
                 it = itn;
 #endif
@@ -446,10 +453,10 @@ __global__ void __launch_bounds__(DISC_THREADS, 2) disc_kernel(const unsigned lo
         __syncthreads();                                    // the list is rewritten by the next round
     }
     // what is left in the queues
-    if (qn0) drain_pass<0>(T, T6, myq, 0, qn0, lane, W, H);
-    if (qn1) drain_pass<1>(T, T6, myq + DISC_QCAP, 0, qn1, lane, W, H);
-    if (qn2) drain_pass<2>(T, T6, myq + 2 * DISC_QCAP, 0, qn2, lane, W, H);
-    if (qn3) drain_pass<3>(T, T6, myq + 3 * DISC_QCAP, 0, qn3, lane, W, H);
+    if (qn0) drain_pass<0>(Tsh, T6sh, myq, 0, qn0, lane, W, H);
+    if (qn1) drain_pass<1>(Tsh, T6sh, myq + DISC_QCAP, 0, qn1, lane, W, H);
+    if (qn2) drain_pass<2>(Tsh, T6sh, myq + 2 * DISC_QCAP, 0, qn2, lane, W, H);
+    if (qn3) drain_pass<3>(Tsh, T6sh, myq + 3 * DISC_QCAP, 0, qn3, lane, W, H);
     __syncthreads();
 
     // push the table down: level 6 (whole row) into the two halves of level 5, then level k into level k - 1
@@ -495,7 +502,7 @@ size_t zfront_smem_bytes(int emax) {
 #endif
     return (rows + 32 + 3 * ZF_ZB) * 4 + 8 + (size_t)ZF_ZB * 32 * 2 + 16;
 }
-constexpr size_t DISC_SMEM = (size_t)(DT_LEVELS * DTH * DT_STRIDE + DTH) * 4 + (size_t)DISC_BL * 12 +
+constexpr size_t DISC_SMEM = (size_t)(DT_LEVELS * DTH * DT_STRIDE + DTH + 64) * 4 + (size_t)DISC_BL * 12 +
                              (size_t)DISC_WARPS * DISC_NCLS * DISC_QCAP * 16 + 16;
 
 uint32_t host_isqrt(uint64_t v) {
