@@ -187,8 +187,11 @@ __device__ __forceinline__ void finish_tile_rest(FinishTile<PITCH> &T, const uin
         }
         __syncthreads();
     }
-    double sum = 0, sum2 = 0, mn = INFINITY, mx = -INFINITY;
-    long long cnt = 0;
+    // sum and sum of squares in double (StackStatistics); smallest and largest as float (the values are floats: the same
+    // numbers), NaN entries add 0.0 and are skipped by fminf / fmaxf -- no branch and no double compare per voxel
+    double sum = 0, sum2 = 0;
+    float mnf = INFINITY, mxf = -INFINITY;
+    int cnt = 0;
     if (col_in) {
 #pragma unroll 4
         for (int tz = 0; tz < FTZ; ++tz) {
@@ -201,14 +204,13 @@ __device__ __forceinline__ void finish_tile_rest(FinishTile<PITCH> &T, const uin
                 v = v * pw;
             }
             if (out) out[(size_t)(z - z_lo) * wh + (size_t)y * w + x] = v;
-            if (v == v) {   // not NaN
-                const double dv = (double)v;
-                sum += dv; sum2 += dv * dv; mn = fmin(mn, dv); mx = fmax(mx, dv); ++cnt;
-            }
+            const bool num = v == v;                                  // not NaN
+            const double dv = num ? (double)v : 0.0;
+            sum += dv; sum2 += dv * dv; mnf = fminf(mnf, v); mxf = fmaxf(mxf, v); cnt += num;
         }
     }
     const int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    block_reduce_stats(sum, sum2, mn, mx, cnt, partials + bid);
+    block_reduce_stats(sum, sum2, (double)mnf, (double)mxf, (long long)cnt, partials + bid);
 }
 
 // Output and statistics cover z in [z_lo, z_hi) of the local volume; `out` and nothing else is indexed
@@ -269,6 +271,49 @@ __global__ void __launch_bounds__(FTX *FTY, 4) finish_kernel(const uint32_t *__r
 // integer) and ballots the flag words, with "inside the image" from the coordinates instead of a marker value.
 // No global address, bounds predicate or load instruction per cell: the staging loop was half of the kernel's
 // instructions, and the kernel is bound by instruction issue.
+// The tile in place: r^2 -> 2*sqrt(r^2), and the "not zero" word of every tile row (cells outside the volume -- zeros
+// from the copy -- are flagged "not zero", as the reference's look() returns -1 there).  The 40 cells of a tile row are
+// 32 + 8: the 8 beyond column 32 are taken four rows per warp step (with a row per step they kept 8 of 32 lanes busy
+// through a second table lookup, store and ballot: 11 % of the kernel's instructions); their flags are the upper word
+// of the row's 64-bit mask.
+template <bool ALL_IN>
+__device__ __forceinline__ void finish_convert_tile(FinishTile<40> &T, const float *__restrict__ ttab, int bx, int by, int bz, int w,
+                                                    int h, int d, int tid) {
+    constexpr int HXT = 40, FXO = 4;
+    constexpr int NWARP = (FTX * FTY) / 32;
+    const int lane = tid & 31, warp = tid >> 5;
+    uint32_t *raw = reinterpret_cast<uint32_t *>(T.S);
+    uint32_t *nzw = reinterpret_cast<uint32_t *>(&T.nzrow[0][0]);      // row r = lz * HY + ly: low word nzw[2 r], high word nzw[2 r + 1]
+    for (int i = tid; i < HZ * HY * (HXT - 32); i += FTX * FTY) {      // whole warps: 8 cells x 4 rows per warp
+        const int r = i >> 3, j = i & 7;
+        bool in1 = true;
+        if (!ALL_IN) {
+            const int lz = r / HY, ly = r - lz * HY;
+            const int gy = by + ly - 2, gz = bz + lz - 2;
+            in1 = gy >= 0 && gy < h && gz >= 0 && gz < d && bx - FXO + 32 + j < w;
+        }
+        const uint32_t v1 = raw[r * HXT + 32 + j];
+        T.S[r * HXT + 32 + j] = thickness_lut(v1, ttab);
+        const unsigned b = __ballot_sync(0xFFFFFFFFu, v1 != 0u || !in1);
+        if (j == 0) nzw[2 * r + 1] = (b >> (lane & 24)) & 0xFFu;
+    }
+    const int gx0 = bx - FXO + lane;
+    const bool x0_in = gx0 >= 0 && gx0 < w;
+    for (int r = warp, lz = 0, ly = warp; r < HZ * HY; r += NWARP) {   // NWARP <= HY: (lz, ly) advance without a division
+        bool in0 = true;
+        if (!ALL_IN) {
+            const int gy = by + ly - 2, gz = bz + lz - 2;
+            in0 = x0_in && gy >= 0 && gy < h && gz >= 0 && gz < d;
+            ly += NWARP;
+            if (ly >= HY) { ly -= HY; ++lz; }
+        }
+        const uint32_t v0 = raw[r * HXT + lane];
+        T.S[r * HXT + lane] = thickness_lut(v0, ttab);
+        const unsigned nz0 = __ballot_sync(0xFFFFFFFFu, v0 != 0u || !in0);
+        if (lane == 0) nzw[2 * r] = nz0;
+    }
+}
+
 constexpr int HXT = 40, FXO = 4;
 __global__ void __launch_bounds__(FTX *FTY, 4) finish_tma_kernel(const __grid_constant__ CUtensorMap map,
                                                               const uint8_t *__restrict__ original, int w, int h, int d,
@@ -289,35 +334,10 @@ __global__ void __launch_bounds__(FTX *FTY, 4) finish_tma_kernel(const __grid_co
     __syncthreads();                                     // the barrier is initialised before anybody polls it
     if (tid < 32) tma::mbar_wait(&bar, 0);               // one warp polls, the others sleep in the block barrier
     __syncthreads();
-    constexpr int NWARP = (FTX * FTY) / 32;
-    uint32_t *raw = reinterpret_cast<uint32_t *>(T.S);
-    uint32_t *nzw = reinterpret_cast<uint32_t *>(&T.nzrow[0][0]);      // row r = lz * HY + ly: low word nzw[2 r], high word nzw[2 r + 1]
-    // The 40 cells of a tile row are 32 + 8.  The 8 beyond column 32 are taken four rows per warp step (with a row per
-    // step they kept 8 of 32 lanes busy through a second table lookup, store and ballot: 11 % of the kernel's
-    // instructions); their flags are the upper word of the row's 64-bit mask.
-    for (int i = tid; i < HZ * HY * (HXT - 32); i += FTX * FTY) {      // whole warps: 8 cells x 4 rows per warp
-        const int r = i >> 3, j = i & 7;
-        const int lz = r / HY, ly = r - lz * HY;
-        const int gy = by + ly - 2, gz = bz + lz - 2;
-        const bool in1 = gy >= 0 && gy < h && gz >= 0 && gz < d && bx - FXO + 32 + j < w;
-        const uint32_t v1 = raw[r * HXT + 32 + j];
-        T.S[r * HXT + 32 + j] = thickness_lut(v1, ttab);
-        // outside cells (zeros from the copy) are flagged "not zero", as the reference's look() returns -1 there
-        const unsigned b = __ballot_sync(0xFFFFFFFFu, v1 != 0u || !in1);
-        if (j == 0) nzw[2 * r + 1] = (b >> (lane & 24)) & 0xFFu;
-    }
-    const int gx0 = bx - FXO + lane;
-    const bool x0_in = gx0 >= 0 && gx0 < w;
-    for (int r = warp, lz = 0, ly = warp; r < HZ * HY; r += NWARP) {   // NWARP <= HY: (lz, ly) advance without a division
-        const int gy = by + ly - 2, gz = bz + lz - 2;
-        const bool in0 = x0_in && gy >= 0 && gy < h && gz >= 0 && gz < d;
-        const uint32_t v0 = raw[r * HXT + lane];
-        T.S[r * HXT + lane] = thickness_lut(v0, ttab);
-        const unsigned nz0 = __ballot_sync(0xFFFFFFFFu, v0 != 0u || !in0);
-        if (lane == 0) nzw[2 * r] = nz0;
-        ly += NWARP;
-        if (ly >= HY) { ly -= HY; ++lz; }
-    }
+    // blocks whose whole halo tile lies inside the volume (nine in ten at 1024^3) need no coordinates for the flags
+    const bool all_in = bx >= FXO && bx - FXO + HXT <= w && by >= 2 && by - 2 + HY <= h && bz >= 2 && bz - 2 + HZ <= d;
+    if (all_in) finish_convert_tile<true>(T, ttab, bx, by, bz, w, h, d, tid);
+    else finish_convert_tile<false>(T, ttab, bx, by, bz, w, h, d, tid);
     finish_tile_rest<HXT, FXO>(T, original, bx, by, bz, w, h, d, z_lo, z_hi, fgval, calibrate, pw, out, partials);
 }
 #endif
