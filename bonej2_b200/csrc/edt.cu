@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(1024, 2) edt_tile_kernel(const TIn *__restrict
 // 2 K.  A clamped candidate can only win where the result itself is >= the clamp, and the walk only ends where
 // d^2 has reached the running minimum, so a walk that ends within the pad rows is exact.  Where one does not (a
 // voxel more than ~60 line positions from every feature, or a line without features) the block redoes its tile
-// with the 32-bit walk, 16 columns at a time in the same shared memory.
+// with the 32-bit walk, half of its columns at a time in the same shared memory.
 // Pad rows and block shape, measured at 1024^3 (profiles/r02_stage_edt_pair_kernel_variants.log): 64 pad rows and
 // three blocks of 512 threads per SM (73.7 KB each) -- three tiles in flight per SM hide the strided staging loads of
 // the z pass better than two blocks of 1024 with 96 pad rows (y 1.70 / 2.22 -> 1.51 / 2.08 ms, z 2.27 -> 2.08 ms).
@@ -548,7 +548,7 @@ template <typename TIn, bool WANT_MAX, int K, int TW>
 __global__ void __launch_bounds__(BJT_EDT16_THREADS, BJT_EDT16_BLOCKS) edt_tile16_kernel(const TIn *__restrict__ in, uint32_t *__restrict__ out, int groups,
                                                            long long outer, long long stride, int L, uint32_t n0,
                                                            uint32_t *__restrict__ maxval) {
-    extern __shared__ uint32_t sm_raw[];                 // [EDT16_PAD + L + EDT16_PAD][TW] pairs; the redo: [EDT_PAD + L + EDT_PAD][16] u32
+    extern __shared__ uint32_t sm_raw[];                 // [EDT16_PAD + L + EDT16_PAD][TW] pairs; the redo: [EDT_PAD + L + EDT_PAD][TW] u32
     __shared__ int s_sat;
     constexpr int GPW = 32 / TW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -576,14 +576,14 @@ __global__ void __launch_bounds__(BJT_EDT16_THREADS, BJT_EDT16_BLOCKS) edt_tile1
     uint32_t tmax = edt16_walk<WANT_MAX, K, TW>(sm, out, base, stride, L, n0, &sat);
     if (sat) s_sat = 1;
     __syncthreads();
-    if (s_sat) {                                         // rare: the whole tile again, exact in 32 bits, 16 columns at a time
+    if (s_sat) {                                         // rare: the whole tile again, exact in 32 bits, TW columns at a time
         tmax = 0;
-        uint32_t *sm32 = sm_raw + EDT_PAD * 16;
-        for (int half = 0; half < TW / 8; ++half) {
-            for (int i = threadIdx.x; i < EDT_PAD * 16; i += blockDim.x) { sm32[-EDT_PAD * 16 + i] = 0x3FFFFFFFu; sm32[L * 16 + i] = 0x3FFFFFFFu; }
-            edt_stage_tile<TIn, 16>(in, base + half * 16, stride, L, n0, sm32);
+        uint32_t *sm32 = sm_raw + EDT_PAD * TW;              // [EDT_PAD + L + EDT_PAD][TW] u32: as many bytes as the pairs of 2 TW columns
+        for (int half = 0; half < 2; ++half) {
+            for (int i = threadIdx.x; i < EDT_PAD * TW; i += blockDim.x) { sm32[-EDT_PAD * TW + i] = 0x3FFFFFFFu; sm32[L * TW + i] = 0x3FFFFFFFu; }
+            edt_stage_tile<TIn, TW>(in, base + half * TW, stride, L, n0, sm32);
             __syncthreads();
-            tmax = max(tmax, edt_tile_walk<16, WANT_MAX>(sm32, out, base + half * 16, stride, L, n0));
+            tmax = max(tmax, edt_tile_walk<TW, WANT_MAX>(sm32, out, base + half * TW, stride, L, n0));
             __syncthreads();
         }
     }
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(BJT_EDT16_THREADS, BJT_EDT16_BLOCKS) edt_tile1
 template <typename TIn, bool WANT_MAX, int TW>
 static bool launch_edt_tile16_tw(const TIn *in, uint32_t *out, int w, long long nouter, long long outer, long long stride, int L,
                                  uint32_t n0, uint32_t *maxval, cudaStream_t s) {
-    const size_t smem = std::max((size_t)(L + 2 * EDT16_PAD) * TW * 4, (size_t)(L + 2 * EDT_PAD) * 16 * 4);   // pairs; the redo's u32 tile
+    const size_t smem = (size_t)(L + 2 * std::max(EDT16_PAD, EDT_PAD)) * TW * 4;        // pairs of 2 TW columns; the redo's u32 tile of TW columns
     if (w % (2 * TW) != 0 || smem > (size_t)(227 * 1024 / BJT_EDT16_BLOCKS - 1024) || (uintptr_t)in % 8 != 0 || (uintptr_t)out % 8 != 0) return false;
     const int groups = w / (2 * TW);
     cudaFuncSetAttribute(edt_tile16_kernel<TIn, WANT_MAX, BJT_EDT16_K, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
