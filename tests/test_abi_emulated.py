@@ -70,6 +70,18 @@ def test_both_maps_in_one_call(emu_ctx, oracle):
         G._cmp_stats(st, o["stats"])
 
 
+@pytest.mark.parametrize("depth", [75, 33])
+def test_both_maps_streamed_in_chunks(emu_ctx, oracle, depth):
+    """host-buffer calls paint, finish and send the map home in chunks of planes that halve towards the end of a run
+    (75 planes: 64 + 11; 33: 32 + 1 -- a one-plane last chunk, whose cleanup reads planes of the chunk before)"""
+    vol = shapes.random_blobs((depth, 9, 32), 4)
+    (m_th, s_th, _), (m_sp, s_sp, _) = emu_ctx.thickness_both(vol, mask=True)
+    for inverse, m, st in ((False, m_th, s_th), (True, m_sp, s_sp)):
+        o = oracle.process_image(vol, inverse=inverse, mask=True)
+        G._cmp_map(m, o["map"])
+        G._cmp_stats(st, o["stats"])
+
+
 def test_thickness_wrapper_command(emu_ctx):
     """the C++ mirror of the ThicknessWrapper command (tests/test_thickness_wrapper.py, the tests that produce maps)"""
     from bonej2_b200 import wrapper

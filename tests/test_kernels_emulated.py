@@ -67,6 +67,16 @@ def test_edt_pair_kernel_tile_widths(oracle, guard_behind, shape):
         assert np.array_equal(got, want) and mx == int(want.max())
 
 
+def test_edt_pair_kernel_redo_of_a_16_column_tile(oracle, guard_behind):
+    """a width of 16 with one background voxel: a 16-column pair tile (what lines of 2048 take as well) whose walks
+    leave the pad rows, redone 8 columns at a time in 32 bits"""
+    vol = np.full((1, 150, 16), 255, np.uint8)
+    vol[0, 7, 5] = 0
+    _, want = oracle.edt(vol)
+    got, mx = emu.edt_sq(vol)
+    assert np.array_equal(got, want) and mx == int(want.max())
+
+
 def test_edt_pair_kernel_redoes_only_what_saturates(oracle, guard_behind):
     """tiles of short walks beside tiles whose walks leave the pad rows (the block redoes the tile in 32 bits), values
     above the 16-bit clamp (55000) included; and a tile in which only a few columns saturate"""
